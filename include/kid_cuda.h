@@ -1,0 +1,190 @@
+/*
+ * kid_cuda.h — C ABI of libkid_cuda.so, the B200 (sm_100a) implementation of
+ * KinematicDriver.jl's hot path: the ODE right-hand side + SSPRK33 step loop of
+ * K1DModel, K2DModel and BoxModel.
+ *
+ * The reference has no FFI seam: its drivers hand `rhs!(dY, Y, aux, t)` to
+ * OrdinaryDiffEq (`ODE.solve(problem, ODE.SSPRK33(); dt, saveat, callback)`).
+ * The entry points below are what a Julia `ccall` shim binds in place of that
+ * hand-off.  Each comment cites the reference interface it replaces
+ * (paths relative to the reference checkout).
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on error; the message is
+ *    available from kid_last_error() (thread-local).
+ *  - `void*` host buffers hold FLOAT_TYPE elements (float if float_type ==
+ *    KID_F32, double if KID_F64); they are borrowed for the duration of the
+ *    call only.  No torch / CUDA types appear in any signature.
+ *  - host state layout is `[column][variable][level]`, level fastest: exactly
+ *    `parent(Y)` of the reference's ClimaCore column FieldVector, column after
+ *    column (src/Common/ode_utils.jl:23-54 gives the variable order).
+ *  - a handle is not thread-safe; distinct handles may be used concurrently
+ *    (the reference's calibration loop runs one simulation per thread:
+ *    calibration/OptimizationUtils.jl:206).
+ *  - there is NO CPU fallback: every compute entry point fails if no CUDA
+ *    device is present.
+ */
+#ifndef KID_CUDA_H
+#define KID_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "kid_params.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KID_ABI_VERSION 1
+
+/* src/{BoxModel,K1DModel,K2DModel}/ode_utils.jl: which make_rhs_function */
+enum kid_model {
+    KID_MODEL_BOX = 0,         /* src/BoxModel/ode_utils.jl:10-22 */
+    KID_MODEL_K1D = 1,         /* src/K1DModel/ode_utils.jl:29-49 */
+    KID_MODEL_K1D_COL_SED = 2, /* src/K1DModel/ode_utils.jl:56-73 */
+    KID_MODEL_K2D = 3          /* src/K2DModel/ode_utils.jl:36-54 */
+};
+/* src/Common/equation_types.jl:31-61 / helper_functions.jl:4-93 */
+enum kid_moisture { KID_MOIST_EQ = 0, KID_MOIST_NONEQ = 1 };
+enum kid_precip { KID_PRECIP_NONE = 0, KID_PRECIP_0M = 1, KID_PRECIP_1M = 2, KID_PRECIP_2M = 3 };
+enum kid_rain_formation {
+    KID_RF_CLIMA_1M = 0, KID_RF_KK2000 = 1, KID_RF_B1994 = 2, KID_RF_TC1980 = 3,
+    KID_RF_LD2004 = 4, KID_RF_VARTIMESCALE = 5,       /* Precipitation1M */
+    KID_RF_SB2006 = 6, KID_RF_SB2006NL = 7            /* Precipitation2M */
+};
+enum kid_sedimentation { KID_SED_CLIMA_1M = 0, KID_SED_SB2006 = 1, KID_SED_CHEN2022 = 2 };
+enum kid_float { KID_F32 = 0, KID_F64 = 1 }; /* FLOAT_TYPE (parse_commandline.jl:10-14) */
+
+/* per-column scalars that the reference keeps in kid_params / common_params /
+ * aux and that differ between ensemble members (calibration/KiDUtils.jl:45-81) */
+enum kid_column_scalar {
+    KID_COL_W1 = 0,            /* kid_params.w1   (K1DModel/tendency.jl:243) */
+    KID_COL_Q_SURF = 1,        /* aux.q_surf      (K1DModel/ode_utils.jl:96) */
+    KID_COL_PRESCRIBED_ND = 2  /* common_params.prescribed_Nd */
+};
+
+/* aux fields readable by kid_get_aux: everything simulation_output() reads
+ * (src/Common/netcdf_io.jl:144-170; schema src/Common/ode_utils.jl:110-175) */
+enum kid_aux_field {
+    KID_AUX_RHO = 0, KID_AUX_RHO_DRY, KID_AUX_P, KID_AUX_T, KID_AUX_THETA_LIQ_ICE, KID_AUX_THETA_DRY,
+    KID_AUX_Q_TOT, KID_AUX_Q_LIQ, KID_AUX_Q_ICE, KID_AUX_Q_RAI, KID_AUX_Q_SNO,
+    KID_AUX_N_LIQ, KID_AUX_N_RAI, KID_AUX_N_AER,
+    KID_AUX_TERM_VEL_RAI, KID_AUX_TERM_VEL_SNO, KID_AUX_TERM_VEL_N_RAI,
+    KID_AUX_SRC_Q_TOT, KID_AUX_SRC_Q_LIQ, KID_AUX_SRC_Q_ICE, KID_AUX_SRC_Q_RAI, KID_AUX_SRC_Q_SNO,
+    KID_AUX_SRC_N_AER, KID_AUX_SRC_N_LIQ, KID_AUX_SRC_N_RAI,
+    KID_AUX_ACT_N_AER, KID_AUX_ACT_N_LIQ,
+    KID_AUX_CLOUD_SRC_Q_LIQ, KID_AUX_CLOUD_SRC_Q_ICE,
+    KID_NAUX
+};
+
+typedef struct kid_config {
+    int32_t abi_version;     /* = KID_ABI_VERSION */
+    int32_t params_version;  /* = KID_PARAMS_VERSION */
+    int32_t model;           /* enum kid_model */
+    int32_t moisture;        /* enum kid_moisture */
+    int32_t precip;          /* enum kid_precip */
+    int32_t rain_formation;  /* enum kid_rain_formation */
+    int32_t sedimentation;   /* enum kid_sedimentation */
+    int32_t float_type;      /* enum kid_float */
+    int32_t nz;              /* levels per column (n_elem; 1 for BoxModel) */
+    int32_t nc;              /* columns owned by this handle (K2D: helem_local*(npoly+1)) */
+    int32_t helem;           /* K2D: horizontal elements owned by this handle */
+    int32_t npoly;           /* K2D: polynomial degree (Nq = npoly+1 GLL nodes) */
+    int32_t helem_global;    /* K2D: elements of the whole periodic domain */
+    int32_t helem_offset;    /* K2D: global index of this handle's first element */
+    /* CommonParameters / kid_params switches (src/Common/parameters.jl:18-41) */
+    int32_t precip_sources;
+    int32_t precip_sinks;
+    int32_t open_system_activation;
+    int32_t local_activation;
+    int32_t qtot_flux_correction;
+    int32_t device;          /* CUDA device ordinal */
+    int32_t reserved[8];
+    double z_min, z_max;     /* make_function_space (K1DModel/ode_utils.jl:9-21) */
+    double dt;               /* TimeStepping.dt (src/Common/ode_utils.jl:12-16) */
+    double domain_width;     /* K2D aux.domain_width  */
+    double domain_height;    /* K2D aux.domain_height */
+} kid_config_t;
+
+typedef struct kid_handle kid_handle_t;
+
+/* number of prognostic variables of a (moisture, precip) pair and their order:
+ * initialise_state, src/Common/ode_utils.jl:23-54.  Returns -1 if unsupported. */
+int kid_nvars(int moisture, int precip);
+/* writes the NUL-separated variable names ("rhoq_tot\0rhoq_liq\0...") */
+int kid_var_names(int moisture, int precip, char* buf, size_t buflen);
+
+/* replaces: aux = initialise_aux(...) + Y = initialise_state(...) allocation
+ * (src/Common/ode_utils.jl:61-175, K1DModel/ode_utils.jl:80-117) */
+int kid_create(const kid_config_t* cfg, kid_handle_t** out);
+void kid_destroy(kid_handle_t* h);
+
+/* replaces: the parameter structs captured in `aux` and in the style types.
+ * `params` is nsets x KID_NPARAMS doubles.  nsets == 1: one set for every
+ * column.  nsets > 1: column c uses set column_to_set[c] (calibration
+ * ensembles: calibration/KiDUtils.jl:378-382 update_parameters!). */
+int kid_set_params(kid_handle_t* h, const double* params, int32_t nparams, int32_t nsets,
+                   const int32_t* column_to_set);
+
+/* replaces: aux.thermo_variables.{ρ_dry,T} from the initial profile (time
+ * invariant: src/Common/tendency.jl:34-135).  per_column == 0: one profile of
+ * nz values shared by all columns; else nc x nz values, level fastest. */
+int kid_set_profiles(kid_handle_t* h, const void* rho_dry, const void* T, int32_t per_column);
+
+/* per-column scalars; values == NULL resets to the value in the param table */
+int kid_set_column_scalar(kid_handle_t* h, int32_t which, const void* values);
+
+/* replaces: Y = initialise_state(...) / reading integrator.u.
+ * kid_set_state also snapshots the aux microphysics fields that the reference
+ * initialises from the initial profile and never refreshes on some paths
+ * (aux N_aer in BoxModel / col_sed; previous-call q_rai,N_liq,N_rai in K2D). */
+int kid_set_state(kid_handle_t* h, const void* Y);
+int kid_get_state(kid_handle_t* h, void* Y);
+
+/* replaces: ODE.solve!(integrator) between two save/callback times: advances
+ * the device-resident state by nsteps SSPRK33 steps of size dt starting at
+ * time t0 (3 rhs evaluations per step).  Asynchronous w.r.t. the host. */
+int kid_step(kid_handle_t* h, double t0, int32_t nsteps);
+/* how many model steps one kernel launch fuses (0 = library default) */
+int kid_set_steps_per_launch(kid_handle_t* h, int32_t n);
+
+/* replaces: one rhs!(dY, Y, aux, t) call (testing / parity of a single
+ * evaluation).  dY_out has the layout of kid_get_state. */
+int kid_rhs(kid_handle_t* h, double t, void* dY_out);
+
+/* replaces: reading aux.* in simulation_output (netcdf_io.jl:144-170); the
+ * field is evaluated from the current state at time t (what the FSAL rhs call
+ * leaves in aux).  out: nc x nz values, level fastest. */
+int kid_get_aux(kid_handle_t* h, double t, int32_t field, void* out);
+/* replaces: maximum(aux.microph_variables.q_liq) (netcdf_io.jl:166) */
+int kid_reduce_max(kid_handle_t* h, double t, int32_t field, double* out);
+
+/* K2D domain decomposition: the caller (one process per GPU) exchanges the
+ * packed edge-node tendencies of its first/last element with its periodic
+ * neighbours between the two halves of every SSPRK33 stage.
+ *   kid_k2d_stage_begin: rhs for stage s (0,1,2) of the step starting at t0,
+ *       leaves the un-DSS'd tendencies on the device and packs the edges.
+ *   kid_k2d_edge_buffers: device pointers of the send (left,right) and recv
+ *       (left,right) buffers, each edge_count FLOAT_TYPE elements.
+ *   kid_k2d_stage_end: DSS average with the received edges + stage update.
+ * kid_step() on a K2D handle with helem == helem_global does all of this
+ * internally (single GPU, periodic wrap inside the kernel). */
+int kid_k2d_stage_begin(kid_handle_t* h, double t0, int32_t stage);
+int kid_k2d_edge_buffers(kid_handle_t* h, void** send_left, void** send_right, void** recv_left,
+                         void** recv_right, size_t* edge_count);
+int kid_k2d_stage_end(kid_handle_t* h, int32_t stage);
+
+/* plumbing */
+int kid_synchronize(kid_handle_t* h);
+void* kid_stream(kid_handle_t* h);            /* the cudaStream_t kernels are launched on */
+void* kid_state_device_ptr(kid_handle_t* h);  /* device SoA state, [var][level][column] */
+int64_t kid_launch_count(kid_handle_t* h);    /* kernels launched by this handle so far */
+const char* kid_last_error(void);
+const char* kid_version(void);
+int kid_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KID_CUDA_H */

@@ -1,0 +1,234 @@
+"""ctypes binding of libkid_cuda.so (include/kid_cuda.h) — the only way the host side reaches the GPU.
+
+There is deliberately no fallback: if the shared library is missing or no CUDA device is
+visible, every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+KID_ABI_VERSION = 1
+KID_PARAMS_VERSION = 1
+
+# enum kid_model
+MODEL_BOX, MODEL_K1D, MODEL_K1D_COL_SED, MODEL_K2D = 0, 1, 2, 3
+# enum kid_float
+F32, F64 = 0, 1
+# enum kid_column_scalar
+COL_W1, COL_Q_SURF, COL_PRESCRIBED_ND = 0, 1, 2
+
+AUX_FIELDS = [
+    "ρ", "ρ_dry", "p", "T", "θ_liq_ice", "θ_dry",
+    "q_tot", "q_liq", "q_ice", "q_rai", "q_sno", "N_liq", "N_rai", "N_aer",
+    "term_vel_rai", "term_vel_sno", "term_vel_N_rai",
+    "precip_sources.q_tot", "precip_sources.q_liq", "precip_sources.q_ice", "precip_sources.q_rai",
+    "precip_sources.q_sno", "precip_sources.N_aer", "precip_sources.N_liq", "precip_sources.N_rai",
+    "activation_sources.N_aer", "activation_sources.N_liq",
+    "cloud_sources.q_liq", "cloud_sources.q_ice",
+]
+AUX_ID = {n: i for i, n in enumerate(AUX_FIELDS)}
+
+
+class KidConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("params_version", C.c_int32),
+        ("model", C.c_int32), ("moisture", C.c_int32), ("precip", C.c_int32),
+        ("rain_formation", C.c_int32), ("sedimentation", C.c_int32), ("float_type", C.c_int32),
+        ("nz", C.c_int32), ("nc", C.c_int32), ("helem", C.c_int32), ("npoly", C.c_int32),
+        ("helem_global", C.c_int32), ("helem_offset", C.c_int32),
+        ("precip_sources", C.c_int32), ("precip_sinks", C.c_int32),
+        ("open_system_activation", C.c_int32), ("local_activation", C.c_int32),
+        ("qtot_flux_correction", C.c_int32), ("device", C.c_int32),
+        ("reserved", C.c_int32 * 8),
+        ("z_min", C.c_double), ("z_max", C.c_double), ("dt", C.c_double),
+        ("domain_width", C.c_double), ("domain_height", C.c_double),
+    ]
+
+
+def make_config(**kw) -> KidConfig:
+    cfg = KidConfig()
+    cfg.abi_version, cfg.params_version = KID_ABI_VERSION, KID_PARAMS_VERSION
+    cfg.helem = cfg.helem_global = 0
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def dtype_of(float_type: int):
+    return np.float32 if float_type == F32 else np.float64
+
+
+_LIB = None
+LIB_PATH = Path(__file__).resolve().parents[1] / "csrc" / "libkid_cuda.so"
+
+
+class KidCudaError(RuntimeError):
+    pass
+
+
+def load_library(path: os.PathLike | None = None) -> C.CDLL:
+    """dlopen libkid_cuda.so and declare every symbol of include/kid_cuda.h."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    p = Path(path) if path else LIB_PATH
+    if not p.exists():
+        raise KidCudaError(f"{p} not found: build it with `python __graft_entry__.py build` "
+                           "(there is no CPU fallback for the hot path)")
+    lib = C.CDLL(str(p))
+    H = C.c_void_p
+    sig = {
+        "kid_nvars": (C.c_int, [C.c_int, C.c_int]),
+        "kid_var_names": (C.c_int, [C.c_int, C.c_int, C.c_char_p, C.c_size_t]),
+        "kid_create": (C.c_int, [C.POINTER(KidConfig), C.POINTER(H)]),
+        "kid_destroy": (None, [H]),
+        "kid_set_params": (C.c_int, [H, C.POINTER(C.c_double), C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
+        "kid_set_profiles": (C.c_int, [H, C.c_void_p, C.c_void_p, C.c_int32]),
+        "kid_set_column_scalar": (C.c_int, [H, C.c_int32, C.c_void_p]),
+        "kid_set_state": (C.c_int, [H, C.c_void_p]),
+        "kid_get_state": (C.c_int, [H, C.c_void_p]),
+        "kid_step": (C.c_int, [H, C.c_double, C.c_int32]),
+        "kid_set_steps_per_launch": (C.c_int, [H, C.c_int32]),
+        "kid_rhs": (C.c_int, [H, C.c_double, C.c_void_p]),
+        "kid_get_aux": (C.c_int, [H, C.c_double, C.c_int32, C.c_void_p]),
+        "kid_reduce_max": (C.c_int, [H, C.c_double, C.c_int32, C.POINTER(C.c_double)]),
+        "kid_k2d_stage_begin": (C.c_int, [H, C.c_double, C.c_int32]),
+        "kid_k2d_edge_buffers": (C.c_int, [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+        "kid_k2d_stage_end": (C.c_int, [H, C.c_int32]),
+        "kid_synchronize": (C.c_int, [H]),
+        "kid_stream": (C.c_void_p, [H]),
+        "kid_state_device_ptr": (C.c_void_p, [H]),
+        "kid_launch_count": (C.c_int64, [H]),
+        "kid_last_error": (C.c_char_p, []),
+        "kid_version": (C.c_char_p, []),
+        "kid_device_count": (C.c_int, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype, fn.argtypes = res, args
+    lib._kid_symbols = tuple(sig)
+    if path is None:
+        _LIB = lib
+    return lib
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Handle:
+    """Thin OO wrapper of a kid_handle_t*; array arguments are numpy arrays of FLOAT_TYPE."""
+
+    def __init__(self, cfg: KidConfig, lib: C.CDLL | None = None):
+        self.lib = lib or load_library()
+        self.cfg = cfg
+        self.dtype = dtype_of(cfg.float_type)
+        self.nvars = self.lib.kid_nvars(cfg.moisture, cfg.precip)
+        if self.nvars < 0:
+            raise KidCudaError("unsupported (moisture, precip) pair")
+        self._h = C.c_void_p()
+        self._check(self.lib.kid_create(C.byref(cfg), C.byref(self._h)))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise KidCudaError(self.lib.kid_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.kid_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- inputs
+    def set_params(self, table: np.ndarray, column_to_set: np.ndarray | None = None):
+        t = np.ascontiguousarray(table, dtype=np.float64)
+        nsets = 1 if t.ndim == 1 else t.shape[0]
+        nparams = t.shape[-1]
+        idx = None
+        if column_to_set is not None:
+            idx = np.ascontiguousarray(column_to_set, dtype=np.int32)
+        self._check(self.lib.kid_set_params(self._h, t.ctypes.data_as(C.POINTER(C.c_double)), nparams, nsets,
+                                            idx.ctypes.data_as(C.POINTER(C.c_int32)) if idx is not None else None))
+
+    def set_profiles(self, ρ_dry: np.ndarray, T: np.ndarray):
+        r = np.ascontiguousarray(ρ_dry, dtype=self.dtype)
+        t = np.ascontiguousarray(T, dtype=self.dtype)
+        per_column = int(r.ndim == 2)
+        self._check(self.lib.kid_set_profiles(self._h, _ptr(r), _ptr(t), per_column))
+
+    def set_column_scalar(self, which: int, values: np.ndarray | None):
+        if values is None:
+            self._check(self.lib.kid_set_column_scalar(self._h, which, None))
+            return
+        v = np.ascontiguousarray(np.broadcast_to(np.asarray(values, dtype=self.dtype), (self.cfg.nc,)))
+        self._check(self.lib.kid_set_column_scalar(self._h, which, _ptr(v)))
+
+    def set_state(self, Y: np.ndarray):
+        y = np.ascontiguousarray(Y, dtype=self.dtype)
+        assert y.size == self.cfg.nc * self.nvars * self.cfg.nz, (y.shape, self.cfg.nc, self.nvars, self.cfg.nz)
+        self._check(self.lib.kid_set_state(self._h, _ptr(y)))
+
+    # ---- outputs
+    def get_state(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.cfg.nc, self.nvars, self.cfg.nz), dtype=self.dtype)
+        self._check(self.lib.kid_get_state(self._h, _ptr(out)))
+        return out
+
+    def rhs(self, t: float) -> np.ndarray:
+        out = np.empty((self.cfg.nc, self.nvars, self.cfg.nz), dtype=self.dtype)
+        self._check(self.lib.kid_rhs(self._h, float(t), _ptr(out)))
+        return out
+
+    def get_aux(self, t: float, field) -> np.ndarray:
+        fid = AUX_ID[field] if isinstance(field, str) else int(field)
+        out = np.empty((self.cfg.nc, self.cfg.nz), dtype=self.dtype)
+        self._check(self.lib.kid_get_aux(self._h, float(t), fid, _ptr(out)))
+        return out
+
+    def reduce_max(self, t: float, field) -> float:
+        fid = AUX_ID[field] if isinstance(field, str) else int(field)
+        v = C.c_double()
+        self._check(self.lib.kid_reduce_max(self._h, float(t), fid, C.byref(v)))
+        return v.value
+
+    # ---- stepping
+    def step(self, t0: float, nsteps: int):
+        self._check(self.lib.kid_step(self._h, float(t0), int(nsteps)))
+
+    def set_steps_per_launch(self, n: int):
+        self._check(self.lib.kid_set_steps_per_launch(self._h, int(n)))
+
+    def synchronize(self):
+        self._check(self.lib.kid_synchronize(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.kid_stream(self._h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.kid_launch_count(self._h))
+
+    # ---- K2D split-stage API (domain decomposition)
+    def k2d_stage_begin(self, t0: float, stage: int):
+        self._check(self.lib.kid_k2d_stage_begin(self._h, float(t0), int(stage)))
+
+    def k2d_stage_end(self, stage: int):
+        self._check(self.lib.kid_k2d_stage_end(self._h, int(stage)))
+
+    def k2d_edge_buffers(self):
+        p = [C.c_void_p() for _ in range(4)]
+        n = C.c_size_t()
+        self._check(self.lib.kid_k2d_edge_buffers(self._h, *[C.byref(x) for x in p], C.byref(n)))
+        return [x.value for x in p], n.value

@@ -1,0 +1,255 @@
+"""Model assembly: the host-side mirror of src/{K1DModel,K2DModel,BoxModel}/ode_utils.jl and
+src/Common/ode_utils.jl, on top of libkid_cuda.so.
+
+A `Case` is everything the reference hands to `ODE.ODEProblem(ode_rhs!, Y, tspan, aux)`:
+configuration (styles, grid, switches), the flattened parameter structs, the time-invariant
+profiles (aux.thermo_variables.{ρ_dry,T}), per-column scalars and the initial state Y.
+`apply_case` uploads a Case into any backend with the kid_b200.lib.Handle method surface
+(the CUDA library, or — in tests only — the CPU oracle).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import equation_types as ET
+from . import initial_condition as IC
+from . import parameters as PR
+from .lib import (COL_PRESCRIBED_ND, COL_Q_SURF, COL_W1, F32, F64, MODEL_BOX, MODEL_K1D, MODEL_K1D_COL_SED,
+                  MODEL_K2D, Handle, KidConfig, make_config)
+
+
+@dataclass
+class TimeStepping:
+    """src/Common/ode_utils.jl:12-16"""
+    dt: float
+    dt_io: float
+    t_max: float
+
+
+@dataclass
+class Case:
+    cfg: KidConfig
+    params: np.ndarray            # KID_NPARAMS table (or nsets x KID_NPARAMS)
+    ρ_dry: np.ndarray             # [nz] or [nc, nz]
+    T: np.ndarray
+    Y0: np.ndarray                # [nc, nvars, nz]
+    var_names: tuple
+    col_scalars: dict = field(default_factory=dict)   # which -> [nc] values
+    column_to_set: np.ndarray | None = None
+    z_centers: np.ndarray | None = None
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def dtype(self):
+        return np.float32 if self.cfg.float_type == F32 else np.float64
+
+
+def float_enum(FT) -> int:
+    return F32 if np.dtype(FT) == np.float32 else F64
+
+
+def initialise_state(moisture, precip, ip: dict) -> np.ndarray:
+    """src/Common/ode_utils.jl:23-54 — Y as a [nvars, nz] array in the reference's field order."""
+    names = ET.state_variable_names(moisture, precip)
+    return np.stack([np.asarray(ip[n]) for n in names], axis=0)
+
+
+def make_function_space(FT, z_min, z_max, n_elem):
+    """src/K1DModel/ode_utils.jl:9-21 — returns (center z, face z) of the uniform column."""
+    faces = np.linspace(float(z_min), float(z_max), int(n_elem) + 1)
+    centers = 0.5 * (faces[:-1] + faces[1:])
+    return centers.astype(FT), faces.astype(FT)
+
+
+_K1D_DEFAULTS = dict(
+    moisture_choice="EquilibriumMoisture", precipitation_choice="Precipitation1M",
+    rain_formation_scheme_choice=None, sedimentation_scheme_choice=None,
+    prescribed_Nd=1e8, open_system_activation=False, local_activation=False,
+    precip_sources=True, precip_sinks=True, qtot_flux_correction=False,
+    z_min=0.0, z_max=2000.0, n_elem=128, dt=1.0, dt_output=30.0, t_ini=0.0, t_end=3600.0,
+    w1=2.0, t1=600.0, p0=100000.0, r_dry=0.04e-6, std_dry=1.4, kappa=0.9,
+    z_0=0.0, z_1=740.0, z_2=3260.0, rv_0=0.015, rv_1=0.0138, rv_2=0.0024,
+    tht_0=297.9, tht_1=297.9, tht_2=312.66, init_sounding="ShipwayHill2012", velocity="ShipwayHill2012",
+)
+
+
+def kid_options(**overrides) -> dict:
+    """Defaults of test/experiments/KiD_driver/parse_commandline.jl:10-174."""
+    unknown = set(overrides) - set(_K1D_DEFAULTS) - {"FLOAT_TYPE", "toml_overrides"}
+    if unknown:
+        raise KeyError(f"unknown KiD option(s): {sorted(unknown)}")
+    o = dict(_K1D_DEFAULTS)
+    o.update(overrides)
+    return o
+
+
+def _toml_from_opts(FT, opts):
+    td = PR.override_toml_dict(
+        FT=FT, w1=opts["w1"], t1=opts["t1"], p0=opts["p0"], z_0=opts["z_0"], z_1=opts["z_1"], z_2=opts["z_2"],
+        rv_0=opts["rv_0"], rv_1=opts["rv_1"], rv_2=opts["rv_2"], tht_0=opts["tht_0"], tht_1=opts["tht_1"],
+        tht_2=opts["tht_2"], precip_sources=int(opts["precip_sources"]), precip_sinks=int(opts["precip_sinks"]),
+        qtot_flux_correction=int(opts["qtot_flux_correction"]), prescribed_Nd=opts["prescribed_Nd"],
+        open_system_activation=int(opts["open_system_activation"]), local_activation=int(opts["local_activation"]),
+        r_dry=opts["r_dry"], std_dry=opts["std_dry"], kappa=opts["kappa"])
+    if opts.get("rain_formation_scheme_choice") == "SB2006NL":  # run_KiD_simulation.jl:65-69
+        td["SB2006_raindrops_terminal_velocity_coeff_aR"] = 6.0
+        td["SB2006_raindrops_terminal_velocity_coeff_bR"] = 9.76
+        td["SB2006_raindrops_terminal_velocity_coeff_cR"] = 1490.0
+    for k, v in (opts.get("toml_overrides") or {}).items():
+        if k not in td:
+            raise KeyError(f"unknown ClimaParams name {k}")
+        td[k] = v
+    return td
+
+
+def k1d_case(FT=np.float64, nc: int = 1, model: int = MODEL_K1D, device: int = 0, **options) -> Case:
+    """Everything run_KiD_simulation.jl:13-157 builds before ODE.init, for nc identical columns."""
+    opts = kid_options(**options)
+    if opts["z_2"] < opts["z_max"]:
+        raise ValueError("z_max cannot be higher than z_2")
+    if opts["velocity"] != "ShipwayHill2012" or opts["init_sounding"] != "ShipwayHill2012":
+        raise NotImplementedError("only the ShipwayHill2012 velocity/sounding is on the device hot path")
+    FT = np.dtype(FT).type
+    td = _toml_from_opts(FT, opts)
+    common_params = PR.create_common_parameters(td)
+    kid_params = PR.create_kid_parameters(td)
+    thermo_params = PR.create_thermodynamics_parameters(td)
+    moisture = ET.get_moisture_type(opts["moisture_choice"], td)
+    precip = ET.get_precipitation_type(opts["precipitation_choice"], td,
+                                       rain_formation_choice=opts["rain_formation_scheme_choice"],
+                                       sedimentation_choice=opts["sedimentation_scheme_choice"])
+    nz = int(opts["n_elem"])
+    zc, zf = make_function_space(FT, opts["z_min"], opts["z_max"], nz)
+    ρ_profile = IC.ρ_ivp(FT, kid_params, thermo_params, opts["init_sounding"])
+    ip = IC.initial_condition_1d(FT, common_params, kid_params, thermo_params, ρ_profile, zc, opts["init_sounding"])
+    q_surf = IC.init_profile(FT, kid_params, thermo_params, FT(0), opts["init_sounding"])["qv"]
+    Y_col = initialise_state(moisture, precip, ip).astype(FT)
+    cfg = make_config(
+        model=model, moisture=moisture.kid_enum, precip=precip.kid_enum, rain_formation=precip.rain_formation,
+        sedimentation=precip.sedimentation, float_type=float_enum(FT), nz=nz, nc=nc,
+        precip_sources=int(common_params.precip_sources), precip_sinks=int(common_params.precip_sinks),
+        open_system_activation=int(common_params.open_system_activation),
+        local_activation=int(common_params.local_activation),
+        qtot_flux_correction=int(kid_params.qtot_flux_correction), device=device,
+        z_min=float(opts["z_min"]), z_max=float(opts["z_max"]), dt=float(opts["dt"]))
+    table = PR.flatten_params(td, precip.rain_formation)
+    Y0 = np.broadcast_to(Y_col, (nc,) + Y_col.shape).copy()
+    return Case(cfg=cfg, params=table, ρ_dry=ip["ρ_dry"].astype(FT), T=ip["T"].astype(FT), Y0=Y0,
+                var_names=ET.state_variable_names(moisture, precip),
+                col_scalars={COL_Q_SURF: np.full(nc, q_surf, dtype=FT)}, z_centers=zc,
+                meta=dict(opts=opts, toml=td, moisture=moisture, precip=precip, ip=ip,
+                          TS=TimeStepping(opts["dt"], opts["dt_output"], opts["t_end"])))
+
+
+def box_case(FT=np.float64, nc: int = 1, device: int = 0, precipitation_choice="Precipitation2M",
+             rain_formation_choice="SB2006", qt=1e-3, Nd=1e8, k=2.0, rhod=1.22, dt=1.0, dt_output=30.0,
+             t_ini=0.0, t_end=3600.0, microphys_params=None, precip_sinks=0) -> Case:
+    """run_box_simulation.jl:12-81 for nc boxes.  qt, Nd may be arrays of length nc (ensemble)."""
+    FT = np.dtype(FT).type
+    qt_a = np.broadcast_to(np.asarray(qt, dtype=np.float64), (nc,))
+    Nd_a = np.broadcast_to(np.asarray(Nd, dtype=np.float64), (nc,))
+    td = PR.override_toml_dict(FT=FT, precip_sources=1, precip_sinks=precip_sinks, prescribed_Nd=float(Nd_a[0]))
+    for kk, v in (microphys_params or {}).items():
+        if kk not in td:
+            raise KeyError(f"unknown ClimaParams name {kk}")
+        td[kk] = v
+    common_params = PR.create_common_parameters(td)
+    thermo_params = PR.create_thermodynamics_parameters(td)
+    moisture = ET.get_moisture_type("NonEquilibriumMoisture", td)
+    precip = ET.get_precipitation_type(precipitation_choice, td, rain_formation_choice=rain_formation_choice)
+    names = ET.state_variable_names(moisture, precip)
+    Y0 = np.zeros((nc, len(names), 1), dtype=FT)
+    ρ_dry = np.zeros((nc, 1), dtype=FT)
+    T = np.zeros((nc, 1), dtype=FT)
+    cache = {}
+    for c in range(nc):
+        key = (qt_a[c], Nd_a[c])
+        if key not in cache:
+            cache[key] = IC.initial_condition_0d(FT, thermo_params, qt_a[c], Nd_a[c], k, rhod)
+        ip = cache[key]
+        Y0[c, :, 0] = [ip[n] for n in names]
+        ρ_dry[c, 0], T[c, 0] = ip["ρ_dry"], ip["T"]
+    cfg = make_config(
+        model=MODEL_BOX, moisture=moisture.kid_enum, precip=precip.kid_enum, rain_formation=precip.rain_formation,
+        sedimentation=precip.sedimentation, float_type=float_enum(FT), nz=1, nc=nc,
+        precip_sources=int(common_params.precip_sources), precip_sinks=int(common_params.precip_sinks),
+        open_system_activation=0, local_activation=0, qtot_flux_correction=0, device=device,
+        z_min=0.0, z_max=1.0, dt=float(dt))
+    table = PR.flatten_params(td, precip.rain_formation)
+    return Case(cfg=cfg, params=table, ρ_dry=ρ_dry, T=T, Y0=Y0, var_names=names,
+                col_scalars={COL_PRESCRIBED_ND: Nd_a.astype(FT)}, z_centers=np.array([0.5], dtype=FT),
+                meta=dict(toml=td, moisture=moisture, precip=precip, TS=TimeStepping(dt, dt_output, t_end)))
+
+
+def apply_case(handle, case: Case):
+    """Upload a Case into a backend handle (order matters: params and profiles before the state)."""
+    handle.set_params(case.params, case.column_to_set)
+    handle.set_profiles(case.ρ_dry, case.T)
+    for which, values in case.col_scalars.items():
+        handle.set_column_scalar(which, values)
+    handle.set_state(case.Y0)
+    return handle
+
+
+def make_handle(case: Case, backend=Handle):
+    return apply_case(backend(case.cfg), case)
+
+
+# ------------------------------------------------------------------ ensembles
+def splitmix64(x: np.ndarray) -> np.ndarray:
+    """Counter-based hash used for the deterministic synthetic ensembles."""
+    x = (np.asarray(x, dtype=np.uint64) + np.uint64(0x9E3779B97F4A7C15))
+    z = x
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def uniform01(seed: int, c: np.ndarray, k: int) -> np.ndarray:
+    with np.errstate(over="ignore"):
+        h = splitmix64(np.uint64(seed) ^ (np.asarray(c, dtype=np.uint64) * np.uint64(8) + np.uint64(k)))
+    return (h >> np.uint64(11)).astype(np.float64) / float(1 << 53)
+
+
+def k1d_ensemble_case(FT=np.float32, nc: int = 1024, seed: int = 20240601, n_profiles: int = 16,
+                      column_offset: int = 0, device: int = 0, **options) -> Case:
+    """Synthetic calibration-style ensemble of SURVEY §8(d): member c perturbs w1, prescribed Nd and the
+    surface pressure p0 (quantised to n_profiles distinct soundings so the host-side IVP stays cheap)."""
+    FT = np.dtype(FT).type
+    c = np.arange(column_offset, column_offset + nc)
+    w1 = 2.0 * (0.5 + uniform01(seed, c, 0))
+    Nd = 10.0 ** (7.0 + 1.5 * uniform01(seed, c, 1))
+    pidx = np.minimum((uniform01(seed, c, 2) * n_profiles).astype(np.int64), n_profiles - 1)
+    p0_levels = 1e5 * (0.98 + 0.04 * (np.arange(n_profiles) + 0.5) / n_profiles)
+    base = None
+    bank_ρ, bank_T, bank_Y, bank_q = [], [], [], []
+    for p0 in p0_levels:
+        cs = k1d_case(FT, nc=1, device=device, **{**options, "p0": float(p0)})
+        base = base or cs
+        bank_ρ.append(cs.ρ_dry); bank_T.append(cs.T); bank_Y.append(cs.Y0[0]); bank_q.append(cs.col_scalars[COL_Q_SURF][0])
+    bank_ρ, bank_T, bank_Y, bank_q = map(np.asarray, (bank_ρ, bank_T, bank_Y, bank_q))
+    Y0 = bank_Y[pidx].astype(FT)
+    names = base.var_names
+    if "N_aer" in names:  # IC N_aer = prescribed_Nd·ρ_dry/1.225 (initial_condition.jl:171)
+        Y0[:, names.index("N_aer"), :] = (Nd[:, None] * bank_ρ[pidx].astype(np.float64) / 1.225).astype(FT)
+    cfg = base.cfg
+    cfg.nc = nc
+    return Case(cfg=cfg, params=base.params, ρ_dry=bank_ρ[pidx].astype(FT), T=bank_T[pidx].astype(FT), Y0=Y0,
+                var_names=names,
+                col_scalars={COL_Q_SURF: bank_q[pidx].astype(FT), COL_W1: w1.astype(FT),
+                             COL_PRESCRIBED_ND: Nd.astype(FT)},
+                z_centers=base.z_centers, meta=dict(base.meta, seed=seed, n_profiles=n_profiles))
+
+
+def box_ensemble_case(FT=np.float64, nc: int = 1024, seed: int = 20240601, n_ic: int = 64, column_offset: int = 0,
+                      device: int = 0, **options) -> Case:
+    """Synthetic box ensemble of SURVEY §8(d): qt = 1e-3·(0.5+1.5u0), Nd = 10^(7.5+u1), quantised to
+    n_ic x n_ic distinct initial conditions."""
+    c = np.arange(column_offset, column_offset + nc)
+    iq = np.minimum((uniform01(seed, c, 0) * n_ic).astype(np.int64), n_ic - 1)
+    iN = np.minimum((uniform01(seed, c, 1) * n_ic).astype(np.int64), n_ic - 1)
+    qt = 1e-3 * (0.5 + 1.5 * (iq + 0.5) / n_ic)
+    Nd = 10.0 ** (7.5 + (iN + 0.5) / n_ic)
+    return box_case(FT, nc=nc, device=device, qt=qt, Nd=Nd, **options)
