@@ -1,0 +1,449 @@
+// libkid_cuda.so — implementation of the C ABI declared in include/kid_cuda.h.
+// Host-side plumbing only (device memory, layout conversion, launch geometry); all
+// arithmetic of the hot path lives in kid_kernels.cuh / kid_physics.cuh.  There is no CPU
+// fallback: every entry point that computes fails when no CUDA device is usable.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kid_launch.h"
+
+using namespace kid;
+
+namespace {
+thread_local std::string g_err;
+int fail(const std::string& m) { g_err = m; return 1; }
+#define KID_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e__) + " (libkid_cuda has no CPU fallback)"); \
+    } while (0)
+
+int nvars_of(int moisture, int precip) {
+    if (moisture != KID_MOIST_EQ && moisture != KID_MOIST_NONEQ) return -1;
+    if (precip < KID_PRECIP_NONE || precip > KID_PRECIP_2M) return -1;
+    int n = 1 + (moisture == KID_MOIST_NONEQ ? 2 : 0);
+    if (precip == KID_PRECIP_1M || precip == KID_PRECIP_2M) n += 2;
+    if (precip == KID_PRECIP_2M) n += 3;
+    return n;
+}
+int na_index(int moisture, int precip) {  // index of N_aer in the state, -1 if absent
+    return precip == KID_PRECIP_2M ? nvars_of(moisture, precip) - 1 : -1;
+}
+const LaunchTable* table_of(int precip) {
+    switch (precip) {
+        case KID_PRECIP_NONE: return launch_table_precip0();
+        case KID_PRECIP_0M: return launch_table_precip1();
+        case KID_PRECIP_1M: return launch_table_precip2();
+        case KID_PRECIP_2M: return launch_table_precip3();
+    }
+    return nullptr;
+}
+}  // namespace
+
+struct kid_handle {
+    kid_config_t cfg{};
+    int nv = 0, ncp = 0;
+    bool f64 = false;
+    size_t fsz = 4;
+    cudaStream_t stream = nullptr;
+    void *Y = nullptr, *rho_dry = nullptr, *T = nullptr, *w1 = nullptr, *q_surf = nullptr, *Nd = nullptr;
+    void *aux_Naer = nullptr, *out = nullptr, *staging = nullptr;
+    size_t staging_bytes = 0, out_bytes = 0;
+    int prof_per_column = 0;
+    DevSwitches sw{};
+    const LaunchTable* lt = nullptr;
+    int steps_per_launch = 0;
+    int64_t launches = 0;
+    std::vector<double> params;
+    bool params_set = false, profiles_set = false, state_set = false;
+    int C = 32, NW = 1;
+};
+
+namespace {
+
+size_t state_elems(const kid_handle* h) { return size_t(h->nv) * h->cfg.nz * h->ncp; }
+
+int ensure_staging(kid_handle* h, size_t bytes) {
+    if (h->staging_bytes >= bytes) return 0;
+    if (h->staging) cudaFree(h->staging);
+    h->staging = nullptr;
+    h->staging_bytes = 0;
+    KID_CUDA(cudaMalloc(&h->staging, bytes));
+    h->staging_bytes = bytes;
+    return 0;
+}
+int ensure_out(kid_handle* h, size_t bytes) {
+    if (h->out_bytes >= bytes) return 0;
+    if (h->out) cudaFree(h->out);
+    h->out = nullptr;
+    h->out_bytes = 0;
+    KID_CUDA(cudaMalloc(&h->out, bytes));
+    h->out_bytes = bytes;
+    return 0;
+}
+
+template <class FT>
+void fill_const(std::vector<FT>& v, size_t n, double x) { v.assign(n, FT(x)); }
+
+// upload a host vector of nc per-column values into a padded [ncp] device array
+int upload_columns(kid_handle* h, void* dst, const void* src_ft, double fallback) {
+    const int nc = h->cfg.nc, ncp = h->ncp;
+    if (h->f64) {
+        std::vector<double> v(ncp, fallback);
+        if (src_ft) std::memcpy(v.data(), src_ft, size_t(nc) * 8);
+        for (int i = nc; i < ncp; ++i) v[i] = v[nc - 1];
+        KID_CUDA(cudaMemcpyAsync(dst, v.data(), size_t(ncp) * 8, cudaMemcpyHostToDevice, h->stream));
+        KID_CUDA(cudaStreamSynchronize(h->stream));
+    } else {
+        std::vector<float> v(ncp, float(fallback));
+        if (src_ft) std::memcpy(v.data(), src_ft, size_t(nc) * 4);
+        for (int i = nc; i < ncp; ++i) v[i] = v[nc - 1];
+        KID_CUDA(cudaMemcpyAsync(dst, v.data(), size_t(ncp) * 4, cudaMemcpyHostToDevice, h->stream));
+        KID_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+// host [nc][nv][nz] -> device [nv][nz][ncp]
+int to_device_layout(kid_handle* h, const void* host, void* dev, int nv) {
+    const int nc = h->cfg.nc, nz = h->cfg.nz;
+    size_t bytes = size_t(nc) * nv * nz * h->fsz;
+    if (ensure_staging(h, bytes)) return 1;
+    KID_CUDA(cudaMemcpyAsync(h->staging, host, bytes, cudaMemcpyHostToDevice, h->stream));
+    dim3 block(32, 8), grid((h->ncp + 31) / 32, (nv * nz + 31) / 32);
+    if (h->f64)
+        host_to_device_layout<double><<<grid, block, 0, h->stream>>>((const double*)h->staging, (double*)dev, nc, h->ncp, nv, nz);
+    else
+        host_to_device_layout<float><<<grid, block, 0, h->stream>>>((const float*)h->staging, (float*)dev, nc, h->ncp, nv, nz);
+    KID_CUDA(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+// device [nv][nz][ncp] -> host [nc][nv][nz]
+int to_host_layout(kid_handle* h, const void* dev, void* host, int nv) {
+    const int nc = h->cfg.nc, nz = h->cfg.nz;
+    size_t bytes = size_t(nc) * nv * nz * h->fsz;
+    if (ensure_staging(h, bytes)) return 1;
+    dim3 block(32, 8), grid((h->ncp + 31) / 32, (nv * nz + 31) / 32);
+    if (h->f64)
+        device_to_host_layout<double><<<grid, block, 0, h->stream>>>((const double*)dev, (double*)h->staging, nc, h->ncp, nv, nz);
+    else
+        device_to_host_layout<float><<<grid, block, 0, h->stream>>>((const float*)dev, (float*)h->staging, nc, h->ncp, nv, nz);
+    KID_CUDA(cudaGetLastError());
+    h->launches++;
+    KID_CUDA(cudaMemcpyAsync(host, h->staging, bytes, cudaMemcpyDeviceToHost, h->stream));
+    KID_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+template <class FT>
+KArgs<FT> make_args(kid_handle* h, double t0, int nsteps, int diag_mode, int field) {
+    KArgs<FT> a{};
+    a.Y = (FT*)h->Y;
+    a.rho_dry = (const FT*)h->rho_dry;
+    a.T = (const FT*)h->T;
+    a.w1 = (const FT*)h->w1;
+    a.q_surf = (const FT*)h->q_surf;
+    a.Nd = (const FT*)h->Nd;
+    a.aux_Naer = (const FT*)h->aux_Naer;
+    a.out = (FT*)h->out;
+    a.nz = h->cfg.nz;
+    a.nc = h->cfg.nc;
+    a.ncp = h->ncp;
+    a.prof_per_column = h->prof_per_column;
+    a.model = h->cfg.model;
+    a.nsteps = nsteps;
+    a.C = h->C;
+    a.NW = h->NW;
+    a.diag_mode = diag_mode;
+    a.field = field;
+    a.dt = FT(h->cfg.dt);
+    a.dz = FT((h->cfg.z_max - h->cfg.z_min) / h->cfg.nz);
+    a.t0 = t0;
+    a.sw = h->sw;
+    return a;
+}
+
+int check_ready(kid_handle* h) {
+    if (!h) return fail("null handle");
+    if (!h->params_set) return fail("kid_set_params has not been called");
+    if (!h->profiles_set) return fail("kid_set_profiles has not been called");
+    if (!h->state_set) return fail("kid_set_state has not been called");
+    return 0;
+}
+
+// tile geometry: the largest power-of-two number of columns per CTA whose tile fits in
+// shared memory, and as many level chunks as 512 threads / 3 levels per chunk allow
+int choose_tile(kid_handle* h) {
+    int dev = 0, max_smem = 0;
+    KID_CUDA(cudaGetDevice(&dev));
+    KID_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const int nz = h->cfg.nz, moist = h->cfg.moisture;
+    int C = 32;
+    while (C > 1) {
+        size_t s = h->f64 ? h->lt->k1d_smem_d(moist, nz, C) : h->lt->k1d_smem_f(moist, nz, C);
+        if (s <= size_t(max_smem)) break;
+        C /= 2;
+    }
+    size_t s = h->f64 ? h->lt->k1d_smem_d(moist, nz, C) : h->lt->k1d_smem_f(moist, nz, C);
+    if (s > size_t(max_smem)) return fail("column too tall for one shared-memory tile (nz too large)");
+    int NW = std::max(1, std::min(512 / C, nz / 3));
+    if (h->cfg.reserved[0] > 0) NW = std::max(1, std::min(NW, int(h->cfg.reserved[0])));  // tuning override
+    h->C = C;
+    h->NW = NW;
+    return 0;
+}
+
+int launch_tile(kid_handle* h, double t0, int nsteps, int diag_mode, int field) {
+    cudaError_t e;
+    if (h->f64) e = h->lt->k1d_d(h->cfg.moisture, diag_mode != 0, make_args<double>(h, t0, nsteps, diag_mode, field), h->stream);
+    else e = h->lt->k1d_f(h->cfg.moisture, diag_mode != 0, make_args<float>(h, t0, nsteps, diag_mode, field), h->stream);
+    if (e != cudaSuccess) return fail(std::string("k1d_tile_kernel launch: ") + cudaGetErrorString(e));
+    h->launches++;
+    return 0;
+}
+int launch_box(kid_handle* h, double t0, int nsteps) {
+    cudaError_t e;
+    if (h->f64) e = h->lt->box_d(h->cfg.moisture, make_args<double>(h, t0, nsteps, 0, 0), h->stream);
+    else e = h->lt->box_f(h->cfg.moisture, make_args<float>(h, t0, nsteps, 0, 0), h->stream);
+    if (e != cudaSuccess) return fail(std::string("box_step_kernel launch: ") + cudaGetErrorString(e));
+    h->launches++;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kid_nvars(int moisture, int precip) { return nvars_of(moisture, precip); }
+
+int kid_var_names(int moisture, int precip, char* buf, size_t buflen) {
+    int n = nvars_of(moisture, precip);
+    if (n < 0) return fail("unsupported (moisture, precip) pair");
+    std::string s = std::string("rhoq_tot") + '\0';
+    if (moisture == KID_MOIST_NONEQ) s += std::string("rhoq_liq") + '\0' + std::string("rhoq_ice") + '\0';
+    if (precip >= KID_PRECIP_1M) s += std::string("rhoq_rai") + '\0' + std::string("rhoq_sno") + '\0';
+    if (precip == KID_PRECIP_2M) s += std::string("N_liq") + '\0' + std::string("N_rai") + '\0' + std::string("N_aer") + '\0';
+    if (s.size() > buflen) return fail("buffer too small");
+    std::memcpy(buf, s.data(), s.size());
+    return 0;
+}
+
+int kid_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int kid_create(const kid_config_t* cfg, kid_handle_t** out) {
+    if (!cfg || !out) return fail("null argument");
+    *out = nullptr;
+    if (cfg->abi_version != KID_ABI_VERSION) return fail("kid_config_t.abi_version mismatch");
+    if (cfg->params_version != KID_PARAMS_VERSION) return fail("kid_config_t.params_version mismatch");
+    int nv = nvars_of(cfg->moisture, cfg->precip);
+    if (nv < 0) return fail("unsupported (moisture, precip) pair: only Equilibrium/NonEquilibrium moisture and No/0M/1M/2M precipitation are on the device path");
+    if (cfg->model < KID_MODEL_BOX || cfg->model > KID_MODEL_K2D) return fail("invalid model");
+    if (cfg->float_type != KID_F32 && cfg->float_type != KID_F64) return fail("invalid float_type");
+    if (cfg->nz < 1 || cfg->nc < 1) return fail("nz and nc must be positive");
+    if (cfg->model == KID_MODEL_BOX && cfg->nz != 1) return fail("BoxModel needs nz == 1");
+    if ((cfg->model == KID_MODEL_K1D || cfg->model == KID_MODEL_K1D_COL_SED) && cfg->nz < 3)
+        return fail("K1DModel needs at least 3 levels (Extrapolate boundary stencils)");
+    if (!(cfg->dt > 0)) return fail("dt must be positive");
+    if (cfg->sedimentation == KID_SED_CHEN2022) return fail("sedimentation Chen2022 is not implemented on the device path");
+    if (cfg->precip == KID_PRECIP_1M && (cfg->rain_formation < KID_RF_CLIMA_1M || cfg->rain_formation > KID_RF_VARTIMESCALE))
+        return fail("invalid rain_formation for Precipitation1M");
+    if (cfg->precip == KID_PRECIP_2M && cfg->rain_formation != KID_RF_SB2006 && cfg->rain_formation != KID_RF_SB2006NL)
+        return fail("invalid rain_formation for Precipitation2M");
+    if (cfg->model == KID_MODEL_K2D) return fail("K2DModel: not implemented in this build");
+    if (kid_device_count() < 1) return fail("no CUDA device visible: libkid_cuda has no CPU fallback");
+    KID_CUDA(cudaSetDevice(cfg->device));
+
+    kid_handle* h = new kid_handle();
+    h->cfg = *cfg;
+    h->nv = nv;
+    h->ncp = (cfg->nc + 31) / 32 * 32;
+    h->f64 = cfg->float_type == KID_F64;
+    h->fsz = h->f64 ? 8 : 4;
+    h->lt = table_of(cfg->precip);
+    h->sw.rain_formation = cfg->rain_formation;
+    h->sw.sb_limited = cfg->rain_formation != KID_RF_SB2006NL;
+    h->sw.precip_sources = cfg->precip_sources;
+    h->sw.precip_sinks = cfg->precip_sinks;
+    h->sw.open_system_activation = cfg->open_system_activation;
+    h->sw.local_activation = cfg->local_activation;
+    h->sw.qtot_flux_correction = cfg->qtot_flux_correction;
+    auto cleanup = [&](int rc) { kid_destroy(h); return rc; };
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail("cudaStreamCreate failed"));
+    size_t colb = size_t(h->ncp) * h->fsz;
+    if (cudaMalloc(&h->Y, state_elems(h) * h->fsz) != cudaSuccess) return cleanup(fail("cudaMalloc(state) failed"));
+    if (cudaMemsetAsync(h->Y, 0, state_elems(h) * h->fsz, h->stream) != cudaSuccess) return cleanup(fail("cudaMemset failed"));
+    if (cudaMalloc(&h->w1, colb) != cudaSuccess || cudaMalloc(&h->q_surf, colb) != cudaSuccess ||
+        cudaMalloc(&h->Nd, colb) != cudaSuccess)
+        return cleanup(fail("cudaMalloc(column scalars) failed"));
+    if (cudaMemsetAsync(h->q_surf, 0, colb, h->stream) != cudaSuccess) return cleanup(fail("cudaMemset failed"));
+    if (choose_tile(h)) return cleanup(1);
+    *out = h;
+    return 0;
+}
+
+void kid_destroy(kid_handle_t* h) {
+    if (!h) return;
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : {h->Y, h->rho_dry, h->T, h->w1, h->q_surf, h->Nd, h->aux_Naer, h->out, h->staging})
+        if (p) cudaFree(p);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int kid_set_params(kid_handle_t* h, const double* params, int32_t nparams, int32_t nsets, const int32_t* column_to_set) {
+    if (!h || !params) return fail("null argument");
+    if (nparams != KID_NPARAMS) return fail("kid_set_params: nparams != KID_NPARAMS (header/library version skew)");
+    if (nsets != 1 || column_to_set) return fail("kid_set_params: per-column parameter sets are not implemented in this build");
+    h->params.assign(params, params + KID_NPARAMS);
+    if (h->f64) {
+        DevParams<double> P;
+        fill_dev_params(P, params);
+        KID_CUDA(h->lt->upload_params_d(P, h->stream));
+    } else {
+        DevParams<float> P;
+        fill_dev_params(P, params);
+        KID_CUDA(h->lt->upload_params_f(P, h->stream));
+    }
+    KID_CUDA(cudaStreamSynchronize(h->stream));
+    // per-column scalars default to the table values
+    if (upload_columns(h, h->w1, nullptr, params[KID_P_kid_w1])) return 1;
+    if (upload_columns(h, h->Nd, nullptr, params[KID_P_com_prescribed_Nd])) return 1;
+    h->params_set = true;
+    return 0;
+}
+
+int kid_set_profiles(kid_handle_t* h, const void* rho_dry, const void* T, int32_t per_column) {
+    if (!h || !rho_dry || !T) return fail("null argument");
+    const int nz = h->cfg.nz;
+    size_t n = per_column ? size_t(nz) * h->ncp : size_t(nz);
+    for (void** p : {&h->rho_dry, &h->T}) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+        KID_CUDA(cudaMalloc(p, n * h->fsz));
+        KID_CUDA(cudaMemsetAsync(*p, 0, n * h->fsz, h->stream));
+    }
+    h->prof_per_column = per_column ? 1 : 0;
+    if (per_column) {
+        if (to_device_layout(h, rho_dry, h->rho_dry, 1)) return 1;
+        KID_CUDA(cudaStreamSynchronize(h->stream));
+        if (to_device_layout(h, T, h->T, 1)) return 1;
+    } else {
+        KID_CUDA(cudaMemcpyAsync(h->rho_dry, rho_dry, n * h->fsz, cudaMemcpyHostToDevice, h->stream));
+        KID_CUDA(cudaMemcpyAsync(h->T, T, n * h->fsz, cudaMemcpyHostToDevice, h->stream));
+    }
+    KID_CUDA(cudaStreamSynchronize(h->stream));
+    h->profiles_set = true;
+    return 0;
+}
+
+int kid_set_column_scalar(kid_handle_t* h, int32_t which, const void* values) {
+    if (!h) return fail("null handle");
+    if (!h->params_set) return fail("kid_set_params must be called before kid_set_column_scalar");
+    switch (which) {
+        case KID_COL_W1: return upload_columns(h, h->w1, values, h->params[KID_P_kid_w1]);
+        case KID_COL_Q_SURF: return upload_columns(h, h->q_surf, values, 0.0);
+        case KID_COL_PRESCRIBED_ND: return upload_columns(h, h->Nd, values, h->params[KID_P_com_prescribed_Nd]);
+    }
+    return fail("invalid column scalar id");
+}
+
+int kid_set_state(kid_handle_t* h, const void* Y) {
+    if (!h || !Y) return fail("null argument");
+    if (to_device_layout(h, Y, h->Y, h->nv)) return 1;
+    // aux.microph_variables.N_aer is built from the initial profile and never refreshed by
+    // the Box / col_sed rhs (no precompute_aux_activation! call): snapshot it
+    int na = na_index(h->cfg.moisture, h->cfg.precip);
+    if (na >= 0 && (h->cfg.model == KID_MODEL_BOX || h->cfg.model == KID_MODEL_K1D_COL_SED)) {
+        size_t plane = size_t(h->cfg.nz) * h->ncp * h->fsz;
+        if (!h->aux_Naer) KID_CUDA(cudaMalloc(&h->aux_Naer, plane));
+        KID_CUDA(cudaMemcpyAsync(h->aux_Naer, (const char*)h->Y + size_t(na) * plane, plane, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    KID_CUDA(cudaStreamSynchronize(h->stream));
+    h->state_set = true;
+    return 0;
+}
+
+int kid_get_state(kid_handle_t* h, void* Y) {
+    if (!h || !Y) return fail("null argument");
+    if (!h->state_set) return fail("kid_set_state has not been called");
+    return to_host_layout(h, h->Y, Y, h->nv);
+}
+
+int kid_set_steps_per_launch(kid_handle_t* h, int32_t n) {
+    if (!h) return fail("null handle");
+    if (n < 0) return fail("steps_per_launch must be >= 0");
+    h->steps_per_launch = n;
+    return 0;
+}
+
+int kid_step(kid_handle_t* h, double t0, int32_t nsteps) {
+    if (check_ready(h)) return 1;
+    if (nsteps < 0) return fail("nsteps must be >= 0");
+    int spl = h->steps_per_launch > 0 ? h->steps_per_launch : nsteps;
+    int done = 0;
+    while (done < nsteps) {
+        int n = std::min(spl, nsteps - done);
+        double t = t0 + double(done) * h->cfg.dt;
+        int rc = (h->cfg.model == KID_MODEL_BOX) ? launch_box(h, t, n) : launch_tile(h, t, n, 0, 0);
+        if (rc) return rc;
+        done += n;
+    }
+    return 0;
+}
+
+int kid_rhs(kid_handle_t* h, double t, void* dY_out) {
+    if (check_ready(h)) return 1;
+    if (!dY_out) return fail("null argument");
+    if (ensure_out(h, state_elems(h) * h->fsz)) return 1;
+    KID_CUDA(cudaMemsetAsync(h->out, 0, state_elems(h) * h->fsz, h->stream));
+    if (launch_tile(h, t, 1, 1, 0)) return 1;
+    return to_host_layout(h, h->out, dY_out, h->nv);
+}
+
+int kid_get_aux(kid_handle_t* h, double t, int32_t field, void* out) {
+    if (check_ready(h)) return 1;
+    if (!out) return fail("null argument");
+    if (field < 0 || field >= KID_NAUX) return fail("invalid aux field id");
+    if (ensure_out(h, state_elems(h) * h->fsz)) return 1;
+    if (launch_tile(h, t, 1, 2, field)) return 1;
+    return to_host_layout(h, h->out, out, 1);
+}
+
+int kid_reduce_max(kid_handle_t* h, double t, int32_t field, double* out) {
+    if (check_ready(h)) return 1;
+    if (!out) return fail("null argument");
+    size_t n = size_t(h->cfg.nc) * h->cfg.nz;
+    std::vector<char> buf(n * h->fsz);
+    if (kid_get_aux(h, t, field, buf.data())) return 1;
+    double m = -1e300;
+    if (h->f64) for (size_t i = 0; i < n; ++i) m = std::max(m, ((double*)buf.data())[i]);
+    else for (size_t i = 0; i < n; ++i) m = std::max(m, double(((float*)buf.data())[i]));
+    *out = m;
+    return 0;
+}
+
+int kid_k2d_stage_begin(kid_handle_t*, double, int32_t) { return fail("K2DModel: not implemented in this build"); }
+int kid_k2d_edge_buffers(kid_handle_t*, void**, void**, void**, void**, size_t*) { return fail("K2DModel: not implemented in this build"); }
+int kid_k2d_stage_end(kid_handle_t*, int32_t) { return fail("K2DModel: not implemented in this build"); }
+
+int kid_synchronize(kid_handle_t* h) {
+    if (!h) return fail("null handle");
+    KID_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+void* kid_stream(kid_handle_t* h) { return h ? (void*)h->stream : nullptr; }
+void* kid_state_device_ptr(kid_handle_t* h) { return h ? h->Y : nullptr; }
+int64_t kid_launch_count(kid_handle_t* h) { return h ? h->launches : 0; }
+const char* kid_last_error(void) { return g_err.c_str(); }
+const char* kid_version(void) { return "libkid_cuda 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,503 @@
+// Kernels of the hot path (sm_100a): BoxModel and K1DModel rhs + SSPRK33.
+//
+// Device state layout (structure of arrays over the batch of columns):
+//     Y[var][level][column], column fastest, row pitch ncp (columns padded to 32)
+// so that the 32 lanes of a warp always touch 32 neighbouring columns of one (var, level)
+// row: every global access is one fully used 128-byte line (f32) / two lines (f64).
+//
+// k1d_tile_kernel: one CTA owns a TILE of C columns x all nz levels and keeps the tile's
+// state in shared memory for the whole launch (all SSPRK33 stages of `nsteps` steps), so
+// HBM sees one read and one write of the state per STEP while the rhs — thermodynamics,
+// terminal velocities, ARG activation + cloud-base search, condensation, 0M/1M/2M process
+// rates, the upwind-corrected advection/sedimentation stencil and the SSPRK33 stage combine
+// — is evaluated from shared memory/registers.  Thread (c, j) owns column c and the j-th
+// contiguous chunk of levels; a warp is 32 columns at the SAME levels, so the branches of
+// the microphysics (cloud / no cloud / rain) are warp-coherent across ensemble members.
+// The vertical stencil is a sliding window in registers (face flux carried upward); only the
+// chunk-edge values come from neighbouring threads through shared memory.
+//
+// Replaces (reference): rhs! closures src/K1DModel/ode_utils.jl:29-73,
+// src/BoxModel/ode_utils.jl:10-22, the SSPRK33 loop of ODE.solve
+// (test/experiments/KiD_driver/run_KiD_simulation.jl:159-166).
+#pragma once
+#include <climits>
+#include <type_traits>
+
+#include "kid_physics.cuh"
+
+namespace kid {
+
+// compile-time loop: f(std::integral_constant<int, I>) for I in [0, N)
+template <int I, int N, class F>
+KID_DEV void static_for(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+template <class FT>
+struct KArgs {
+    FT* Y;                  // [NV][nz][ncp] device state (in/out)
+    const FT* rho_dry;      // [nz][ncp] or [nz]
+    const FT* T;            // same shape
+    const FT* w1;           // [ncp] kid_params.w1 per column
+    const FT* q_surf;       // [ncp] aux.q_surf per column
+    const FT* Nd;           // [ncp] common_params.prescribed_Nd per column
+    const FT* aux_Naer;     // [nz][ncp] aux.microph_variables.N_aer snapshot (Box / col_sed), may be null
+    FT* out;                // DIAG: dY [NV][nz][ncp] (mode 1) or one aux field [nz][ncp] (mode 2)
+    int nz, nc, ncp;
+    int prof_per_column;    // 0: rho_dry/T are [nz]; 1: [nz][ncp]
+    int model;              // enum kid_model
+    int nsteps;
+    int C, NW;              // tile: columns per CTA, level chunks per column
+    int diag_mode, field;   // 0 = step, 1 = rhs only, 2 = aux field
+    FT dt, dz;
+    double t0;
+    DevSwitches sw;
+};
+
+// ------------------------------------------------------------ advected variables
+enum { VEL_AIR = 0, VEL_VT1 = 1, VEL_VT2 = 2 };
+enum { BC_SET = 0, BC_EXTRAP = 1 };
+enum { BV_ZERO = 0, BV_QSURF = 1, BV_AERO = 2 };
+enum { FCC_ALWAYS = 0, FCC_QTOT_FLAG = 1 };
+struct AdvVar {
+    int idx, vel, bot, botval, top, fcc, to_tot;
+};
+// K1D advection tables: src/K1DModel/tendency.jl:274-289 (Eq), :306-332 (NonEq),
+// :353-400 (1M), :401-435 (2M)
+template <int MOIST, int PRECIP>
+__host__ __device__ constexpr int adv_count() {
+    using L = Lay<MOIST, PRECIP>;
+    return 1 + (L::neq ? 2 : 0) + (PRECIP == KID_PRECIP_1M ? 2 : 0) + (PRECIP == KID_PRECIP_2M ? 4 : 0);
+}
+template <int MOIST, int PRECIP>
+__host__ __device__ constexpr AdvVar adv_entry(int i) {
+    using L = Lay<MOIST, PRECIP>;
+    if (i == 0) return {L::tot, VEL_AIR, BC_SET, BV_QSURF, BC_EXTRAP, FCC_QTOT_FLAG, 0};
+    int b = 1;
+    if (L::neq) {
+        if (i == 1) return {L::liq, VEL_AIR, BC_SET, BV_ZERO, BC_EXTRAP, FCC_ALWAYS, 0};
+        if (i == 2) return {L::ice, VEL_AIR, BC_SET, BV_ZERO, BC_EXTRAP, FCC_ALWAYS, 0};
+        b = 3;
+    }
+    if (PRECIP == KID_PRECIP_1M) {
+        if (i == b) return {L::rai, VEL_VT1, BC_EXTRAP, BV_ZERO, BC_SET, FCC_ALWAYS, 1};
+        return {L::sno, VEL_VT2, BC_EXTRAP, BV_ZERO, BC_SET, FCC_ALWAYS, 1};
+    }
+    // 2M
+    if (i == b) return {L::Na, VEL_AIR, BC_SET, BV_AERO, BC_EXTRAP, FCC_ALWAYS, 0};
+    if (i == b + 1) return {L::Nl, VEL_AIR, BC_EXTRAP, BV_ZERO, BC_SET, FCC_ALWAYS, 0};
+    if (i == b + 2) return {L::Nr, VEL_VT2, BC_EXTRAP, BV_ZERO, BC_SET, FCC_ALWAYS, 0};
+    return {L::rai, VEL_VT1, BC_EXTRAP, BV_ZERO, BC_SET, FCC_ALWAYS, 1};
+}
+
+// prescribed momentum flux ρw(t), src/K1DModel/tendency.jl:208-210 (evaluated in double, rounded to FT)
+template <class FT>
+KID_DEV FT rho_w_of_t(FT t, FT w1, FT t1) {
+    return (t < t1) ? FT(double(w1) * sin(M_PI * double(t) / double(t1))) : FT(0);
+}
+
+// SSPRK33 stage combine exactly as OrdinaryDiffEq's perform_step! writes it
+template <class FT>
+KID_DEV FT ssprk33_combine(int stage, FT u, FT y, FT dt, FT k) {
+    if (stage == 0) return y + dt * k;
+    if (stage == 1) return (FT(3) * u + y + dt * k) / FT(4);
+    return (u + FT(2) * y + FT(2) * dt * k) / FT(3);
+}
+template <class FT>
+KID_DEV FT stage_time(int stage, FT t, FT dt) {
+    return stage == 0 ? t : (stage == 1 ? t + dt : t + dt / FT(2));
+}
+
+// requested aux field of one point (kid_get_aux; schema src/Common/ode_utils.jl:110-175)
+template <class FT, int MOIST, int PRECIP, class PRM>
+KID_DEV FT aux_field_value(const PRM& P, int field, const Point<FT>& a, const Sources<FT>& s, FT v1, FT v2, FT act_Nl,
+                           bool open_system) {
+    using L = Lay<MOIST, PRECIP>;
+    TD<FT, PRM> td(P);
+    switch (field) {
+        case KID_AUX_RHO: return a.rho;
+        case KID_AUX_RHO_DRY: return a.rho_dry;
+        case KID_AUX_P: return pressure_point<FT, MOIST, PRECIP>(P, a);
+        case KID_AUX_T: return a.T;
+        case KID_AUX_THETA_DRY: return td.potential_temperature_dry(a.T, a.rho_dry);
+        case KID_AUX_THETA_LIQ_ICE:
+            if constexpr (!L::neq) return td.liquid_ice_pottemp(a.T, a.rho, a.q_tot, a.ql_eq, a.qi_eq);
+            else if constexpr (L::has_pr)
+                return td.liquid_ice_pottemp(a.T, a.rho, a.q_tot, a.q_liq + a.q_rai, a.q_ice + a.q_sno);
+            else return td.liquid_ice_pottemp(a.T, a.rho, a.q_tot, a.q_liq, a.q_ice);
+        case KID_AUX_Q_TOT: return a.q_tot;
+        case KID_AUX_Q_LIQ: return a.q_liq;
+        case KID_AUX_Q_ICE: return a.q_ice;
+        case KID_AUX_Q_RAI: return a.q_rai;
+        case KID_AUX_Q_SNO: return a.q_sno;
+        case KID_AUX_N_LIQ: return a.N_liq;
+        case KID_AUX_N_RAI: return a.N_rai;
+        case KID_AUX_N_AER: return a.N_aer;
+        case KID_AUX_TERM_VEL_RAI: return v1;
+        case KID_AUX_TERM_VEL_SNO: return PRECIP == KID_PRECIP_1M ? v2 : FT(0);
+        case KID_AUX_TERM_VEL_N_RAI: return PRECIP == KID_PRECIP_2M ? v2 : FT(0);
+        case KID_AUX_SRC_Q_TOT: return s.s_tot;
+        case KID_AUX_SRC_Q_LIQ: return s.s_liq;
+        case KID_AUX_SRC_Q_ICE: return s.s_ice;
+        case KID_AUX_SRC_Q_RAI: return s.s_rai;
+        case KID_AUX_SRC_Q_SNO: return s.s_sno;
+        case KID_AUX_SRC_N_AER: return s.s_Na;
+        case KID_AUX_SRC_N_LIQ: return s.s_Nl;
+        case KID_AUX_SRC_N_RAI: return s.s_Nr;
+        case KID_AUX_ACT_N_AER: return (open_system ? FT(0) : FT(-1)) * act_Nl;
+        case KID_AUX_ACT_N_LIQ: return act_Nl;
+        case KID_AUX_CLOUD_SRC_Q_LIQ: return s.cs_liq;
+        case KID_AUX_CLOUD_SRC_Q_ICE: return s.cs_ice;
+    }
+    return FT(0);
+}
+
+// shared-memory footprint of one tile (bytes); must match the carve-up in k1d_tile_kernel
+template <class FT, int MOIST, int PRECIP>
+inline size_t k1d_tile_smem_bytes(int nz, int C) {
+    using L = Lay<MOIST, PRECIP>;
+    constexpr int NADV = adv_count<MOIST, PRECIP>();
+    size_t nfl = size_t(L::NV) * nz * C;       // Ys
+    nfl += size_t(2) * nz * C;                 // rho_dry, T
+    if (L::has_pr) nfl += size_t(2) * nz * C;  // vt1, vt2
+    if (L::is2m) nfl += size_t(nz) * C;        // activation rate
+    nfl += size_t(2) * NADV * C;               // top-extrapolation scratch
+    return nfl * sizeof(FT) + size_t(2) * C * sizeof(int);
+}
+
+template <class FT, int MOIST, int PRECIP, bool DIAG, class PRMSRC>
+__global__ void __launch_bounds__(512, 1) k1d_tile_kernel(const KArgs<FT> A) {
+    using L = Lay<MOIST, PRECIP>;
+    using M = Mth<FT>;
+    constexpr int NV = L::NV;
+    constexpr int NADV = adv_count<MOIST, PRECIP>();
+    const auto& P = PRMSRC::get();
+    const int nz = A.nz, C = A.C, NW = A.NW, ncp = A.ncp;
+    const int c = threadIdx.x, j = threadIdx.y;
+    const int gc = blockIdx.x * C + c;
+    const bool active = gc < A.nc;
+    const int k0 = (j * nz) / NW, k1 = ((j + 1) * nz) / NW;
+    const size_t plane = size_t(nz) * ncp;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FT* Ys = reinterpret_cast<FT*>(smem_raw);  // [NV][nz][C]
+    FT* rds = Ys + size_t(NV) * nz * C;        // [nz][C]
+    FT* Ts = rds + size_t(nz) * C;
+    FT* nxt = Ts + size_t(nz) * C;
+    FT* vt1s = nullptr; FT* vt2s = nullptr; FT* acts = nullptr;
+    if constexpr (L::has_pr) { vt1s = nxt; vt2s = nxt + size_t(nz) * C; nxt += size_t(2) * nz * C; }
+    if constexpr (L::is2m) { acts = nxt; nxt += size_t(nz) * C; }
+    FT* edge = nxt;                            // [2*NADV][C]
+    int* cb = reinterpret_cast<int*>(edge + size_t(2) * NADV * C);  // [2][C]
+    auto sidx = [&](int v, int k) { return (size_t(v) * nz + k) * C + c; };
+    auto kidx = [&](int k) { return size_t(k) * C + c; };
+
+    // ---- load the tile (coalesced: lanes = neighbouring columns)
+    FT w1c = 0, qsurf = 0, Ndc = 0;
+    if (active) {
+        for (int k = k0; k < k1; ++k) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) Ys[sidx(v, k)] = A.Y[v * plane + size_t(k) * ncp + gc];
+            size_t pi = A.prof_per_column ? size_t(k) * ncp + gc : size_t(k);
+            rds[kidx(k)] = A.rho_dry[pi];
+            Ts[kidx(k)] = A.T[pi];
+        }
+        w1c = A.w1[gc]; qsurf = A.q_surf[gc]; Ndc = A.Nd[gc];
+    }
+    if (j == 0) { cb[c] = INT_MAX; cb[C + c] = INT_MAX; }
+    __syncthreads();
+
+    const bool k1d = (A.model == KID_MODEL_K1D);
+    const bool with_adv = (A.model == KID_MODEL_K1D || A.model == KID_MODEL_K1D_COL_SED);
+    const bool stale_Naer = (A.model == KID_MODEL_BOX || A.model == KID_MODEL_K1D_COL_SED) && A.aux_Naer != nullptr;
+    const FT dt = A.dt, dz = A.dz;
+    const int nstage_total = DIAG ? 1 : 3 * A.nsteps;
+
+#pragma unroll 1
+    for (int it = 0; it < nstage_total; ++it) {
+        const int step = it / 3, stage = DIAG ? 0 : it % 3;
+        const int par = it & 1;
+        const FT tn = FT(A.t0 + double(step) * double(dt));
+        const FT ts = stage_time(stage, tn, dt);
+        const FT rw = k1d ? rho_w_of_t(ts, w1c, FT(P.kid_t1)) : FT(0);
+
+        // ---- pass 1 (pointwise): terminal velocities and activation rate of the own levels
+        if constexpr (L::has_pr) {
+            if (active) {
+                int first = INT_MAX;
+#pragma unroll 1
+                for (int k = k0; k < k1; ++k) {
+                    FT y[NV];
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) y[v] = Ys[sidx(v, k)];
+                    Point<FT> a;
+                    thermo_point<FT, MOIST, PRECIP>(P, y, rds[kidx(k)], Ts[kidx(k)], a);
+                    FT v1, v2;
+                    terminal_velocities<FT, PRECIP>(P, A.sw, a, v1, v2);
+                    vt1s[kidx(k)] = v1;
+                    vt2s[kidx(k)] = v2;
+                    if constexpr (L::is2m) {
+                        FT S_Nl = FT(0);
+                        if (k1d) {
+                            FT p = pressure_point<FT, MOIST, PRECIP>(P, a);
+                            S_Nl = aerosol_activation_rate<FT>(P, A.sw, a.q_tot, a.q_liq + a.q_rai, a.q_ice,
+                                                               a.N_liq + a.N_rai, a.N_aer, a.T, p, a.rho, rw, dt);
+                            // find_cloud_base! (src/K1DModel/tendency.jl:21-32): the accumulator starts at
+                            // level 1 and is replaced only while its S is 0 and the candidate's S is > 0
+                            bool cand = (k == 0) ? (S_Nl != FT(0)) : (S_Nl > FT(0));
+                            if (cand && first == INT_MAX) first = k;
+                        }
+                        acts[kidx(k)] = S_Nl;
+                    }
+                }
+                if constexpr (L::is2m) {
+                    if (k1d && !A.sw.local_activation && first != INT_MAX) atomicMin(&cb[par * C + c], first);
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- halo pre-read: everything owned by the neighbouring chunks that the sweep needs
+        FT lo[NADV], hi[NADV];
+        FT lo_rd = 0, hi_rd = 0, lo_v1 = 0, hi_v1 = 0, lo_v2 = 0, hi_v2 = 0;
+        int cbk = INT_MAX;
+#pragma unroll
+        for (int i = 0; i < NADV; ++i) lo[i] = hi[i] = FT(0);
+        if (active && with_adv) {
+            static_for<0, NADV>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                constexpr int vi = adv_entry<MOIST, PRECIP>(i).idx;
+                if (k0 > 0) lo[i] = Ys[sidx(vi, k0 - 1)];
+                if (k1 < nz) hi[i] = Ys[sidx(vi, k1)];
+            });
+            if (k0 > 0) lo_rd = rds[kidx(k0 - 1)];
+            if (k1 < nz) hi_rd = rds[kidx(k1)];
+            if constexpr (L::has_pr) {
+                if (k0 > 0) { lo_v1 = vt1s[kidx(k0 - 1)]; lo_v2 = vt2s[kidx(k0 - 1)]; }
+                if (k1 < nz) { hi_v1 = vt1s[kidx(k1)]; hi_v2 = vt2s[kidx(k1)]; }
+            }
+        }
+        if constexpr (L::is2m) {
+            cbk = cb[par * C + c];
+            if (j == 0) cb[(par ^ 1) * C + c] = INT_MAX;
+        }
+        __syncthreads();
+
+        // ---- pass 2: sources + stencil + stage combine, sweeping the own levels upward
+        if (active) {
+            FT Flo[NADV], Clo[NADV];
+#pragma unroll
+            for (int i = 0; i < NADV; ++i) Flo[i] = Clo[i] = FT(0);
+            const FT surf_flux[3] = {FT(0), rw * qsurf, rw * Ndc * (FT(1) - qsurf) / FT(1.225)};
+            if (with_adv && k0 > 0 && k0 < k1) {
+                // faces below the chunk: velocity and fluxes from the pre-read halo
+                FT rho_k = rds[kidx(k0)] + Ys[sidx(L::tot, k0)];
+                FT rho_l = lo_rd + lo[0];
+                FT wa = rw / ((rho_k + rho_l) / FT(2));
+                FT wv[3] = {wa, wa, wa};
+                if constexpr (L::has_pr) {
+                    wv[1] = wa - (vt1s[kidx(k0)] + lo_v1) / FT(2);
+                    wv[2] = wa - (vt2s[kidx(k0)] + lo_v2) / FT(2);
+                }
+                static_for<0, NADV>([&](auto I) {
+                    constexpr int i = decltype(I)::value;
+                    constexpr AdvVar e = adv_entry<MOIST, PRECIP>(i);
+                    FT yk = Ys[sidx(e.idx, k0)];
+                    Flo[i] = wv[e.vel] * ((yk + lo[i]) / FT(2));
+                    Clo[i] = M::abs(wv[e.vel]) * (yk - lo[i]);
+                });
+            }
+#pragma unroll 1
+            for (int k = k0; k < k1; ++k) {
+                FT y[NV], tend[NV];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) y[v] = Ys[sidx(v, k)];
+                Point<FT> a;
+                thermo_point<FT, MOIST, PRECIP>(P, y, rds[kidx(k)], Ts[kidx(k)], a);
+                if (stale_Naer) a.N_aer = A.aux_Naer[size_t(k) * ncp + gc];
+                FT act_Nl = FT(0);
+                if constexpr (L::is2m) {
+                    if (k1d) act_Nl = (A.sw.local_activation || k == cbk) ? acts[kidx(k)] : FT(0);
+                }
+                Sources<FT> src;
+                point_source_tendencies<FT, MOIST, PRECIP>(P, A.sw, a, Ndc, dt, k1d, act_Nl, src, tend);
+
+                if (with_adv) {
+                    const bool has_up = (k + 1 < nz);
+                    const bool up_own = (k + 1 < k1);
+                    // upper face k+1/2 (and k+3/2 for the bottom cell, which copies cell 1's stencil)
+                    FT wv[3] = {FT(0), FT(0), FT(0)}, wv2[3] = {FT(0), FT(0), FT(0)};
+                    FT v1k = FT(0), v2k = FT(0);
+                    if constexpr (L::has_pr) { v1k = vt1s[kidx(k)]; v2k = vt2s[kidx(k)]; }
+                    if (has_up) {
+                        FT rho_u = (up_own ? rds[kidx(k + 1)] : hi_rd) + (up_own ? Ys[sidx(L::tot, k + 1)] : hi[0]);
+                        FT wa = rw / ((rho_u + a.rho) / FT(2));
+                        wv[0] = wv[1] = wv[2] = wa;
+                        if constexpr (L::has_pr) {
+                            FT v1u = up_own ? vt1s[kidx(k + 1)] : hi_v1;
+                            FT v2u = up_own ? vt2s[kidx(k + 1)] : hi_v2;
+                            wv[1] = wa - (v1u + v1k) / FT(2);
+                            wv[2] = wa - (v2u + v2k) / FT(2);
+                        }
+                        if (k == 0) {
+                            FT rho_2 = rds[kidx(2)] + Ys[sidx(L::tot, 2)];
+                            FT wa2 = rw / ((rho_2 + rho_u) / FT(2));
+                            wv2[0] = wv2[1] = wv2[2] = wa2;
+                            if constexpr (L::has_pr) {
+                                wv2[1] = wa2 - (vt1s[kidx(2)] + vt1s[kidx(1)]) / FT(2);
+                                wv2[2] = wa2 - (vt2s[kidx(2)] + vt2s[kidx(1)]) / FT(2);
+                            }
+                        }
+                    }
+                    FT S_tot = FT(0);
+                    bool any_S = false;
+                    static_for<0, NADV>([&](auto I) {
+                        constexpr int i = decltype(I)::value;
+                        constexpr AdvVar e = adv_entry<MOIST, PRECIP>(i);
+                        const FT yk = y[e.idx];
+                        const FT yu = has_up ? (up_own ? Ys[sidx(e.idx, k + 1)] : hi[i]) : FT(0);
+                        const FT w = wv[e.vel];
+                        const FT Fup = has_up ? w * ((yu + yk) / FT(2)) : FT(0);
+                        const FT Cup = has_up ? M::abs(w) * (yu - yk) : FT(0);
+                        FT D, fc;
+                        if (k == 0) {
+                            const FT y2 = Ys[sidx(e.idx, 2)];
+                            const FT w2 = wv2[e.vel];
+                            if (e.bot == BC_SET) D = (Fup - surf_flux[e.botval]) / dz;
+                            else D = (w2 * ((y2 + yu) / FT(2)) - Fup) / dz;
+                            fc = P.num_fcc_scale * (M::abs(w2) * (y2 - yu) - Cup) / dz;
+                        } else if (k == nz - 1) {
+                            if (e.top == BC_SET) D = (FT(0) - Flo[i]) / dz;
+                            else D = edge[size_t(2 * i) * C + c];
+                            fc = edge[size_t(2 * i + 1) * C + c];
+                        } else {
+                            D = (Fup - Flo[i]) / dz;
+                            fc = P.num_fcc_scale * (Cup - Clo[i]) / dz;
+                            if (k == nz - 2) {
+                                edge[size_t(2 * i) * C + c] = D;
+                                edge[size_t(2 * i + 1) * C + c] = fc;
+                            }
+                        }
+                        Flo[i] = Fup;
+                        Clo[i] = Cup;
+                        const bool fcc_on = (e.fcc == FCC_ALWAYS) || A.sw.qtot_flux_correction;
+                        if (e.to_tot) {
+                            FT S = -D;
+                            S += fc;
+                            tend[e.idx] += S;
+                            S_tot = any_S ? S_tot + S : S;
+                            any_S = true;
+                        } else {
+                            tend[e.idx] += -D;
+                            if (fcc_on) tend[e.idx] += fc;
+                        }
+                    });
+                    if (any_S) tend[L::tot] += S_tot;
+                }
+
+                if constexpr (DIAG) {
+                    if (A.diag_mode == 1) {
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) A.out[v * plane + size_t(k) * ncp + gc] = tend[v];
+                    } else {
+                        FT v1 = FT(0), v2 = FT(0);
+                        if constexpr (L::has_pr) { v1 = vt1s[kidx(k)]; v2 = vt2s[kidx(k)]; }
+                        A.out[size_t(k) * ncp + gc] = aux_field_value<FT, MOIST, PRECIP>(
+                            P, A.field, a, src, v1, v2, act_Nl, A.sw.open_system_activation != 0);
+                    }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        const size_t gi = v * plane + size_t(k) * ncp + gc;
+                        FT u = (stage == 0) ? y[v] : A.Y[gi];
+                        FT yn = ssprk33_combine(stage, u, y[v], dt, tend[v]);
+                        Ys[sidx(v, k)] = yn;
+                        if (stage == 2) A.Y[gi] = yn;
+                    }
+                }
+            }
+        }
+        // next stage's pass 1 only touches own levels of Ys and writes vt/act arrays, whose
+        // neighbours were pre-read above; a barrier is still needed when there is no pass 1
+        if constexpr (!L::has_pr) __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ Box model
+// One thread per box, the whole state in registers for all nsteps x 3 stages
+// (src/BoxModel/ode_utils.jl:10-22: zero -> thermo -> precip -> precip sources).
+template <class FT, int MOIST, int PRECIP, class PRMSRC>
+__global__ void __launch_bounds__(128) box_step_kernel(const KArgs<FT> A) {
+    using L = Lay<MOIST, PRECIP>;
+    constexpr int NV = L::NV;
+    const auto& P = PRMSRC::get();
+    const int gc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gc >= A.nc) return;
+    const size_t plane = size_t(A.ncp);  // nz == 1
+    FT u[NV], y[NV], tend[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) u[v] = A.Y[v * plane + gc];
+    const FT rho_dry = A.rho_dry[A.prof_per_column ? gc : 0];
+    const FT T = A.T[A.prof_per_column ? gc : 0];
+    const FT Ndc = A.Nd[gc];
+    const FT Naer_aux = A.aux_Naer ? A.aux_Naer[gc] : FT(0);
+    const FT dt = A.dt;
+#pragma unroll 1
+    for (int s = 0; s < A.nsteps; ++s) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) y[v] = u[v];
+#pragma unroll 1
+        for (int stage = 0; stage < 3; ++stage) {
+            Point<FT> a;
+            thermo_point<FT, MOIST, PRECIP>(P, y, rho_dry, T, a);
+            if (A.aux_Naer) a.N_aer = Naer_aux;
+            Sources<FT> src;
+            point_source_tendencies<FT, MOIST, PRECIP>(P, A.sw, a, Ndc, dt, false, FT(0), src, tend);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) y[v] = ssprk33_combine(stage, u[v], y[v], dt, tend[v]);
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) u[v] = y[v];
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) A.Y[v * plane + gc] = u[v];
+}
+
+// ------------------------------------------------------------ layout transposes
+// host layout [column][var][level] <-> device layout [var][level][column(ncp)]
+template <class FT>
+__global__ void host_to_device_layout(const FT* __restrict__ src, FT* __restrict__ dst, int nc, int ncp, int nv, int nz) {
+    __shared__ FT tile[32][33];
+    // rows = (v, k) flattened (R = nv*nz), cols = columns
+    const int R = nv * nz;
+    int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int cc = c0 + i, r = r0 + threadIdx.x;
+        tile[i][threadIdx.x] = (cc < nc && r < R) ? src[size_t(cc) * R + r] : FT(0);
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int r = r0 + i, cc = c0 + threadIdx.x;
+        if (r < R && cc < ncp) dst[size_t(r) * ncp + cc] = tile[threadIdx.x][i];
+    }
+}
+template <class FT>
+__global__ void device_to_host_layout(const FT* __restrict__ src, FT* __restrict__ dst, int nc, int ncp, int nv, int nz) {
+    __shared__ FT tile[32][33];
+    const int R = nv * nz;
+    int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int r = r0 + i, cc = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < R && cc < ncp) ? src[size_t(r) * ncp + cc] : FT(0);
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int cc = c0 + i, r = r0 + threadIdx.x;
+        if (cc < nc && r < R) dst[size_t(cc) * R + r] = tile[threadIdx.x][i];
+    }
+}
+
+}  // namespace kid

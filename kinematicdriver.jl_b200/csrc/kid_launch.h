@@ -1,0 +1,28 @@
+// Host-side launch interface between the C ABI (kid_capi.cu) and the per-precipitation-style
+// kernel translation units (kid_inst.cu compiled once per KID_PRECIP value, so the four
+// heavy instantiation sets build in parallel and each owns its __constant__ parameter block).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "kid_kernels.cuh"
+
+namespace kid {
+
+struct LaunchTable {
+    cudaError_t (*upload_params_f)(const DevParams<float>&, cudaStream_t);
+    cudaError_t (*upload_params_d)(const DevParams<double>&, cudaStream_t);
+    // K1D / col_sed / (diag of) Box: tile kernel.  diag = false: step; true: rhs / aux mode
+    cudaError_t (*k1d_f)(int moisture, bool diag, const KArgs<float>&, cudaStream_t);
+    cudaError_t (*k1d_d)(int moisture, bool diag, const KArgs<double>&, cudaStream_t);
+    cudaError_t (*box_f)(int moisture, const KArgs<float>&, cudaStream_t);
+    cudaError_t (*box_d)(int moisture, const KArgs<double>&, cudaStream_t);
+    size_t (*k1d_smem_f)(int moisture, int nz, int C);
+    size_t (*k1d_smem_d)(int moisture, int nz, int C);
+};
+
+const LaunchTable* launch_table_precip0();
+const LaunchTable* launch_table_precip1();
+const LaunchTable* launch_table_precip2();
+const LaunchTable* launch_table_precip3();
+
+}  // namespace kid

@@ -253,3 +253,36 @@ def box_ensemble_case(FT=np.float64, nc: int = 1024, seed: int = 20240601, n_ic:
     qt = 1e-3 * (0.5 + 1.5 * (iq + 0.5) / n_ic)
     Nd = 10.0 ** (7.5 + (iN + 0.5) / n_ic)
     return box_case(FT, nc=nc, device=device, qt=qt, Nd=Nd, **options)
+
+
+def custom_case(FT, model: int, moisture_choice: str, precipitation_choice: str, ip: dict, *, z_min=0.0, z_max=1.0,
+                dt=1.0, nc: int = 1, rain_formation_choice=None, sedimentation_choice=None, q_surf=0.0, device: int = 0,
+                **toml_kw) -> Case:
+    """A Case from a hand-written initial-profile dict `ip` of per-level arrays (or scalars for one
+    level) — the `_ip` NamedTuple fixtures of the reference's unit tests
+    (test/unit_tests/common_unit_test.jl:163-197)."""
+    FT = np.dtype(FT).type
+    td = PR.override_toml_dict(FT=FT, **toml_kw)
+    common_params = PR.create_common_parameters(td)
+    kid_params = PR.create_kid_parameters(td)
+    moisture = ET.get_moisture_type(moisture_choice, td)
+    precip = ET.get_precipitation_type(precipitation_choice, td, rain_formation_choice=rain_formation_choice,
+                                       sedimentation_choice=sedimentation_choice)
+    ipa = {k: np.atleast_1d(np.asarray(v, dtype=FT)) for k, v in ip.items()}
+    nz = ipa["ρq_tot"].size
+    names = ET.state_variable_names(moisture, precip)
+    Y_col = np.stack([np.broadcast_to(ipa.get(n, np.zeros(nz, FT)), (nz,)) for n in names]).astype(FT)
+    cfg = make_config(
+        model=model, moisture=moisture.kid_enum, precip=precip.kid_enum, rain_formation=precip.rain_formation,
+        sedimentation=precip.sedimentation, float_type=float_enum(FT), nz=nz, nc=nc,
+        precip_sources=int(common_params.precip_sources), precip_sinks=int(common_params.precip_sinks),
+        open_system_activation=int(common_params.open_system_activation),
+        local_activation=int(common_params.local_activation),
+        qtot_flux_correction=int(kid_params.qtot_flux_correction), device=device,
+        z_min=float(z_min), z_max=float(z_max), dt=float(dt))
+    zc, _ = make_function_space(FT, z_min, z_max, nz)
+    return Case(cfg=cfg, params=PR.flatten_params(td, precip.rain_formation),
+                ρ_dry=np.broadcast_to(ipa["ρ_dry"], (nz,)).astype(FT), T=np.broadcast_to(ipa["T"], (nz,)).astype(FT),
+                Y0=np.broadcast_to(Y_col, (nc,) + Y_col.shape).copy(), var_names=names,
+                col_scalars={COL_Q_SURF: np.full(nc, q_surf, dtype=FT)}, z_centers=zc,
+                meta=dict(toml=td, moisture=moisture, precip=precip))

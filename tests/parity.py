@@ -1,0 +1,38 @@
+"""Shared parity metric of the test-suite.
+
+For every prognostic variable v the error is
+    err_v = max |a_v - b_v| / max( max|b_v| , FLOOR * group_scale )
+where group_scale is the largest magnitude among the variables of the same kind (mass
+densities ρq_* or number densities N_*).  The floor keeps fields that are pure round-off
+noise in the reference formulation itself (e.g. ρq_sno in a warm run, N_aer in the box
+model: `triangle_inequality_limiter(0, M) = M - sqrt(M*M)` is ±ulp(M), not 0) from
+dominating a relative measure."""
+import numpy as np
+
+FLOOR = 1e-6
+
+
+def group_of(name: str) -> str:
+    return "N" if name.startswith("N_") else "q"
+
+
+def errors(a, b, var_names):
+    """a, b: [nc, nvars, nz] -> {var: err}"""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = {}
+    for i, v in enumerate(var_names):
+        g = group_of(v)
+        scale[g] = max(scale.get(g, 0.0), float(np.max(np.abs(b[:, i]))))
+    out = {}
+    for i, v in enumerate(var_names):
+        den = max(float(np.max(np.abs(b[:, i]))), FLOOR * scale[group_of(v)], 1e-300)
+        out[v] = float(np.max(np.abs(a[:, i] - b[:, i])) / den)
+    return out
+
+
+def field_error(a, b, floor_scale=0.0):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    den = max(float(np.max(np.abs(b))), floor_scale, 1e-300)
+    return float(np.max(np.abs(a - b)) / den)
