@@ -191,7 +191,8 @@ int choose_tile(kid_handle* h) {
     }
     size_t s = h->f64 ? h->lt->k1d_smem_d(moist, nz, C) : h->lt->k1d_smem_f(moist, nz, C);
     if (s > size_t(max_smem)) return fail("column too tall for one shared-memory tile (nz too large)");
-    int NW = std::max(1, std::min(512 / C, nz / 3));
+    int maxt = h->f64 ? tile_max_threads<double>() : tile_max_threads<float>();
+    int NW = std::max(1, std::min(maxt / C, nz / 3));
     if (h->cfg.reserved[0] > 0) NW = std::max(1, std::min(NW, int(h->cfg.reserved[0])));  // tuning override
     h->C = C;
     h->NW = NW;

@@ -24,15 +24,29 @@ namespace kid {
     X(snow_gam_m1) X(snow_gam_m2) X(snow_gam_m3)                                    \
     X(ice_gam_m)                                                                    \
     X(sb_gam_vent1)    /* Γ(5/2 + 3β/2)               CM2.rain_evaporation      */  \
-    X(sb_gam_a1)       /* Γ(a+1), a = -1/2 + 3β/2     (upper incomplete Γ recurrence) */
+    X(sb_gam_a1)       /* Γ(a+1), a = -1/2 + 3β/2     (upper incomplete Γ recurrence) */  \
+    /* parameter-only sub-expressions hoisted out of the per-point formulas */      \
+    X(sb_rc)           /* -1/(2cR) log(aR/bR)         CM2.rain_terminal_velocity */ \
+    X(sb_c6pr)         /* (6/π/ρw)^(1/3)                                          */ \
+    X(sc3)             /* (ν_air/D_vapor)^(1/3)       ventilation factors         */ \
+    X(sb_av0) X(sb_bv0) X(sb_av1) X(sb_bv1) /* evaporation ventilation prefactors */ \
+    X(sb_acnv_pref)    /* kcc/20/x*·(ν+2)(ν+4)/(ν+1)²                             */ \
+    X(sb_sc_pref)      /* kcc(ν+2)/(ν+1)                                          */ \
+    X(arg_lns) X(arg_f) X(arg_gg) X(arg_Sm_pref) /* ARG2000 mode constants        */ \
+    X(rain_r0_pow) X(snow_r0_pow) X(ice_r0_pow) /* r0^(me+Δm)                     */ \
+    X(rain_li_exp) X(snow_li_exp) X(ice_li_exp) /* 1/(me+Δm+1)                    */
 
 template <class FT>
-struct DevParams {
+struct DevParamsBody {
 #define KID_X_FIELD(name) FT name;
     KID_PARAM_LIST(KID_X_FIELD)
     KID_DERIVED_LIST(KID_X_FIELD)
 #undef KID_X_FIELD
-    FT pad_to_odd[2];  // keeps sizeof/sizeof(FT) odd: conflict-free when staged per column in shared memory
+};
+template <class FT>
+struct DevParams : DevParamsBody<FT> {
+    // keeps sizeof/sizeof(FT) odd: conflict-free when staged per column in shared memory
+    FT pad_to_odd[(sizeof(DevParamsBody<FT>) / sizeof(FT)) % 2 == 0 ? 1 : 2];
 };
 
 static_assert((sizeof(DevParams<float>) / sizeof(float)) % 2 == 1, "DevParams word count must be odd");
@@ -63,7 +77,27 @@ inline void fill_dev_params(DevParams<FT>& P, const double* table) {
     P.ice_gam_m = G(P.ice_me + P.ice_dm + FT(1));
     P.sb_gam_vent1 = G(FT(2.5) + FT(1.5) * P.sb_beta);
     P.sb_gam_a1 = G(FT(-0.5) + FT(1.5) * P.sb_beta + FT(1));
-    P.pad_to_odd[0] = P.pad_to_odd[1] = FT(0);
+    P.sb_rc = -FT(1) / (FT(2) * P.sb_cR) * FT(std::log(double(P.sb_aR / P.sb_bR)));
+    P.sb_c6pr = FT(std::cbrt(double(FT(6) / FT(M_PI) / P.sb_rho_w)));
+    P.sc3 = FT(std::cbrt(double(P.air_nu_air / P.air_D_vapor)));
+    P.sb_av0 = P.sb_av / FT(std::pow(6.0, double(FT(-2) / FT(3))));
+    P.sb_bv0 = P.sb_bv / FT(std::pow(6.0, double(P.sb_beta / FT(2) - FT(0.5))));
+    P.sb_av1 = P.sb_av * FT(1) / FT(std::cbrt(6.0));
+    P.sb_bv1 = P.sb_bv * P.sb_gam_vent1 / FT(std::pow(6.0, double(P.sb_beta / FT(2) + FT(0.5))));
+    P.sb_acnv_pref = P.sb_kcc / FT(20) / P.sb_x_star * (P.sb_nu_c + FT(2)) * (P.sb_nu_c + FT(4)) /
+                     ((P.sb_nu_c + FT(1)) * (P.sb_nu_c + FT(1)));
+    P.sb_sc_pref = P.sb_kcc * (P.sb_nu_c + FT(2)) / (P.sb_nu_c + FT(1));
+    P.arg_lns = FT(std::log(double(P.kid_std_dry)));
+    P.arg_f = P.arg_f1 * FT(std::exp(double(P.arg_f2 * P.arg_lns * P.arg_lns)));
+    P.arg_gg = P.arg_g1 + P.arg_g2 * P.arg_lns;
+    P.arg_Sm_pref = FT(2) / FT(std::sqrt(double(P.kid_kappa))) / FT(std::pow(double(FT(3) * P.kid_r_dry), 1.5));
+    P.rain_r0_pow = FT(std::pow(double(P.rain_r0), double(P.rain_me + P.rain_dm)));
+    P.snow_r0_pow = FT(std::pow(double(P.snow_r0), double(P.snow_me + P.snow_dm)));
+    P.ice_r0_pow = FT(std::pow(double(P.ice_r0), double(P.ice_me + P.ice_dm)));
+    P.rain_li_exp = FT(1) / (P.rain_me + P.rain_dm + FT(1));
+    P.snow_li_exp = FT(1) / (P.snow_me + P.snow_dm + FT(1));
+    P.ice_li_exp = FT(1) / (P.ice_me + P.ice_dm + FT(1));
+    for (FT& x : P.pad_to_odd) x = FT(0);
 }
 
 // run-time switches shared by every kernel (uniform across the grid)

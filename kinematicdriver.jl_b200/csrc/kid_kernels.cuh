@@ -21,6 +21,17 @@
 // (test/experiments/KiD_driver/run_KiD_simulation.jl:159-166).
 #pragma once
 #include <climits>
+// threads per tile CTA: Float32 fits the sweep in 64 registers (1024 threads = 32 warps per SM);
+// Float64 needs the full 128 (512 threads)
+#ifndef KID_TILE_MAXT_F32
+#define KID_TILE_MAXT_F32 1024
+#endif
+#ifndef KID_TILE_MAXT_F64
+#define KID_TILE_MAXT_F64 512
+#endif
+namespace kid {
+template <class FT> constexpr int tile_max_threads() { return sizeof(FT) == 4 ? KID_TILE_MAXT_F32 : KID_TILE_MAXT_F64; }
+}
 #include <type_traits>
 
 #include "kid_physics.cuh"
@@ -169,7 +180,7 @@ inline size_t k1d_tile_smem_bytes(int nz, int C) {
 }
 
 template <class FT, int MOIST, int PRECIP, bool DIAG, class PRMSRC>
-__global__ void __launch_bounds__(512, 1) k1d_tile_kernel(const KArgs<FT> A) {
+__global__ void __launch_bounds__(tile_max_threads<FT>(), 1) k1d_tile_kernel(const KArgs<FT> A) {
     using L = Lay<MOIST, PRECIP>;
     using M = Mth<FT>;
     constexpr int NV = L::NV;
@@ -241,7 +252,9 @@ __global__ void __launch_bounds__(512, 1) k1d_tile_kernel(const KArgs<FT> A) {
                     vt2s[kidx(k)] = v2;
                     if constexpr (L::is2m) {
                         FT S_Nl = FT(0);
-                        if (k1d) {
+                        // non-local activation keeps only the LOWEST activating level, so once this thread has a
+                        // candidate its higher levels can never be selected: skip their ARG evaluation
+                        if (k1d && (A.sw.local_activation || first == INT_MAX)) {
                             FT p = pressure_point<FT, MOIST, PRECIP>(P, a);
                             S_Nl = aerosol_activation_rate<FT>(P, A.sw, a.q_tot, a.q_liq + a.q_rai, a.q_ice,
                                                                a.N_liq + a.N_rai, a.N_aer, a.T, p, a.rho, rw, dt);

@@ -63,7 +63,7 @@ def dtype_of(float_type: int):
 
 
 _LIB = None
-LIB_PATH = Path(__file__).resolve().parents[1] / "csrc" / "libkid_cuda.so"
+LIB_PATH = Path(os.environ.get("KID_CUDA_LIB") or Path(__file__).resolve().parents[1] / "csrc" / "libkid_cuda.so")
 
 
 class KidCudaError(RuntimeError):

@@ -36,3 +36,23 @@ def field_error(a, b, floor_scale=0.0):
     b = np.asarray(b, dtype=np.float64)
     den = max(float(np.max(np.abs(b))), floor_scale, 1e-300)
     return float(np.max(np.abs(a - b)) / den)
+
+
+def rhs_errors(a, b, Y, var_names, dt, FT):
+    """Tendency parity: err_v = max|a_v - b_v| / max(max|b_v|, 1000·eps(FT)·state_scale/dt).
+    A tendency that is itself a difference of nearly equal numbers (e.g. condensation at equilibrium,
+    (q_eq - q_liq)/τ ≈ 0) carries absolute noise ~eps·|q|/τ; it is measured against the change it
+    produces in the state over one step, not against its own (vanishing) magnitude."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64)
+    eps = float(np.finfo(FT).eps)
+    scale = {}
+    for i, v in enumerate(var_names):
+        g = group_of(v)
+        scale[g] = max(scale.get(g, 0.0), float(np.max(np.abs(Y[:, i]))))
+    out = {}
+    for i, v in enumerate(var_names):
+        den = max(float(np.max(np.abs(b[:, i]))), 1000.0 * eps * scale[group_of(v)] / dt, 1e-300)
+        out[v] = float(np.max(np.abs(a[:, i] - b[:, i])) / den)
+    return out
