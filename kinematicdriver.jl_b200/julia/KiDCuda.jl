@@ -1,0 +1,136 @@
+"""
+    KiDCuda — thin `ccall` shim that lets KinematicDriver.jl's drivers run the rhs + SSPRK33 loop on
+    libkid_cuda.so (include/kid_cuda.h) instead of `ODE.solve(problem, ODE.SSPRK33(); ...)`.
+
+UNTESTED IN THIS REPOSITORY'S CI: no Julia toolchain exists in the build image.  The Python host
+mirror (kid_b200/) exercises exactly the same C ABI and is what the parity tests drive.
+
+Usage inside e.g. test/experiments/KiD_driver/run_KiD_simulation.jl, replacing lines 159-166:
+
+    sol = KiDCuda.solve(moisture, precip, Y, aux, (FT(opts["t_ini"]), FT(opts["t_end"]));
+                        model = :K1D, dt = TS.dt, saveat = TS.dt_io, space = space, callback = affect_output!)
+"""
+module KiDCuda
+
+import ClimaCore as CC
+import KinematicDriver.Common as CO
+
+const libkid = get(ENV, "KID_CUDA_LIB", "libkid_cuda.so")
+
+# ---------------------------------------------------------------- C structs (include/kid_cuda.h)
+Base.@kwdef mutable struct KidConfig
+    abi_version::Int32 = 1
+    params_version::Int32 = 1
+    model::Int32 = 1
+    moisture::Int32 = 0
+    precip::Int32 = 0
+    rain_formation::Int32 = 0
+    sedimentation::Int32 = 0
+    float_type::Int32 = 1
+    nz::Int32 = 1
+    nc::Int32 = 1
+    helem::Int32 = 0
+    npoly::Int32 = 0
+    helem_global::Int32 = 0
+    helem_offset::Int32 = 0
+    precip_sources::Int32 = 1
+    precip_sinks::Int32 = 1
+    open_system_activation::Int32 = 0
+    local_activation::Int32 = 0
+    qtot_flux_correction::Int32 = 0
+    device::Int32 = 0
+    reserved::NTuple{8, Int32} = ntuple(_ -> Int32(0), 8)
+    z_min::Float64 = 0.0
+    z_max::Float64 = 1.0
+    dt::Float64 = 1.0
+    domain_width::Float64 = 0.0
+    domain_height::Float64 = 0.0
+end
+
+struct KidError <: Exception
+    msg::String
+end
+check(rc) = rc == 0 ? nothing : throw(KidError(unsafe_string(ccall((:kid_last_error, libkid), Cstring, ()))))
+
+# ---------------------------------------------------------------- style -> enum
+moisture_enum(::CO.EquilibriumMoisture) = Int32(0)
+moisture_enum(::CO.NonEquilibriumMoisture) = Int32(1)
+moisture_enum(ms) = error("$(typeof(ms).name.name) is not on the device hot path of libkid_cuda (no CPU fallback)")
+precip_enum(::CO.NoPrecipitation) = Int32(0)
+precip_enum(::CO.Precipitation0M) = Int32(1)
+precip_enum(::CO.Precipitation1M) = Int32(2)
+precip_enum(::CO.Precipitation2M) = Int32(3)
+precip_enum(ps) = error("$(typeof(ps).name.name) is not on the device hot path of libkid_cuda (no CPU fallback)")
+
+# The flat parameter table: every entry of include/kid_params.h, read from the structs the reference
+# already built (thermo_params, air_params, activation_params, kid_params, common_params, the style
+# structs).  `param_table` must list the names in the enum order of kid_params.h; the values are
+# whatever the reference structs hold (already of type FT), widened to Float64.
+function param_table(aux, moisture, precip)::Vector{Float64}
+    tp, ap, act, kp, cp = aux.thermo_params, aux.air_params, aux.activation_params, aux.kid_params, aux.common_params
+    TDP = CO.TD.Parameters
+    v = Float64[]
+    # td_*
+    append!(v, Float64[TDP.T_0(tp), TDP.MSLP(tp), TDP.press_triple(tp), TDP.T_triple(tp), TDP.T_freeze(tp),
+                       TDP.T_icenuc(tp), TDP.pow_icenuc(tp), TDP.R_d(tp), TDP.R_v(tp), TDP.cp_d(tp), TDP.cp_v(tp),
+                       TDP.cp_l(tp), TDP.cp_i(tp), TDP.LH_v0(tp), TDP.LH_s0(tp), TDP.grav(tp)])
+    # air_*, arg_*, kid_*, com_*
+    append!(v, Float64[ap.K_therm, ap.D_vapor, ap.ν_air])
+    append!(v, Float64[act.σ, act.M_w, act.R, act.ρ_w, act.ρ_i, act.g, act.f1, act.f2, act.g1, act.g2, act.p1, act.p2])
+    append!(v, Float64[kp.w1, kp.t1, kp.r_dry, kp.std_dry, kp.κ, cp.prescribed_Nd])
+    # ... the remaining blocks (ne_*, p0m_*, rain_*, snow_*, ice_*, ce_*, rf_*, sb_*, num_fcc_scale) are filled the
+    # same way from moisture.liquid/ice, precip.params, precip.rain/snow/ice/ce/rain_formation/sedimentation;
+    # see kid_b200/parameters.py::flatten_params for the field-by-field map.
+    error("param_table: complete the struct-field map for the CloudMicrophysics version in use")
+    return v
+end
+
+# ---------------------------------------------------------------- the ODE.solve replacement
+"""
+    solve(moisture, precip, Y, aux, tspan; model, dt, saveat, callback = nothing, columns = 1)
+
+Uploads `parent(Y)` (host layout [column][variable][level] == ClimaCore's column parent array) and the
+time-invariant ρ_dry/T of `aux.thermo_variables`, steps on the device between save times, downloads the
+state into `Y` at every save time, calls `callback(Y, aux_getter, t)` there, and returns `(; t, u)`.
+"""
+function solve(moisture, precip, Y, aux, tspan; model::Symbol, dt, saveat, nz, z_min, z_max, callback = nothing, device = 0)
+    FT = eltype(parent(Y))
+    cfg = KidConfig(model = Int32(Dict(:Box => 0, :K1D => 1, :K1D_col_sed => 2, :K2D => 3)[model]),
+                    moisture = moisture_enum(moisture), precip = precip_enum(precip),
+                    float_type = Int32(FT == Float32 ? 0 : 1), nz = Int32(nz), nc = Int32(1),
+                    precip_sources = Int32(aux.common_params.precip_sources), precip_sinks = Int32(aux.common_params.precip_sinks),
+                    open_system_activation = Int32(aux.common_params.open_system_activation),
+                    local_activation = Int32(aux.common_params.local_activation),
+                    qtot_flux_correction = Int32(hasproperty(aux, :kid_params) ? aux.kid_params.qtot_flux_correction : 0),
+                    device = Int32(device), z_min = z_min, z_max = z_max, dt = dt)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:kid_create, libkid), Cint, (Ref{KidConfig}, Ref{Ptr{Cvoid}}), cfg, h))
+    try
+        p = param_table(aux, moisture, precip)
+        check(ccall((:kid_set_params, libkid), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32, Int32, Ptr{Int32}), h[], p, length(p), 1, C_NULL))
+        ρ_dry = Array(vec(parent(aux.thermo_variables.ρ_dry)))
+        T = Array(vec(parent(aux.thermo_variables.T)))
+        check(ccall((:kid_set_profiles, libkid), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32), h[], ρ_dry, T, 0))
+        if hasproperty(aux, :q_surf)
+            check(ccall((:kid_set_column_scalar, libkid), Cint, (Ptr{Cvoid}, Int32, Ptr{Cvoid}), h[], 1, FT[aux.q_surf]))
+        end
+        Yh = parent(Y)                       # (nz, nvars) column-major == [variable][level]
+        check(ccall((:kid_set_state, libkid), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), h[], Yh))
+        ts, us = FT[], typeof(Y)[]
+        t = FT(tspan[1])
+        while t < tspan[2]
+            n = Int(round(min(saveat, tspan[2] - t) / dt))
+            check(ccall((:kid_step, libkid), Cint, (Ptr{Cvoid}, Float64, Int32), h[], Float64(t), n))
+            t += n * dt
+            check(ccall((:kid_get_state, libkid), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), h[], Yh))
+            push!(ts, t); push!(us, copy(Y))
+            callback === nothing || callback(Y, (field, out) -> check(ccall((:kid_get_aux, libkid), Cint,
+                (Ptr{Cvoid}, Float64, Int32, Ptr{Cvoid}), h[], Float64(t), field, out)), t)
+        end
+        return (; t = ts, u = us)
+    finally
+        ccall((:kid_destroy, libkid), Cvoid, (Ptr{Cvoid},), h[])
+    end
+end
+
+end # module
