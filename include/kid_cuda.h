@@ -174,6 +174,11 @@ int kid_k2d_stage_begin(kid_handle_t* h, double t0, int32_t stage);
 int kid_k2d_edge_buffers(kid_handle_t* h, void** send_left, void** send_right, void** recv_left,
                          void** recv_right, size_t* edge_count);
 int kid_k2d_stage_end(kid_handle_t* h, int32_t stage);
+/* neighbour exchange between two handles driven by the SAME process (one process steering several
+ * sub-domains / GPUs): right-edge of `left` -> recv_left of `right`, left-edge of `right` -> recv_right of
+ * `left`, ordered on both handles' streams (peer copies over NVLink when the handles sit on different GPUs).
+ * With separate processes the caller exchanges the buffers of kid_k2d_edge_buffers itself (NCCL send/recv). */
+int kid_k2d_exchange_local(kid_handle_t* left, kid_handle_t* right);
 
 /* plumbing */
 int kid_synchronize(kid_handle_t* h);

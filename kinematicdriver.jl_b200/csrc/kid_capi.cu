@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 
+#include "kid_k2d.cuh"
 #include "kid_launch.h"
 
 using namespace kid;
@@ -61,6 +62,13 @@ struct kid_handle {
     std::vector<double> params;
     bool params_set = false, profiles_set = false, state_set = false;
     int C = 32, NW = 1;
+    // K2D
+    void *U = nullptr, *S = nullptr, *prev_aux = nullptr, *xc = nullptr, *out2 = nullptr;
+    void *send_left = nullptr, *send_right = nullptr, *recv_left = nullptr, *recv_right = nullptr;
+    int Nq = 0, nfields = 0;
+    K2DField fields[KID_MAX_DSS];
+    double gll_x[KID_MAX_NQ], gll_w[KID_MAX_NQ], gll_D[KID_MAX_NQ * KID_MAX_NQ];
+    int i_tot = 0, i_liq = -1, i_ice = -1, i_rai = -1, i_sno = -1, i_Nl = -1, i_Nr = -1, i_Na = -1;
 };
 
 namespace {
@@ -165,6 +173,35 @@ KArgs<FT> make_args(kid_handle* h, double t0, int nsteps, int diag_mode, int fie
     a.dz = FT((h->cfg.z_max - h->cfg.z_min) / h->cfg.nz);
     a.t0 = t0;
     a.sw = h->sw;
+    a.xc = (const FT*)h->xc;
+    a.prev_aux = (FT*)h->prev_aux;
+    a.outS = (FT*)h->S;
+    a.update_prev = 0;
+    a.width = h->cfg.domain_width;
+    a.height = h->cfg.domain_height;
+    a.z_min = h->cfg.z_min;
+    return a;
+}
+
+template <class FT>
+K2DArgs<FT> make_k2d_args(kid_handle* h, double t_stage, int stage, int use_recv, int rhs_only) {
+    K2DArgs<FT> a{};
+    a.Y = (FT*)h->Y; a.U = (FT*)h->U; a.dY = (FT*)h->out; a.S = (FT*)h->S; a.out = (FT*)h->out2;
+    a.rho_dry = (const FT*)h->rho_dry; a.w1 = (const FT*)h->w1; a.xc = (const FT*)h->xc;
+    a.send_left = (FT*)h->send_left; a.send_right = (FT*)h->send_right;
+    a.recv_left = (const FT*)h->recv_left; a.recv_right = (const FT*)h->recv_right;
+    a.nz = h->cfg.nz; a.nc = h->cfg.nc; a.ncp = h->ncp; a.nv = h->nv; a.helem = h->cfg.helem; a.Nq = h->Nq;
+    a.prof_per_column = h->prof_per_column;
+    a.nfields = h->nfields;
+    for (int f = 0; f < h->nfields; ++f) a.fields[f] = h->fields[f];
+    a.i_tot = h->i_tot; a.i_rai = h->i_rai; a.i_sno = h->i_sno; a.precip = h->cfg.precip;
+    a.stage = stage; a.use_recv = use_recv; a.rhs_only = rhs_only;
+    a.dt = FT(h->cfg.dt); a.t = FT(t_stage); a.t1 = FT(h->params[KID_P_kid_t1]);
+    a.z_min = FT(h->cfg.z_min); a.dz = FT((h->cfg.z_max - h->cfg.z_min) / h->cfg.nz);
+    a.width = h->cfg.domain_width; a.height = h->cfg.domain_height;
+    a.dxe = h->cfg.domain_width / h->cfg.helem_global;
+    for (int i = 0; i < h->Nq * h->Nq; ++i) a.D[i] = FT(h->gll_D[i]);
+    for (int i = 0; i < h->Nq; ++i) a.w[i] = FT(h->gll_w[i]);
     return a;
 }
 
@@ -199,10 +236,17 @@ int choose_tile(kid_handle* h) {
     return 0;
 }
 
-int launch_tile(kid_handle* h, double t0, int nsteps, int diag_mode, int field) {
+int launch_tile(kid_handle* h, double t0, int nsteps, int diag_mode, int field, int update_prev = 0) {
     cudaError_t e;
-    if (h->f64) e = h->lt->k1d_d(h->cfg.moisture, diag_mode != 0, make_args<double>(h, t0, nsteps, diag_mode, field), h->stream);
-    else e = h->lt->k1d_f(h->cfg.moisture, diag_mode != 0, make_args<float>(h, t0, nsteps, diag_mode, field), h->stream);
+    if (h->f64) {
+        auto a = make_args<double>(h, t0, nsteps, diag_mode, field);
+        a.update_prev = update_prev;
+        e = h->lt->k1d_d(h->cfg.moisture, diag_mode != 0, a, h->stream);
+    } else {
+        auto a = make_args<float>(h, t0, nsteps, diag_mode, field);
+        a.update_prev = update_prev;
+        e = h->lt->k1d_f(h->cfg.moisture, diag_mode != 0, a, h->stream);
+    }
     if (e != cudaSuccess) return fail(std::string("k1d_tile_kernel launch: ") + cudaGetErrorString(e));
     h->launches++;
     return 0;
@@ -213,6 +257,79 @@ int launch_box(kid_handle* h, double t0, int nsteps) {
     else e = h->lt->box_f(h->cfg.moisture, make_args<float>(h, t0, nsteps, 0, 0), h->stream);
     if (e != cudaSuccess) return fail(std::string("box_step_kernel launch: ") + cudaGetErrorString(e));
     h->launches++;
+    return 0;
+}
+
+// ---- K2D: one SSPRK33 stage = vertical/pointwise rhs (tile kernel) -> horizontal weak divergence + edge pack
+//      -> [neighbour exchange by the caller] -> DSS + stage combine
+double k2d_stage_time(kid_handle* h, double t_step, int stage) {
+    // the stage times as OrdinaryDiffEq forms them in FLOAT_TYPE arithmetic
+    if (h->f64) { double t = t_step, dt = h->cfg.dt; return stage == 0 ? t : (stage == 1 ? t + dt : t + dt / 2.0); }
+    float t = float(t_step), dt = float(h->cfg.dt);
+    return double(stage == 0 ? t : (stage == 1 ? t + dt : t + dt / 2.0f));
+}
+int k2d_begin(kid_handle* h, double t_stage) {
+    if (ensure_out(h, state_elems(h) * h->fsz)) return 1;
+    if (launch_tile(h, t_stage, 1, 1, 0, 1)) return 1;
+    dim3 block(64), grid((h->cfg.helem + 63) / 64, h->cfg.nz);
+    if (h->f64) k2d_hdiv_kernel<double><<<grid, block, 0, h->stream>>>(make_k2d_args<double>(h, t_stage, 0, 0, 0));
+    else k2d_hdiv_kernel<float><<<grid, block, 0, h->stream>>>(make_k2d_args<float>(h, t_stage, 0, 0, 0));
+    KID_CUDA(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+int k2d_end(kid_handle* h, int stage, int use_recv, int rhs_only) {
+    dim3 block(128), grid((h->cfg.nc + 127) / 128, h->cfg.nz);
+    if (h->f64) k2d_dss_update_kernel<double><<<grid, block, 0, h->stream>>>(make_k2d_args<double>(h, 0.0, stage, use_recv, rhs_only));
+    else k2d_dss_update_kernel<float><<<grid, block, 0, h->stream>>>(make_k2d_args<float>(h, 0.0, stage, use_recv, rhs_only));
+    KID_CUDA(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+int k2d_setup(kid_handle* h) {
+    const kid_config_t& c = h->cfg;
+    if (c.npoly < 1 || c.npoly + 1 > KID_MAX_NQ) return fail("K2D: npoly must be in [1, 7]");
+    if (c.helem < 1 || c.helem_global < c.helem || c.helem_offset < 0 || c.helem_offset + c.helem > c.helem_global)
+        return fail("K2D: inconsistent helem / helem_global / helem_offset");
+    if (c.nc != c.helem * (c.npoly + 1)) return fail("K2D: nc must equal helem * (npoly + 1)");
+    if (!(c.domain_width > 0) || !(c.domain_height > 0)) return fail("K2D: domain_width and domain_height must be positive");
+    h->Nq = c.npoly + 1;
+    gll_rule(h->Nq, h->gll_x, h->gll_w, h->gll_D);
+    // state variable indices (src/Common/ode_utils.jl:23-54)
+    int n = 1;
+    if (c.moisture == KID_MOIST_NONEQ) { h->i_liq = n++; h->i_ice = n++; }
+    if (c.precip >= KID_PRECIP_1M) { h->i_rai = n++; h->i_sno = n++; }
+    if (c.precip == KID_PRECIP_2M) { h->i_Nl = n++; h->i_Nr = n++; h->i_Na = n++; }
+    // DSS'd / horizontally advected fields (src/K2DModel/tendency.jl:57-213)
+    int f = 0;
+    h->fields[f++] = {h->i_tot, 0, h->i_tot};
+    if (c.moisture == KID_MOIST_NONEQ) { h->fields[f++] = {h->i_liq, 0, h->i_liq}; h->fields[f++] = {h->i_ice, 0, h->i_ice}; }
+    if (c.precip == KID_PRECIP_1M) { h->fields[f++] = {h->i_rai, 1, 0}; h->fields[f++] = {h->i_sno, 1, 1}; }
+    if (c.precip == KID_PRECIP_2M) { h->fields[f++] = {h->i_Nr, 0, h->i_Nr}; h->fields[f++] = {h->i_rai, 1, 0}; }
+    h->nfields = f;
+    size_t st = state_elems(h) * h->fsz, plane = size_t(c.nz) * h->ncp * h->fsz, edge = size_t(KID_MAX_DSS) * c.nz * h->fsz;
+    KID_CUDA(cudaMalloc(&h->U, st));
+    KID_CUDA(cudaMalloc(&h->out2, st));
+    KID_CUDA(cudaMalloc(&h->S, 2 * plane));
+    KID_CUDA(cudaMalloc(&h->prev_aux, 3 * plane));
+    KID_CUDA(cudaMemsetAsync(h->S, 0, 2 * plane, h->stream));
+    KID_CUDA(cudaMemsetAsync(h->prev_aux, 0, 3 * plane, h->stream));
+    for (void** p : {&h->send_left, &h->send_right, &h->recv_left, &h->recv_right}) {
+        KID_CUDA(cudaMalloc(p, edge));
+        KID_CUDA(cudaMemsetAsync(*p, 0, edge, h->stream));
+    }
+    KID_CUDA(cudaMalloc(&h->xc, size_t(h->ncp) * h->fsz));
+    const double dxe = c.domain_width / c.helem_global;
+    std::vector<double> x(h->ncp, 0.0);
+    for (int e = 0; e < c.helem; ++e)
+        for (int i = 0; i < h->Nq; ++i) x[e * h->Nq + i] = (e + c.helem_offset) * dxe + (h->gll_x[i] + 1.0) * 0.5 * dxe;
+    if (h->f64) {
+        KID_CUDA(cudaMemcpyAsync(h->xc, x.data(), size_t(h->ncp) * 8, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        std::vector<float> xf(x.begin(), x.end());
+        KID_CUDA(cudaMemcpyAsync(h->xc, xf.data(), size_t(h->ncp) * 4, cudaMemcpyHostToDevice, h->stream));
+    }
+    KID_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
@@ -251,7 +368,7 @@ int kid_create(const kid_config_t* cfg, kid_handle_t** out) {
     if (cfg->float_type != KID_F32 && cfg->float_type != KID_F64) return fail("invalid float_type");
     if (cfg->nz < 1 || cfg->nc < 1) return fail("nz and nc must be positive");
     if (cfg->model == KID_MODEL_BOX && cfg->nz != 1) return fail("BoxModel needs nz == 1");
-    if ((cfg->model == KID_MODEL_K1D || cfg->model == KID_MODEL_K1D_COL_SED) && cfg->nz < 3)
+    if ((cfg->model == KID_MODEL_K1D || cfg->model == KID_MODEL_K1D_COL_SED || cfg->model == KID_MODEL_K2D) && cfg->nz < 3)
         return fail("K1DModel needs at least 3 levels (Extrapolate boundary stencils)");
     if (!(cfg->dt > 0)) return fail("dt must be positive");
     if (cfg->sedimentation == KID_SED_CHEN2022) return fail("sedimentation Chen2022 is not implemented on the device path");
@@ -259,7 +376,6 @@ int kid_create(const kid_config_t* cfg, kid_handle_t** out) {
         return fail("invalid rain_formation for Precipitation1M");
     if (cfg->precip == KID_PRECIP_2M && cfg->rain_formation != KID_RF_SB2006 && cfg->rain_formation != KID_RF_SB2006NL)
         return fail("invalid rain_formation for Precipitation2M");
-    if (cfg->model == KID_MODEL_K2D) return fail("K2DModel: not implemented in this build");
     if (kid_device_count() < 1) return fail("no CUDA device visible: libkid_cuda has no CPU fallback");
     KID_CUDA(cudaSetDevice(cfg->device));
 
@@ -287,6 +403,7 @@ int kid_create(const kid_config_t* cfg, kid_handle_t** out) {
         return cleanup(fail("cudaMalloc(column scalars) failed"));
     if (cudaMemsetAsync(h->q_surf, 0, colb, h->stream) != cudaSuccess) return cleanup(fail("cudaMemset failed"));
     if (choose_tile(h)) return cleanup(1);
+    if (cfg->model == KID_MODEL_K2D && k2d_setup(h)) return cleanup(1);
     *out = h;
     return 0;
 }
@@ -294,7 +411,8 @@ int kid_create(const kid_config_t* cfg, kid_handle_t** out) {
 void kid_destroy(kid_handle_t* h) {
     if (!h) return;
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (void* p : {h->Y, h->rho_dry, h->T, h->w1, h->q_surf, h->Nd, h->aux_Naer, h->out, h->staging})
+    for (void* p : {h->Y, h->rho_dry, h->T, h->w1, h->q_surf, h->Nd, h->aux_Naer, h->out, h->staging, h->U, h->S,
+                    h->prev_aux, h->xc, h->out2, h->send_left, h->send_right, h->recv_left, h->recv_right})
         if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -368,6 +486,18 @@ int kid_set_state(kid_handle_t* h, const void* Y) {
         if (!h->aux_Naer) KID_CUDA(cudaMalloc(&h->aux_Naer, plane));
         KID_CUDA(cudaMemcpyAsync(h->aux_Naer, (const char*)h->Y + size_t(na) * plane, plane, cudaMemcpyDeviceToDevice, h->stream));
     }
+    if (h->cfg.model == KID_MODEL_K2D) {
+        if (!h->profiles_set) return fail("kid_set_profiles must be called before kid_set_state for K2DModel");
+        dim3 block(128), grid((h->cfg.nc + 127) / 128, h->cfg.nz);
+        if (h->f64)
+            k2d_init_prev_kernel<double><<<grid, block, 0, h->stream>>>((const double*)h->Y, (const double*)h->rho_dry, (double*)h->prev_aux,
+                h->cfg.nz, h->cfg.nc, h->ncp, h->prof_per_column, h->i_tot, h->i_rai, h->i_Nl, h->i_Nr);
+        else
+            k2d_init_prev_kernel<float><<<grid, block, 0, h->stream>>>((const float*)h->Y, (const float*)h->rho_dry, (float*)h->prev_aux,
+                h->cfg.nz, h->cfg.nc, h->ncp, h->prof_per_column, h->i_tot, h->i_rai, h->i_Nl, h->i_Nr);
+        KID_CUDA(cudaGetLastError());
+        h->launches++;
+    }
     KID_CUDA(cudaStreamSynchronize(h->stream));
     h->state_set = true;
     return 0;
@@ -389,6 +519,18 @@ int kid_set_steps_per_launch(kid_handle_t* h, int32_t n) {
 int kid_step(kid_handle_t* h, double t0, int32_t nsteps) {
     if (check_ready(h)) return 1;
     if (nsteps < 0) return fail("nsteps must be >= 0");
+    if (h->cfg.model == KID_MODEL_K2D) {
+        if (h->cfg.helem != h->cfg.helem_global)
+            return fail("kid_step on a decomposed K2D handle: drive the stages with kid_k2d_stage_begin/_end and exchange the edges");
+        for (int s = 0; s < nsteps; ++s) {
+            double ts = h->f64 ? t0 + double(s) * h->cfg.dt : double(float(t0 + double(s) * h->cfg.dt));
+            for (int stage = 0; stage < 3; ++stage) {
+                if (k2d_begin(h, k2d_stage_time(h, ts, stage))) return 1;
+                if (k2d_end(h, stage, 0, 0)) return 1;
+            }
+        }
+        return 0;
+    }
     int spl = h->steps_per_launch > 0 ? h->steps_per_launch : nsteps;
     int done = 0;
     while (done < nsteps) {
@@ -406,6 +548,12 @@ int kid_rhs(kid_handle_t* h, double t, void* dY_out) {
     if (!dY_out) return fail("null argument");
     if (ensure_out(h, state_elems(h) * h->fsz)) return 1;
     KID_CUDA(cudaMemsetAsync(h->out, 0, state_elems(h) * h->fsz, h->stream));
+    if (h->cfg.model == KID_MODEL_K2D) {
+        if (h->cfg.helem != h->cfg.helem_global) return fail("kid_rhs is only available on an undecomposed K2D handle");
+        if (k2d_begin(h, t)) return 1;
+        if (k2d_end(h, 0, 0, 1)) return 1;
+        return to_host_layout(h, h->out2, dY_out, h->nv);
+    }
     if (launch_tile(h, t, 1, 1, 0)) return 1;
     return to_host_layout(h, h->out, dY_out, h->nv);
 }
@@ -432,9 +580,50 @@ int kid_reduce_max(kid_handle_t* h, double t, int32_t field, double* out) {
     return 0;
 }
 
-int kid_k2d_stage_begin(kid_handle_t*, double, int32_t) { return fail("K2DModel: not implemented in this build"); }
-int kid_k2d_edge_buffers(kid_handle_t*, void**, void**, void**, void**, size_t*) { return fail("K2DModel: not implemented in this build"); }
-int kid_k2d_stage_end(kid_handle_t*, int32_t) { return fail("K2DModel: not implemented in this build"); }
+int kid_k2d_stage_begin(kid_handle_t* h, double t0, int32_t stage) {
+    if (check_ready(h)) return 1;
+    if (h->cfg.model != KID_MODEL_K2D) return fail("not a K2D handle");
+    if (stage < 0 || stage > 2) return fail("stage must be 0, 1 or 2");
+    double ts = h->f64 ? t0 : double(float(t0));
+    return k2d_begin(h, k2d_stage_time(h, ts, stage));
+}
+int kid_k2d_edge_buffers(kid_handle_t* h, void** send_left, void** send_right, void** recv_left, void** recv_right,
+                         size_t* edge_count) {
+    if (!h || h->cfg.model != KID_MODEL_K2D) return fail("not a K2D handle");
+    if (send_left) *send_left = h->send_left;
+    if (send_right) *send_right = h->send_right;
+    if (recv_left) *recv_left = h->recv_left;
+    if (recv_right) *recv_right = h->recv_right;
+    if (edge_count) *edge_count = size_t(h->nfields) * h->cfg.nz;
+    return 0;
+}
+int kid_k2d_stage_end(kid_handle_t* h, int32_t stage) {
+    if (check_ready(h)) return 1;
+    if (h->cfg.model != KID_MODEL_K2D) return fail("not a K2D handle");
+    if (stage < 0 || stage > 2) return fail("stage must be 0, 1 or 2");
+    return k2d_end(h, stage, 1, 0);
+}
+
+int kid_k2d_exchange_local(kid_handle_t* left, kid_handle_t* right) {
+    if (!left || !right) return fail("null handle");
+    if (left->cfg.model != KID_MODEL_K2D || right->cfg.model != KID_MODEL_K2D) return fail("not a K2D handle");
+    if (left->nfields != right->nfields || left->cfg.nz != right->cfg.nz || left->fsz != right->fsz)
+        return fail("kid_k2d_exchange_local: handles of different shape");
+    size_t bytes = size_t(left->nfields) * left->cfg.nz * left->fsz;
+    cudaEvent_t el, er;
+    KID_CUDA(cudaEventCreateWithFlags(&el, cudaEventDisableTiming));
+    KID_CUDA(cudaEventCreateWithFlags(&er, cudaEventDisableTiming));
+    // each copy runs on the RECEIVER's stream after the sender's pack kernel has finished
+    KID_CUDA(cudaEventRecord(el, left->stream));
+    KID_CUDA(cudaEventRecord(er, right->stream));
+    KID_CUDA(cudaStreamWaitEvent(right->stream, el, 0));
+    KID_CUDA(cudaStreamWaitEvent(left->stream, er, 0));
+    KID_CUDA(cudaMemcpyPeerAsync(right->recv_left, right->cfg.device, left->send_right, left->cfg.device, bytes, right->stream));
+    KID_CUDA(cudaMemcpyPeerAsync(left->recv_right, left->cfg.device, right->send_left, right->cfg.device, bytes, left->stream));
+    KID_CUDA(cudaEventDestroy(el));
+    KID_CUDA(cudaEventDestroy(er));
+    return 0;
+}
 
 int kid_synchronize(kid_handle_t* h) {
     if (!h) return fail("null handle");

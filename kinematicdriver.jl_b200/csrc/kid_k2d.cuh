@@ -1,0 +1,193 @@
+// K2DModel horizontal operators (sm_100a): spectral-element weak divergence per element, direct stiffness
+// summation (DSS) at the shared GLL edge nodes, SSPRK33 stage combine.
+//
+// Replaces (reference): the `-hdiv(ρu/ρ·x)` + `CC.Spaces.weighted_dss!` statements of
+// src/K2DModel/tendency.jl:68-70,100-108,152-157,202-207 and the stage axpys of ODE.solve.
+// The vertical/pointwise part of the K2D rhs runs in k1d_tile_kernel (K2D mode) and leaves
+//     dY[var][level][column]   pointwise sources + vertical advection
+//     S[0..1][level][column]   precipitation advection fields (ρq_rai; 1M also ρq_sno)
+// Columns are the GLL nodes, c = element*Nq + node; a rank owns whole elements (x-decomposition).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "kid_physics.cuh"
+
+namespace kid {
+
+constexpr int KID_MAX_NQ = 8;
+constexpr int KID_MAX_DSS = 5;
+
+struct K2DField {
+    int adv_var;  // state variable whose horizontal flux is taken
+    int is_S;     // 0: target is dY plane `plane`; 1: target is S plane `plane`
+    int plane;
+};
+
+template <class FT>
+struct K2DArgs {
+    FT* Y;          // [NV][nz][ncp] stage state (in/out)
+    FT* U;          // [NV][nz][ncp] u^n of the current step
+    FT* dY;         // [NV][nz][ncp]
+    FT* S;          // [2][nz][ncp]
+    FT* out;        // rhs-only mode: final tendencies [NV][nz][ncp]
+    const FT* rho_dry;
+    const FT* w1;   // [ncp]
+    const FT* xc;   // [ncp]
+    FT* send_left; FT* send_right;              // [nfields][nz]
+    const FT* recv_left; const FT* recv_right;  // [nfields][nz]
+    int nz, nc, ncp, nv, helem, Nq, prof_per_column;
+    int nfields;
+    K2DField fields[KID_MAX_DSS];
+    int i_tot, i_rai, i_sno, precip;  // for the S accumulation
+    int stage, use_recv, rhs_only;
+    FT dt, t, t1, z_min, dz;
+    double width, height, dxe;
+    FT D[KID_MAX_NQ * KID_MAX_NQ];  // D[i*Nq+j] = l_j'(ξ_i)
+    FT w[KID_MAX_NQ];               // GLL weights
+};
+
+// one thread per (element, level): weak divergence of every horizontally advected field, then pack the
+// rank-edge nodes for the neighbour exchange
+template <class FT>
+__global__ void k2d_hdiv_kernel(const K2DArgs<FT> A) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (e >= A.helem) return;
+    const int Nq = A.Nq;
+    const size_t plane = size_t(A.nz) * A.ncp;
+    const size_t row = size_t(k) * A.ncp;
+    FT rho[KID_MAX_NQ], rho_u[KID_MAX_NQ];
+    const double zc = double(A.z_min) + (k + 0.5) * double(A.dz);
+    for (int j = 0; j < Nq; ++j) {
+        const int c = e * Nq + j;
+        const FT rd = A.rho_dry[A.prof_per_column ? row + c : size_t(k)];
+        rho[j] = rd + A.Y[size_t(A.i_tot) * plane + row + c];
+        const double ts = (A.t < A.t1) ? sin(M_PI * double(A.t) / double(A.t1)) : 0.0;
+        rho_u[j] = FT(0.5 * double(A.w1[c]) * A.width / A.height * cos(M_PI / A.height * zc) *
+                      cos(2.0 * M_PI / A.width * double(A.xc[c])) * ts);
+    }
+    for (int f = 0; f < A.nfields; ++f) {
+        const K2DField fd = A.fields[f];
+        FT flux[KID_MAX_NQ];
+        for (int j = 0; j < Nq; ++j) flux[j] = rho_u[j] / rho[j] * A.Y[size_t(fd.adv_var) * plane + row + e * Nq + j];
+        FT* tgt = (fd.is_S ? A.S : A.dY) + size_t(fd.plane) * plane + row;
+        for (int i = 0; i < Nq; ++i) {
+            FT acc = FT(0);
+            for (int j = 0; j < Nq; ++j) acc += A.D[j * Nq + i] * (A.w[j] * flux[j]);
+            const FT hd = -acc / A.w[i] * (FT(2) / FT(A.dxe));
+            tgt[e * Nq + i] += -hd;
+        }
+        if (e == 0) A.send_left[size_t(f) * A.nz + k] = tgt[0];
+        if (e == A.helem - 1) A.send_right[size_t(f) * A.nz + k] = tgt[(A.helem - 1) * Nq + Nq - 1];
+    }
+}
+
+// one thread per (column, level): DSS the fields, assemble the tendencies, SSPRK33 stage combine
+template <class FT>
+__global__ void k2d_dss_update_kernel(const K2DArgs<FT> A) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (c >= A.nc) return;
+    const int Nq = A.Nq, e = c / Nq, i = c % Nq;
+    const size_t plane = size_t(A.nz) * A.ncp;
+    const size_t row = size_t(k) * A.ncp;
+    FT Sval[2] = {FT(0), FT(0)};
+    FT dss_dY[KID_MAX_DSS];
+    for (int f = 0; f < A.nfields; ++f) {
+        const K2DField fd = A.fields[f];
+        const FT* src = (fd.is_S ? A.S : A.dY) + size_t(fd.plane) * plane + row;
+        FT v = src[c];
+        if (i == 0 || i == Nq - 1) {
+            // weighted_dss!: the duplicated node of two neighbouring elements gets the average of both copies
+            // (uniform mesh: equal weights).  Periodic in x; across a rank boundary the partner value was received.
+            FT partner;
+            if (i == 0) {
+                if (e > 0) partner = src[(e - 1) * Nq + Nq - 1];
+                else partner = A.use_recv ? A.recv_left[size_t(f) * A.nz + k] : src[(A.helem - 1) * Nq + Nq - 1];
+                v = (partner + v) / FT(2);
+            } else {
+                if (e < A.helem - 1) partner = src[(e + 1) * Nq];
+                else partner = A.use_recv ? A.recv_right[size_t(f) * A.nz + k] : src[0];
+                v = (v + partner) / FT(2);
+            }
+        }
+        if (fd.is_S) Sval[fd.plane] = v;
+        dss_dY[f] = v;
+    }
+    for (int var = 0; var < A.nv; ++var) {
+        const size_t gi = size_t(var) * plane + row + c;
+        FT tend = A.dY[gi];
+        for (int f = 0; f < A.nfields; ++f)
+            if (!A.fields[f].is_S && A.fields[f].plane == var) tend = dss_dY[f];
+        if (A.precip == KID_PRECIP_1M) {
+            if (var == A.i_tot) tend += Sval[0] + Sval[1];
+            if (var == A.i_rai) tend += Sval[0];
+            if (var == A.i_sno) tend += Sval[1];
+        } else if (A.precip == KID_PRECIP_2M) {
+            if (var == A.i_tot) tend += Sval[0];
+            if (var == A.i_rai) tend += Sval[0];
+        }
+        if (A.rhs_only) { A.out[gi] = tend; continue; }
+        const FT y = A.Y[gi];
+        FT u = (A.stage == 0) ? y : A.U[gi];
+        if (A.stage == 0) A.U[gi] = y;
+        FT yn;
+        if (A.stage == 0) yn = y + A.dt * tend;
+        else if (A.stage == 1) yn = (FT(3) * u + y + A.dt * tend) / FT(4);
+        else yn = (u + FT(2) * y + FT(2) * A.dt * tend) / FT(3);
+        A.Y[gi] = yn;
+    }
+}
+
+// aux.microph_variables.{q_rai, N_liq, N_rai} as initialise_aux builds them from the initial profile
+template <class FT>
+__global__ void k2d_init_prev_kernel(const FT* Y, const FT* rho_dry, FT* prev, int nz, int nc, int ncp, int prof_per_column,
+                                     int i_tot, int i_rai, int i_Nl, int i_Nr) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (c >= nc) return;
+    const size_t plane = size_t(nz) * ncp, pi = size_t(k) * ncp + c;
+    const FT rho = rho_dry[prof_per_column ? pi : size_t(k)] + Y[size_t(i_tot) * plane + pi];
+    prev[pi] = i_rai >= 0 ? Y[size_t(i_rai) * plane + pi] / rho : FT(0);
+    prev[plane + pi] = i_Nl >= 0 ? Y[size_t(i_Nl) * plane + pi] : FT(0);
+    prev[2 * plane + pi] = i_Nr >= 0 ? Y[size_t(i_Nr) * plane + pi] : FT(0);
+}
+
+// Gauss-Lobatto-Legendre nodes, weights and differentiation matrix D[i][j] = l_j'(ξ_i) (host, double)
+inline void gll_rule(int Nq, double* x, double* w, double* D) {
+    const int N = Nq - 1;
+    auto legendre = [&](double xi, double& PN, double& PNm1) {
+        double p0 = 1, p1 = xi;
+        for (int n = 2; n <= N; ++n) { double p2 = ((2 * n - 1) * xi * p1 - (n - 1) * p0) / n; p0 = p1; p1 = p2; }
+        PN = (N == 0) ? 1 : p1; PNm1 = (N == 0) ? 0 : p0;
+    };
+    for (int i = 0; i < Nq; ++i) {
+        double xi = -std::cos(M_PI * i / N);
+        if (i > 0 && i < N) {
+            for (int it = 0; it < 100; ++it) {
+                double PN, PNm1;
+                legendre(xi, PN, PNm1);
+                double dx = (N * (PNm1 - xi * PN)) / (-double(N) * (N + 1) * PN);
+                xi -= dx;
+                if (std::fabs(dx) < 1e-16) break;
+            }
+        } else xi = (i == 0) ? -1.0 : 1.0;
+        double PN, PNm1;
+        legendre(xi, PN, PNm1);
+        x[i] = xi;
+        w[i] = 2.0 / (N * (N + 1) * PN * PN);
+    }
+    double bw[KID_MAX_NQ];
+    for (int j = 0; j < Nq; ++j) { bw[j] = 1.0; for (int m = 0; m < Nq; ++m) if (m != j) bw[j] /= (x[j] - x[m]); }
+    for (int i = 0; i < Nq; ++i) {
+        double diag = 0;
+        for (int j = 0; j < Nq; ++j) {
+            if (i == j) continue;
+            D[i * Nq + j] = bw[j] / bw[i] / (x[i] - x[j]);
+            diag -= D[i * Nq + j];
+        }
+        D[i * Nq + i] = diag;
+    }
+}
+
+}  // namespace kid

@@ -66,6 +66,14 @@ struct KArgs {
     FT dt, dz;
     double t0;
     DevSwitches sw;
+    // K2D only (src/K2DModel): node x coordinate per column, previous-call aux (q_rai, N_liq, N_rai) that
+    // activation reads before precompute_aux_precip! refreshes them, separate output of the precipitation
+    // advection fields S1/S2 (they are DSS'd on their own before being added to ρq_tot)
+    const FT* xc;           // [ncp]
+    FT* prev_aux;           // [3][nz][ncp]
+    FT* outS;               // [2][nz][ncp]
+    int update_prev;
+    double width, height, z_min;
 };
 
 // ------------------------------------------------------------ advected variables
@@ -221,8 +229,9 @@ __global__ void __launch_bounds__(tile_max_threads<FT>(), 1) k1d_tile_kernel(con
     if (j == 0) { cb[c] = INT_MAX; cb[C + c] = INT_MAX; }
     __syncthreads();
 
-    const bool k1d = (A.model == KID_MODEL_K1D);
-    const bool with_adv = (A.model == KID_MODEL_K1D || A.model == KID_MODEL_K1D_COL_SED);
+    const bool k2d = DIAG && (A.model == KID_MODEL_K2D);  // K2D steps through the rhs-only instantiation
+    const bool k1d = (A.model == KID_MODEL_K1D) || k2d;   // velocity, activation, condensation switched on
+    const bool with_adv = (A.model == KID_MODEL_K1D || A.model == KID_MODEL_K1D_COL_SED) || k2d;
     const bool stale_Naer = (A.model == KID_MODEL_BOX || A.model == KID_MODEL_K1D_COL_SED) && A.aux_Naer != nullptr;
     const FT dt = A.dt, dz = A.dz;
     const int nstage_total = DIAG ? 1 : 3 * A.nsteps;
@@ -233,7 +242,18 @@ __global__ void __launch_bounds__(tile_max_threads<FT>(), 1) k1d_tile_kernel(con
         const int par = it & 1;
         const FT tn = FT(A.t0 + double(step) * double(dt));
         const FT ts = stage_time(stage, tn, dt);
-        const FT rw = k1d ? rho_w_of_t(ts, w1c, FT(P.kid_t1)) : FT(0);
+        // K1D: ρw(t) uniform over the column (K1DModel/tendency.jl:240-248).  K2D: ρw(x, z_face, t) from the
+        // stream function (K2DModel/tendency.jl:4-9), evaluated in double and rounded like the reference's map
+        FT rw = (k1d && !k2d) ? rho_w_of_t(ts, w1c, FT(P.kid_t1)) : FT(0);
+        double wxd = 0.0;
+        if (k2d && active)
+            wxd = (ts < FT(P.kid_t1)) ? double(w1c) * sin(2.0 * M_PI / A.width * double(A.xc[gc])) *
+                                            sin(M_PI * double(ts) / double(FT(P.kid_t1)))
+                                      : 0.0;
+        auto rwf = [&](int kface) -> FT {  // ρw at face kface (between cells kface-1 and kface)
+            if (!k2d) return rw;
+            return FT(wxd * sin(M_PI / A.height * (A.z_min + double(dz) * kface)));
+        };
 
         // ---- pass 1 (pointwise): terminal velocities and activation rate of the own levels
         if constexpr (L::has_pr) {
@@ -254,10 +274,25 @@ __global__ void __launch_bounds__(tile_max_threads<FT>(), 1) k1d_tile_kernel(con
                         FT S_Nl = FT(0);
                         // non-local activation keeps only the LOWEST activating level, so once this thread has a
                         // candidate its higher levels can never be selected: skip their ARG evaluation
-                        if (k1d && (A.sw.local_activation || first == INT_MAX)) {
+                        FT q_rai_act = a.q_rai, N_liq_act = a.N_liq, N_rai_act = a.N_rai;
+                        if (k2d) {
+                            // K2D calls activation BEFORE precompute_aux_precip! (K2DModel/ode_utils.jl:43-44): it
+                            // sees the q_rai, N_liq, N_rai the previous rhs! call left in aux
+                            const size_t pi = size_t(k) * ncp + gc;
+                            q_rai_act = A.prev_aux[pi];
+                            N_liq_act = A.prev_aux[plane + pi];
+                            N_rai_act = A.prev_aux[2 * plane + pi];
+                            if (A.update_prev) {
+                                A.prev_aux[pi] = a.q_rai;
+                                A.prev_aux[plane + pi] = a.N_liq;
+                                A.prev_aux[2 * plane + pi] = a.N_rai;
+                            }
+                        }
+                        if (k1d && (A.sw.local_activation || first == INT_MAX || k2d)) {
                             FT p = pressure_point<FT, MOIST, PRECIP>(P, a);
-                            S_Nl = aerosol_activation_rate<FT>(P, A.sw, a.q_tot, a.q_liq + a.q_rai, a.q_ice,
-                                                               a.N_liq + a.N_rai, a.N_aer, a.T, p, a.rho, rw, dt);
+                            FT rw_c = k2d ? (rwf(k + 1) + rwf(k)) / FT(2) : rw;  // InterpolateF2C
+                            S_Nl = aerosol_activation_rate<FT>(P, A.sw, a.q_tot, a.q_liq + q_rai_act, a.q_ice,
+                                                               N_liq_act + N_rai_act, a.N_aer, a.T, p, a.rho, rw_c, dt);
                             // find_cloud_base! (src/K1DModel/tendency.jl:21-32): the accumulator starts at
                             // level 1 and is replaced only while its S is 0 and the candidate's S is > 0
                             bool cand = (k == 0) ? (S_Nl != FT(0)) : (S_Nl > FT(0));
@@ -304,12 +339,12 @@ __global__ void __launch_bounds__(tile_max_threads<FT>(), 1) k1d_tile_kernel(con
             FT Flo[NADV], Clo[NADV];
 #pragma unroll
             for (int i = 0; i < NADV; ++i) Flo[i] = Clo[i] = FT(0);
-            const FT surf_flux[3] = {FT(0), rw * qsurf, rw * Ndc * (FT(1) - qsurf) / FT(1.225)};
+            const FT surf_flux[3] = {FT(0), rw * qsurf, rw * Ndc * (FT(1) - qsurf) / FT(1.225)};  // ρw0 = 0 in K2D
             if (with_adv && k0 > 0 && k0 < k1) {
                 // faces below the chunk: velocity and fluxes from the pre-read halo
                 FT rho_k = rds[kidx(k0)] + Ys[sidx(L::tot, k0)];
                 FT rho_l = lo_rd + lo[0];
-                FT wa = rw / ((rho_k + rho_l) / FT(2));
+                FT wa = rwf(k0) / ((rho_k + rho_l) / FT(2));
                 FT wv[3] = {wa, wa, wa};
                 if constexpr (L::has_pr) {
                     wv[1] = wa - (vt1s[kidx(k0)] + lo_v1) / FT(2);
@@ -347,7 +382,7 @@ __global__ void __launch_bounds__(tile_max_threads<FT>(), 1) k1d_tile_kernel(con
                     if constexpr (L::has_pr) { v1k = vt1s[kidx(k)]; v2k = vt2s[kidx(k)]; }
                     if (has_up) {
                         FT rho_u = (up_own ? rds[kidx(k + 1)] : hi_rd) + (up_own ? Ys[sidx(L::tot, k + 1)] : hi[0]);
-                        FT wa = rw / ((rho_u + a.rho) / FT(2));
+                        FT wa = rwf(k + 1) / ((rho_u + a.rho) / FT(2));
                         wv[0] = wv[1] = wv[2] = wa;
                         if constexpr (L::has_pr) {
                             FT v1u = up_own ? vt1s[kidx(k + 1)] : hi_v1;
@@ -357,7 +392,7 @@ __global__ void __launch_bounds__(tile_max_threads<FT>(), 1) k1d_tile_kernel(con
                         }
                         if (k == 0) {
                             FT rho_2 = rds[kidx(2)] + Ys[sidx(L::tot, 2)];
-                            FT wa2 = rw / ((rho_2 + rho_u) / FT(2));
+                            FT wa2 = rwf(2) / ((rho_2 + rho_u) / FT(2));
                             wv2[0] = wv2[1] = wv2[2] = wa2;
                             if constexpr (L::has_pr) {
                                 wv2[1] = wa2 - (vt1s[kidx(2)] + vt1s[kidx(1)]) / FT(2);
@@ -370,6 +405,10 @@ __global__ void __launch_bounds__(tile_max_threads<FT>(), 1) k1d_tile_kernel(con
                     static_for<0, NADV>([&](auto I) {
                         constexpr int i = decltype(I)::value;
                         constexpr AdvVar e = adv_entry<MOIST, PRECIP>(i);
+                        // K2D (K2DModel/tendency.jl:114-213): N_liq and N_aer are not advected, the precipitation
+                        // divergence extrapolates at BOTH ends, q_tot always gets the flux correction
+                        if (k2d && (e.idx == L::Nl || e.idx == L::Na)) return;
+                        const int top_bc = (k2d && e.vel != VEL_AIR) ? BC_EXTRAP : e.top;
                         const FT yk = y[e.idx];
                         const FT yu = has_up ? (up_own ? Ys[sidx(e.idx, k + 1)] : hi[i]) : FT(0);
                         const FT w = wv[e.vel];
@@ -383,7 +422,7 @@ __global__ void __launch_bounds__(tile_max_threads<FT>(), 1) k1d_tile_kernel(con
                             else D = (w2 * ((y2 + yu) / FT(2)) - Fup) / dz;
                             fc = P.num_fcc_scale * (M::abs(w2) * (y2 - yu) - Cup) / dz;
                         } else if (k == nz - 1) {
-                            if (e.top == BC_SET) D = (FT(0) - Flo[i]) / dz;
+                            if (top_bc == BC_SET) D = (FT(0) - Flo[i]) / dz;
                             else D = edge[size_t(2 * i) * C + c];
                             fc = edge[size_t(2 * i + 1) * C + c];
                         } else {
@@ -396,10 +435,14 @@ __global__ void __launch_bounds__(tile_max_threads<FT>(), 1) k1d_tile_kernel(con
                         }
                         Flo[i] = Fup;
                         Clo[i] = Cup;
-                        const bool fcc_on = (e.fcc == FCC_ALWAYS) || A.sw.qtot_flux_correction;
+                        const bool fcc_on = (e.fcc == FCC_ALWAYS) || A.sw.qtot_flux_correction || k2d;
                         if (e.to_tot) {
                             FT S = -D;
                             S += fc;
+                            if (k2d) {  // S is DSS'd on its own before it is added to ρq_tot and its own variable
+                                A.outS[size_t(e.vel == VEL_VT1 ? 0 : 1) * plane + size_t(k) * ncp + gc] = S;
+                                return;
+                            }
                             tend[e.idx] += S;
                             S_tot = any_S ? S_tot + S : S;
                             any_S = true;

@@ -100,6 +100,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         "kid_k2d_edge_buffers": (C.c_int, [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
         "kid_k2d_stage_end": (C.c_int, [H, C.c_int32]),
+        "kid_k2d_exchange_local": (C.c_int, [H, H]),
         "kid_synchronize": (C.c_int, [H]),
         "kid_stream": (C.c_void_p, [H]),
         "kid_state_device_ptr": (C.c_void_p, [H]),
@@ -226,6 +227,9 @@ class Handle:
 
     def k2d_stage_end(self, stage: int):
         self._check(self.lib.kid_k2d_stage_end(self._h, int(stage)))
+
+    def k2d_exchange_local(self, right: "Handle"):
+        self._check(self.lib.kid_k2d_exchange_local(self._h, right._h))
 
     def k2d_edge_buffers(self):
         p = [C.c_void_p() for _ in range(4)]
