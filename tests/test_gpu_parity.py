@@ -7,7 +7,7 @@ Tolerances (relative, metric in tests/parity.py), stated per float type and per 
       Float32  see RHS_TOL_F32: the reference's limiter F + M - sqrt(F^2 + M^2) cancels
                catastrophically in Float32 when F << M (the result is quantised to ulp(M)); a
                1-ulp difference in M between two libm implementations therefore moves a source by
-               ulp(M).  Mass tendencies are compared to 2e-3, number tendencies to 2e-2.
+               ulp(M).  Mass tendencies are compared to 5e-3, number tendencies to 2e-2.
   STATE after K steps from an identical state
       Float64  1e-8 (K <= 60), 1e-6 (K = 600), except Equilibrium + 2M: 1e-1 — there the reference
                feeds activation with S = p_v/p_vs - 1 where q_vap == q_vs exactly in cloud, so the
@@ -54,7 +54,7 @@ def state_tol(FT, var, nsteps, ms, ps):
 def rhs_tol(FT, var):
     if FT == np.float64:
         return 1e-8
-    return 2e-2 if var.startswith("N_") else 2e-3
+    return 2e-2 if var.startswith("N_") else 5e-3
 
 
 def developed_state(FT, t_dev=900, **opts):
