@@ -53,6 +53,9 @@ struct kid_handle {
     cudaStream_t stream = nullptr;
     void *Y = nullptr, *rho_dry = nullptr, *T = nullptr, *w1 = nullptr, *q_surf = nullptr, *Nd = nullptr;
     void *aux_Naer = nullptr, *out = nullptr, *staging = nullptr;
+    void *prm_sets = nullptr, *col_to_set = nullptr;  // per-column parameter sets (calibration ensembles)
+    void *ps_liq = nullptr, *ps_mix = nullptr;        // p_sat(T) per grid point (profile constants)
+    bool consts_dirty = true;
     size_t staging_bytes = 0, out_bytes = 0;
     int prof_per_column = 0;
     DevSwitches sw{};
@@ -158,6 +161,10 @@ KArgs<FT> make_args(kid_handle* h, double t0, int nsteps, int diag_mode, int fie
     a.q_surf = (const FT*)h->q_surf;
     a.Nd = (const FT*)h->Nd;
     a.aux_Naer = (const FT*)h->aux_Naer;
+    a.ps_liq = (const FT*)h->ps_liq;
+    a.ps_mix = (const FT*)h->ps_mix;
+    a.prm_sets = (const DevParams<FT>*)h->prm_sets;
+    a.col_to_set = (const int*)h->col_to_set;
     a.out = (FT*)h->out;
     a.nz = h->cfg.nz;
     a.nc = h->cfg.nc;
@@ -210,6 +217,16 @@ int check_ready(kid_handle* h) {
     if (!h->params_set) return fail("kid_set_params has not been called");
     if (!h->profiles_set) return fail("kid_set_profiles has not been called");
     if (!h->state_set) return fail("kid_set_state has not been called");
+    if (h->consts_dirty) {
+        // (re)evaluate the time-invariant profile constants after params or profiles changed; a shared profile
+        // with per-column thermodynamic parameter sets is not supported (the constants would differ per column)
+        cudaError_t e;
+        if (h->f64) e = h->lt->consts_d(make_args<double>(h, 0.0, 0, 0, 0), (double*)h->ps_liq, (double*)h->ps_mix, h->stream);
+        else e = h->lt->consts_f(make_args<float>(h, 0.0, 0, 0, 0), (float*)h->ps_liq, (float*)h->ps_mix, h->stream);
+        if (e != cudaSuccess) return fail(std::string("profile_consts_kernel launch: ") + cudaGetErrorString(e));
+        h->launches++;
+        h->consts_dirty = false;
+    }
     return 0;
 }
 
@@ -220,13 +237,14 @@ int choose_tile(kid_handle* h) {
     KID_CUDA(cudaGetDevice(&dev));
     KID_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const int nz = h->cfg.nz, moist = h->cfg.moisture;
+    const bool pcp = h->prm_sets != nullptr;
     int C = 32;
     while (C > 1) {
-        size_t s = h->f64 ? h->lt->k1d_smem_d(moist, nz, C) : h->lt->k1d_smem_f(moist, nz, C);
+        size_t s = h->f64 ? h->lt->k1d_smem_d(moist, nz, C, pcp) : h->lt->k1d_smem_f(moist, nz, C, pcp);
         if (s <= size_t(max_smem)) break;
         C /= 2;
     }
-    size_t s = h->f64 ? h->lt->k1d_smem_d(moist, nz, C) : h->lt->k1d_smem_f(moist, nz, C);
+    size_t s = h->f64 ? h->lt->k1d_smem_d(moist, nz, C, pcp) : h->lt->k1d_smem_f(moist, nz, C, pcp);
     if (s > size_t(max_smem)) return fail("column too tall for one shared-memory tile (nz too large)");
     int maxt = h->f64 ? tile_max_threads<double>() : tile_max_threads<float>();
     int NW = std::max(1, std::min(maxt / C, nz / 3));
@@ -411,7 +429,7 @@ int kid_create(const kid_config_t* cfg, kid_handle_t** out) {
 void kid_destroy(kid_handle_t* h) {
     if (!h) return;
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (void* p : {h->Y, h->rho_dry, h->T, h->w1, h->q_surf, h->Nd, h->aux_Naer, h->out, h->staging, h->U, h->S,
+    for (void* p : {h->ps_liq, h->ps_mix, h->prm_sets, h->col_to_set, h->Y, h->rho_dry, h->T, h->w1, h->q_surf, h->Nd, h->aux_Naer, h->out, h->staging, h->U, h->S,
                     h->prev_aux, h->xc, h->out2, h->send_left, h->send_right, h->recv_left, h->recv_right})
         if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -421,8 +439,53 @@ void kid_destroy(kid_handle_t* h) {
 int kid_set_params(kid_handle_t* h, const double* params, int32_t nparams, int32_t nsets, const int32_t* column_to_set) {
     if (!h || !params) return fail("null argument");
     if (nparams != KID_NPARAMS) return fail("kid_set_params: nparams != KID_NPARAMS (header/library version skew)");
-    if (nsets != 1 || column_to_set) return fail("kid_set_params: per-column parameter sets are not implemented in this build");
+    if (nsets < 1) return fail("kid_set_params: nsets must be >= 1");
+    if (nsets > 1 && !column_to_set) return fail("kid_set_params: nsets > 1 needs column_to_set");
+    if (nsets > 1 && h->cfg.model == KID_MODEL_K2D) return fail("kid_set_params: per-column parameter sets are not supported for K2DModel");
     h->params.assign(params, params + KID_NPARAMS);
+    h->consts_dirty = true;
+    for (void** p : {&h->prm_sets, &h->col_to_set}) { if (*p) cudaFree(*p); *p = nullptr; }
+    if (nsets > 1) {
+        const int nc = h->cfg.nc;
+        std::vector<int> idx(h->ncp, 0);
+        for (int c = 0; c < nc; ++c) {
+            if (column_to_set[c] < 0 || column_to_set[c] >= nsets) return fail("kid_set_params: column_to_set entry out of range");
+            idx[c] = column_to_set[c];
+        }
+        KID_CUDA(cudaMalloc(&h->col_to_set, size_t(h->ncp) * sizeof(int)));
+        KID_CUDA(cudaMemcpyAsync(h->col_to_set, idx.data(), size_t(h->ncp) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        std::vector<double> w1(nc), nd(nc);
+        for (int c = 0; c < nc; ++c) {
+            w1[c] = params[size_t(idx[c]) * KID_NPARAMS + KID_P_kid_w1];
+            nd[c] = params[size_t(idx[c]) * KID_NPARAMS + KID_P_com_prescribed_Nd];
+        }
+        // set 0 also goes to the __constant__ block: it serves the profile constants of a SHARED profile
+        // (thermodynamic parameters must then be common to all sets)
+        if (h->f64) {
+            std::vector<DevParams<double>> sets(nsets);
+            for (int i = 0; i < nsets; ++i) fill_dev_params(sets[i], params + size_t(i) * KID_NPARAMS);
+            KID_CUDA(h->lt->upload_params_d(sets[0], h->stream));
+            KID_CUDA(cudaMalloc(&h->prm_sets, sets.size() * sizeof(sets[0])));
+            KID_CUDA(cudaMemcpyAsync(h->prm_sets, sets.data(), sets.size() * sizeof(sets[0]), cudaMemcpyHostToDevice, h->stream));
+            KID_CUDA(cudaStreamSynchronize(h->stream));
+            if (upload_columns(h, h->w1, w1.data(), 0)) return 1;
+            if (upload_columns(h, h->Nd, nd.data(), 0)) return 1;
+        } else {
+            std::vector<DevParams<float>> sets(nsets);
+            for (int i = 0; i < nsets; ++i) fill_dev_params(sets[i], params + size_t(i) * KID_NPARAMS);
+            KID_CUDA(h->lt->upload_params_f(sets[0], h->stream));
+            KID_CUDA(cudaMalloc(&h->prm_sets, sets.size() * sizeof(sets[0])));
+            KID_CUDA(cudaMemcpyAsync(h->prm_sets, sets.data(), sets.size() * sizeof(sets[0]), cudaMemcpyHostToDevice, h->stream));
+            KID_CUDA(cudaStreamSynchronize(h->stream));
+            std::vector<float> w1f(w1.begin(), w1.end()), ndf(nd.begin(), nd.end());
+            if (upload_columns(h, h->w1, w1f.data(), 0)) return 1;
+            if (upload_columns(h, h->Nd, ndf.data(), 0)) return 1;
+        }
+        if (choose_tile(h)) return 1;
+        h->params_set = true;
+        return 0;
+    }
+    if (choose_tile(h)) return 1;
     if (h->f64) {
         DevParams<double> P;
         fill_dev_params(P, params);
@@ -444,7 +507,8 @@ int kid_set_profiles(kid_handle_t* h, const void* rho_dry, const void* T, int32_
     if (!h || !rho_dry || !T) return fail("null argument");
     const int nz = h->cfg.nz;
     size_t n = per_column ? size_t(nz) * h->ncp : size_t(nz);
-    for (void** p : {&h->rho_dry, &h->T}) {
+    h->consts_dirty = true;
+    for (void** p : {&h->rho_dry, &h->T, &h->ps_liq, &h->ps_mix}) {
         if (*p) cudaFree(*p);
         *p = nullptr;
         KID_CUDA(cudaMalloc(p, n * h->fsz));

@@ -56,6 +56,10 @@ struct KArgs {
     const FT* q_surf;       // [ncp] aux.q_surf per column
     const FT* Nd;           // [ncp] common_params.prescribed_Nd per column
     const FT* aux_Naer;     // [nz][ncp] aux.microph_variables.N_aer snapshot (Box / col_sed), may be null
+    const FT* ps_liq;       // saturation vapour pressure over liquid / of the mixed phase at the (time-invariant) T,
+    const FT* ps_mix;       // same shape as T; filled by profile_consts_kernel when params or profiles change
+    const DevParams<FT>* prm_sets;  // per-column parameter sets (calibration ensembles), null if one set is shared
+    const int* col_to_set;          // [ncp] column -> parameter set
     FT* out;                // DIAG: dY [NV][nz][ncp] (mode 1) or one aux field [nz][ncp] (mode 2)
     int nz, nc, ncp;
     int prof_per_column;    // 0: rho_dry/T are [nz]; 1: [nz][ncp]
@@ -176,9 +180,10 @@ KID_DEV FT aux_field_value(const PRM& P, int field, const Point<FT>& a, const So
 
 // shared-memory footprint of one tile (bytes); must match the carve-up in k1d_tile_kernel
 template <class FT, int MOIST, int PRECIP>
-inline size_t k1d_tile_smem_bytes(int nz, int C) {
+inline size_t k1d_tile_smem_bytes(int nz, int C, bool per_column_params = false) {
     using L = Lay<MOIST, PRECIP>;
     constexpr int NADV = adv_count<MOIST, PRECIP>();
+    if (per_column_params) return k1d_tile_smem_bytes<FT, MOIST, PRECIP>(nz, C, false) + size_t(C) * sizeof(DevParams<FT>) + 16;
     size_t nfl = size_t(L::NV) * nz * C;       // Ys
     nfl += size_t(2) * nz * C;                 // rho_dry, T
     if (L::has_pr) nfl += size_t(2) * nz * C;  // vt1, vt2
@@ -193,7 +198,6 @@ __global__ void __launch_bounds__(tile_max_threads<FT>(), 1) k1d_tile_kernel(con
     using M = Mth<FT>;
     constexpr int NV = L::NV;
     constexpr int NADV = adv_count<MOIST, PRECIP>();
-    const auto& P = PRMSRC::get();
     const int nz = A.nz, C = A.C, NW = A.NW, ncp = A.ncp;
     const int c = threadIdx.x, j = threadIdx.y;
     const int gc = blockIdx.x * C + c;
@@ -211,6 +215,22 @@ __global__ void __launch_bounds__(tile_max_threads<FT>(), 1) k1d_tile_kernel(con
     if constexpr (L::is2m) { acts = nxt; nxt += size_t(nz) * C; }
     FT* edge = nxt;                            // [2*NADV][C]
     int* cb = reinterpret_cast<int*>(edge + size_t(2) * NADV * C);  // [2][C]
+    // parameters: the shared __constant__ block, or this column's own set staged in shared memory as
+    // [column][word] with an odd word count (conflict-free when the 32 lanes read the same field)
+    const DevParams<FT>* Pp;
+    if constexpr (PRMSRC::per_column) {
+        size_t off = (reinterpret_cast<size_t>(cb + 2 * C) + 15) & ~size_t(15);
+        DevParams<FT>* sp = reinterpret_cast<DevParams<FT>*>(off);
+        if (gc < A.nc) {
+            const FT* src = reinterpret_cast<const FT*>(A.prm_sets + A.col_to_set[gc]);
+            FT* dst = reinterpret_cast<FT*>(sp + c);
+            for (int w = j; w < int(sizeof(DevParams<FT>) / sizeof(FT)); w += NW) dst[w] = src[w];
+        }
+        Pp = sp + c;
+    } else {
+        Pp = &PRMSRC::get();
+    }
+    const DevParams<FT>& P = *Pp;
     auto sidx = [&](int v, int k) { return (size_t(v) * nz + k) * C + c; };
     auto kidx = [&](int k) { return size_t(k) * C + c; };
 
@@ -265,7 +285,8 @@ __global__ void __launch_bounds__(tile_max_threads<FT>(), 1) k1d_tile_kernel(con
 #pragma unroll
                     for (int v = 0; v < NV; ++v) y[v] = Ys[sidx(v, k)];
                     Point<FT> a;
-                    thermo_point<FT, MOIST, PRECIP>(P, y, rds[kidx(k)], Ts[kidx(k)], a);
+                    const size_t ppi = A.prof_per_column ? size_t(k) * ncp + gc : size_t(k);
+                    thermo_point<FT, MOIST, PRECIP>(P, y, rds[kidx(k)], Ts[kidx(k)], A.ps_liq[ppi], A.ps_mix[ppi], a);
                     FT v1, v2;
                     terminal_velocities<FT, PRECIP>(P, A.sw, a, v1, v2);
                     vt1s[kidx(k)] = v1;
@@ -292,7 +313,7 @@ __global__ void __launch_bounds__(tile_max_threads<FT>(), 1) k1d_tile_kernel(con
                             FT p = pressure_point<FT, MOIST, PRECIP>(P, a);
                             FT rw_c = k2d ? (rwf(k + 1) + rwf(k)) / FT(2) : rw;  // InterpolateF2C
                             S_Nl = aerosol_activation_rate<FT>(P, A.sw, a.q_tot, a.q_liq + q_rai_act, a.q_ice,
-                                                               N_liq_act + N_rai_act, a.N_aer, a.T, p, a.rho, rw_c, dt);
+                                                               N_liq_act + N_rai_act, a.N_aer, a.T, a.ps_liq, p, a.rho, rw_c, dt);
                             // find_cloud_base! (src/K1DModel/tendency.jl:21-32): the accumulator starts at
                             // level 1 and is replaced only while its S is 0 and the candidate's S is > 0
                             bool cand = (k == 0) ? (S_Nl != FT(0)) : (S_Nl > FT(0));
@@ -364,7 +385,8 @@ __global__ void __launch_bounds__(tile_max_threads<FT>(), 1) k1d_tile_kernel(con
 #pragma unroll
                 for (int v = 0; v < NV; ++v) y[v] = Ys[sidx(v, k)];
                 Point<FT> a;
-                thermo_point<FT, MOIST, PRECIP>(P, y, rds[kidx(k)], Ts[kidx(k)], a);
+                const size_t ppi = A.prof_per_column ? size_t(k) * ncp + gc : size_t(k);
+                thermo_point<FT, MOIST, PRECIP>(P, y, rds[kidx(k)], Ts[kidx(k)], A.ps_liq[ppi], A.ps_mix[ppi], a);
                 if (stale_Naer) a.N_aer = A.aux_Naer[size_t(k) * ncp + gc];
                 FT act_Nl = FT(0);
                 if constexpr (L::is2m) {
@@ -489,8 +511,17 @@ template <class FT, int MOIST, int PRECIP, class PRMSRC>
 __global__ void __launch_bounds__(128) box_step_kernel(const KArgs<FT> A) {
     using L = Lay<MOIST, PRECIP>;
     constexpr int NV = L::NV;
-    const auto& P = PRMSRC::get();
     const int gc = blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ __align__(16) unsigned char box_smem[];
+    const DevParams<FT>* Pp;
+    if constexpr (PRMSRC::per_column) {
+        DevParams<FT>* sp = reinterpret_cast<DevParams<FT>*>(box_smem);
+        if (gc < A.nc) sp[threadIdx.x] = A.prm_sets[A.col_to_set[gc]];
+        Pp = sp + threadIdx.x;
+    } else {
+        Pp = &PRMSRC::get();
+    }
+    const DevParams<FT>& P = *Pp;
     if (gc >= A.nc) return;
     const size_t plane = size_t(A.ncp);  // nz == 1
     FT u[NV], y[NV], tend[NV];
@@ -498,6 +529,7 @@ __global__ void __launch_bounds__(128) box_step_kernel(const KArgs<FT> A) {
     for (int v = 0; v < NV; ++v) u[v] = A.Y[v * plane + gc];
     const FT rho_dry = A.rho_dry[A.prof_per_column ? gc : 0];
     const FT T = A.T[A.prof_per_column ? gc : 0];
+    const FT psl = A.ps_liq[A.prof_per_column ? gc : 0], psm = A.ps_mix[A.prof_per_column ? gc : 0];
     const FT Ndc = A.Nd[gc];
     const FT Naer_aux = A.aux_Naer ? A.aux_Naer[gc] : FT(0);
     const FT dt = A.dt;
@@ -508,7 +540,7 @@ __global__ void __launch_bounds__(128) box_step_kernel(const KArgs<FT> A) {
 #pragma unroll 1
         for (int stage = 0; stage < 3; ++stage) {
             Point<FT> a;
-            thermo_point<FT, MOIST, PRECIP>(P, y, rho_dry, T, a);
+            thermo_point<FT, MOIST, PRECIP>(P, y, rho_dry, T, psl, psm, a);
             if (A.aux_Naer) a.N_aer = Naer_aux;
             Sources<FT> src;
             point_source_tendencies<FT, MOIST, PRECIP>(P, A.sw, a, Ndc, dt, false, FT(0), src, tend);
@@ -520,6 +552,24 @@ __global__ void __launch_bounds__(128) box_step_kernel(const KArgs<FT> A) {
     }
 #pragma unroll
     for (int v = 0; v < NV; ++v) A.Y[v * plane + gc] = u[v];
+}
+
+// --------------------------------------------------- time-invariant profile constants
+// p_sat,liq(T) and p_sat,mixed(T) per grid point (full-accuracy pow/exp; evaluated once per upload)
+template <class FT, class PRMSRC>
+__global__ void profile_consts_kernel(const FT* __restrict__ T, FT* __restrict__ ps_liq, FT* __restrict__ ps_mix, int nz, int nc,
+                                      int ncp, int per_column, const DevParams<FT>* prm_sets, const int* col_to_set) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (c >= (per_column ? nc : 1)) return;
+    const DevParams<FT>* Pp;
+    if constexpr (PRMSRC::per_column) Pp = prm_sets + col_to_set[c];
+    else Pp = &PRMSRC::get();
+    TD<FT, DevParams<FT>> td(*Pp);
+    const size_t i = per_column ? size_t(k) * ncp + c : size_t(k);
+    const FT t = T[i];
+    ps_liq[i] = td.psat_liquid(t);
+    ps_mix[i] = td.psat_mixed(t, td.liquid_fraction_T(t));
 }
 
 // ------------------------------------------------------------ layout transposes

@@ -289,3 +289,42 @@ def custom_case(FT, model: int, moisture_choice: str, precipitation_choice: str,
                 Y0=np.broadcast_to(Y_col, (nc,) + Y_col.shape).copy(), var_names=names,
                 col_scalars={COL_Q_SURF: np.full(nc, q_surf, dtype=FT)}, z_centers=zc,
                 meta=dict(toml=td, moisture=moisture, precip=precip))
+
+
+def with_parameter_sets(case: Case, overrides: list[dict], column_to_set=None) -> Case:
+    """Calibration-style ensemble: `overrides[s]` maps ClimaParams names to the values of parameter set s
+    (what calibration/KiDUtils.jl:378-382 `update_parameters!` writes into the toml dict per ensemble member);
+    column c uses set column_to_set[c] (default: round-robin)."""
+    td0 = case.meta["toml"]
+    rf = case.meta["precip"].rain_formation
+    tables = []
+    for ov in overrides:
+        td = dict(td0)
+        for k, v in ov.items():
+            if k not in td:
+                raise KeyError(f"unknown ClimaParams name {k}")
+            td[k] = v
+        tables.append(PR.flatten_params(td, rf))
+    nc = case.cfg.nc
+    idx = np.arange(nc) % len(overrides) if column_to_set is None else np.asarray(column_to_set)
+    new = Case(cfg=case.cfg, params=np.stack(tables), ρ_dry=case.ρ_dry, T=case.T, Y0=case.Y0, var_names=case.var_names,
+               col_scalars=dict(case.col_scalars), column_to_set=idx.astype(np.int32), z_centers=case.z_centers,
+               meta=dict(case.meta, overrides=overrides))
+    return new
+
+
+def split_by_parameter_set(case: Case):
+    """Yield (column indices, single-set Case) per parameter set — lets a backend that handles one set per handle
+    (the test oracle) run a multi-set ensemble."""
+    import copy
+    for s in range(case.params.shape[0]):
+        cols = np.where(case.column_to_set == s)[0]
+        if cols.size == 0:
+            continue
+        cfg = copy.copy(case.cfg)
+        cfg.nc = int(cols.size)
+        pc = case.ρ_dry.ndim == 2
+        yield cols, Case(cfg=cfg, params=case.params[s], ρ_dry=case.ρ_dry[cols] if pc else case.ρ_dry,
+                         T=case.T[cols] if pc else case.T, Y0=case.Y0[cols], var_names=case.var_names,
+                         col_scalars={k: np.asarray(v)[cols] for k, v in case.col_scalars.items()},
+                         z_centers=case.z_centers, meta=case.meta)

@@ -372,3 +372,61 @@ def test_full_size_k1d_ensemble_65536_columns():
     Ys = gs.get_state()
     assert np.all(np.isfinite(Yb))
     assert np.array_equal(Yb.reshape(reps, -1), np.broadcast_to(Ys.reshape(1, -1), (reps, Ys.size)))
+
+
+# ------------------------------------------------------- per-column parameter sets (calibration ensembles)
+def _run_multi_set(cs, t0, nsteps):
+    g = M.make_handle(cs, Handle)
+    g.step(t0, nsteps)
+    Yg = g.get_state()
+    Yo = np.empty_like(Yg)
+    for cols, sub in M.split_by_parameter_set(cs):
+        o = M.make_handle(sub, OracleHandle)
+        o.step(t0, nsteps)
+        Yo[cols] = o.get_state()
+    return Yg, Yo
+
+
+@pytest.mark.parametrize("FT", FTS)
+def test_per_column_parameter_sets_k1d_1m(FT):
+    """BASELINE config 3 style: NonEq + 1M, every member with its own (χv_rai, χa_rai, τ_acnv) as in
+    calibration/examples/grid_search/grid_search.jl:10-13; 45 columns over 7 parameter sets."""
+    base = M.k1d_case(FT, nc=45, n_elem=32, moisture_choice="NonEquilibriumMoisture", precipitation_choice="Precipitation1M")
+    ov = [{"rain_terminal_velocity_size_relation_coefficient_chiv": 0.2 + 0.3 * s,
+           "rain_cross_section_size_relation_coefficient_chia": 0.5 + 0.7 * s,
+           "rain_autoconversion_timescale": 500.0 + 200.0 * s} for s in range(7)]
+    cs = M.with_parameter_sets(base, ov)
+    Yg, Yo = _run_multi_set(cs, 0.0, 500)
+    e = errors(Yg, Yo, cs.var_names)
+    for v, err in e.items():
+        assert err <= state_tol(FT, v, 500, "NonEquilibriumMoisture", "Precipitation1M"), (v, err, e)
+    n = list(cs.var_names)
+    per_set = [Yo[cs.column_to_set == s][:, n.index("ρq_rai")].max() for s in range(7)]
+    assert np.unique(np.round(per_set, 12)).size > 3  # the sets really change the physics
+
+
+@pytest.mark.parametrize("FT", FTS)
+def test_per_column_parameter_sets_k1d_2m(FT):
+    """2M: kcc, kcr varied by ±25 % (priors of calibration/examples/Box/config.jl:25-30), one set per column."""
+    base = M.k1d_case(FT, nc=9, n_elem=32, moisture_choice="NonEquilibriumMoisture", precipitation_choice="Precipitation2M")
+    ov = [{"SB2006_collection_kernel_coeff_kcc": 4.44e9 * (0.75 + 0.0625 * s),
+           "SB2006_collection_kernel_coeff_kcr": 5.25 * (1.25 - 0.0625 * s), "prescribed_flow_w1": 1.5 + 0.05 * s}
+          for s in range(9)]
+    cs = M.with_parameter_sets(base, ov)
+    cs.col_scalars.pop(lib.COL_W1, None)  # w1 comes from each column's parameter set
+    Yg, Yo = _run_multi_set(cs, 0.0, 500)
+    e = errors(Yg, Yo, cs.var_names)
+    for v, err in e.items():
+        assert err <= state_tol(FT, v, 500, "NonEquilibriumMoisture", "Precipitation2M"), (v, err, e)
+
+
+@pytest.mark.parametrize("FT", FTS)
+def test_per_column_parameter_sets_box(FT):
+    base = M.box_case(FT, nc=70, precipitation_choice="Precipitation2M", qt=np.linspace(6e-4, 2e-3, 70))
+    ov = [{"SB2006_collection_kernel_coeff_kcc": 4.44e9 * (0.75 + 0.1 * s), "SB2006_collection_kernel_coeff_kcr": 5.25 * (0.8 + 0.1 * s)}
+          for s in range(5)]
+    cs = M.with_parameter_sets(base, ov)
+    Yg, Yo = _run_multi_set(cs, 0.0, 600)
+    e = errors(Yg, Yo, cs.var_names)
+    for v, err in e.items():
+        assert err <= (1e-8 if FT == np.float64 else (5e-2 if v.startswith("N_") else 5e-3)), (v, err, e)
