@@ -36,6 +36,7 @@ sys.path.insert(0, str(ROOT))
 NZ = 128
 BYTES_PER_GP_STEP = 2 * 8 * 4 + 2 * 4  # NonEq+2M f32: read+write 8 prognostics, read per-column ρ_dry, T
 METRIC = "grid-point-steps/s"
+ORDER = "sorted"
 PREROLL_SPL = 60  # the untimed pre-roll runs in launches of 60 fused steps
 
 
@@ -85,8 +86,10 @@ class ClockSampler:
 
 def build_case(nc: int, column_offset: int, device: int):
     from kid_b200 import model as M
+    # member order: the ensemble is stored sorted by (sounding, w1, Nd) so that neighbouring columns (the 32 lanes of a
+    # warp) follow the same microphysics branches; the hash order of SURVEY §8(d) is available with --order hash
     return M.k1d_ensemble_case(np.float32, nc=nc, n_profiles=16, column_offset=column_offset, device=device, n_elem=NZ,
-                               moisture_choice="NonEquilibriumMoisture", precipitation_choice="Precipitation2M")
+                               order=ORDER, moisture_choice="NonEquilibriumMoisture", precipitation_choice="Precipitation2M")
 
 
 def cpu_reference_throughput(case, Y_dev_sample, t_start: float, target_s: float = 15.0):
@@ -268,6 +271,7 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "KiD 1D NonEq+Precipitation2M(SB2006) ensemble, 128 levels, Float32 (BASELINE configs[3])",
                        "columns_per_gpu": nc, "levels": NZ, "steps_per_launch": spl, "t_start_s": t_timed0,
+                       "member_order": ORDER + (" by (sounding, w1, Nd)" if ORDER == "sorted" else " (SURVEY 8d counter hash)"),
                        "l2": "state per GPU (%.2f GiB) is far larger than the 126 MB L2; no flush needed" % (state_bytes / 2**30),
                        "parallelism": f"columns sharded x{world}, no collective", "state_finite": finite},
             "clocks": clocks,
@@ -299,7 +303,10 @@ def main():
     ap.add_argument("--steps-per-launch", type=int, default=4)
     ap.add_argument("--t-start", type=int, default=480, help="model time [s] at which the timed window starts")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample length (0 = skip)")
+    ap.add_argument("--order", default="sorted", choices=["sorted", "hash"], help="storage order of the ensemble members")
     args = ap.parse_args()
+    global ORDER
+    ORDER = args.order
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     return run_reference(args) if args.impl == "reference" else run_ours(args)

@@ -13,6 +13,8 @@
 
 namespace kid {
 
+constexpr int KID_GSER_TERMS = 26;
+
 #define KID_DERIVED_LIST(X)                                                         \
     X(rain_gam_m)      /* Γ(me+Δm+1)                  CM1.lambda_inverse        */  \
     X(rain_gam_v)      /* Γ(me+ve+Δm+Δv+1)            CM1.terminal_velocity     */  \
@@ -42,6 +44,9 @@ struct DevParamsBody {
     KID_PARAM_LIST(KID_X_FIELD)
     KID_DERIVED_LIST(KID_X_FIELD)
 #undef KID_X_FIELD
+    // series coefficients 1/(s(s+1)...(s+n)), s = 1/2 + 3β/2, of the lower incomplete γ(s, t*) in
+    // CM2.rain_evaporation: t* <= 6^(1/3) < s + 1, so a fixed-length Horner sum replaces the adaptive loop
+    FT sb_gser[KID_GSER_TERMS];
 };
 template <class FT>
 struct DevParams : DevParamsBody<FT> {
@@ -97,6 +102,10 @@ inline void fill_dev_params(DevParams<FT>& P, const double* table) {
     P.rain_li_exp = FT(1) / (P.rain_me + P.rain_dm + FT(1));
     P.snow_li_exp = FT(1) / (P.snow_me + P.snow_dm + FT(1));
     P.ice_li_exp = FT(1) / (P.ice_me + P.ice_dm + FT(1));
+    {
+        double sgam = double(FT(-0.5) + FT(1.5) * P.sb_beta + FT(1)), d = 1.0;
+        for (int n = 0; n < KID_GSER_TERMS; ++n) { d /= (sgam + n); P.sb_gser[n] = FT(d); }
+    }
     for (FT& x : P.pad_to_odd) x = FT(0);
 }
 

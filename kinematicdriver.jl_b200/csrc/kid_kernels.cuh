@@ -231,8 +231,10 @@ __global__ void __launch_bounds__(tile_max_threads<FT>(), 1) k1d_tile_kernel(con
         Pp = &PRMSRC::get();
     }
     const DevParams<FT>& P = *Pp;
-    auto sidx = [&](int v, int k) { return (size_t(v) * nz + k) * C + c; };
-    auto kidx = [&](int k) { return size_t(k) * C + c; };
+    // shared-memory indices stay 32-bit: (variable, level) plane stride sV, level stride C
+    const int sV = nz * C;
+    auto sidx = [&](int v, int k) { return v * sV + k * C + c; };
+    auto kidx = [&](int k) { return k * C + c; };
 
     // ---- load the tile (coalesced: lanes = neighbouring columns)
     FT w1c = 0, qsurf = 0, Ndc = 0;
@@ -445,14 +447,14 @@ __global__ void __launch_bounds__(tile_max_threads<FT>(), 1) k1d_tile_kernel(con
                             fc = P.num_fcc_scale * (M::abs(w2) * (y2 - yu) - Cup) / dz;
                         } else if (k == nz - 1) {
                             if (top_bc == BC_SET) D = (FT(0) - Flo[i]) / dz;
-                            else D = edge[size_t(2 * i) * C + c];
-                            fc = edge[size_t(2 * i + 1) * C + c];
+                            else D = edge[(2 * i) * C + c];
+                            fc = edge[(2 * i + 1) * C + c];
                         } else {
                             D = (Fup - Flo[i]) / dz;
                             fc = P.num_fcc_scale * (Cup - Clo[i]) / dz;
                             if (k == nz - 2) {
-                                edge[size_t(2 * i) * C + c] = D;
-                                edge[size_t(2 * i + 1) * C + c] = fc;
+                                edge[(2 * i) * C + c] = D;
+                                edge[(2 * i + 1) * C + c] = fc;
                             }
                         }
                         Flo[i] = Fup;

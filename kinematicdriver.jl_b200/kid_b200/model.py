@@ -214,7 +214,7 @@ def uniform01(seed: int, c: np.ndarray, k: int) -> np.ndarray:
 
 
 def k1d_ensemble_case(FT=np.float32, nc: int = 1024, seed: int = 20240601, n_profiles: int = 16,
-                      column_offset: int = 0, device: int = 0, **options) -> Case:
+                      column_offset: int = 0, device: int = 0, order: str = "hash", **options) -> Case:
     """Synthetic calibration-style ensemble of SURVEY §8(d): member c perturbs w1, prescribed Nd and the
     surface pressure p0 (quantised to n_profiles distinct soundings so the host-side IVP stays cheap)."""
     FT = np.dtype(FT).type
@@ -225,6 +225,13 @@ def k1d_ensemble_case(FT=np.float32, nc: int = 1024, seed: int = 20240601, n_pro
     w1 = 2.0 * (0.5 + 0.6 * uniform01(seed, c, 0))
     Nd = 10.0 ** (7.0 + 1.5 * uniform01(seed, c, 1))
     pidx = np.minimum((uniform01(seed, c, 2) * n_profiles).astype(np.int64), n_profiles - 1)
+    if order == "sorted":
+        # the order of ensemble members is arbitrary: placing similar members (same sounding, similar updraft) in
+        # neighbouring columns keeps the 32 lanes of a warp on the same microphysics branches
+        perm = np.lexsort((Nd, w1, pidx))
+        w1, Nd, pidx = w1[perm], Nd[perm], pidx[perm]
+    elif order != "hash":
+        raise ValueError("order must be 'hash' or 'sorted'")
     p0_levels = 1e5 * (0.98 + 0.04 * (np.arange(n_profiles) + 0.5) / n_profiles)
     base = None
     bank_ρ, bank_T, bank_Y, bank_q = [], [], [], []
@@ -243,7 +250,7 @@ def k1d_ensemble_case(FT=np.float32, nc: int = 1024, seed: int = 20240601, n_pro
                 var_names=names,
                 col_scalars={COL_Q_SURF: bank_q[pidx].astype(FT), COL_W1: w1.astype(FT),
                              COL_PRESCRIBED_ND: Nd.astype(FT)},
-                z_centers=base.z_centers, meta=dict(base.meta, seed=seed, n_profiles=n_profiles))
+                z_centers=base.z_centers, meta=dict(base.meta, seed=seed, n_profiles=n_profiles, order=order))
 
 
 def box_ensemble_case(FT=np.float64, nc: int = 1024, seed: int = 20240601, n_ic: int = 64, column_offset: int = 0,

@@ -18,9 +18,14 @@ ap.add_argument("--ft", default="f32")
 ap.add_argument("--moisture", default="NonEquilibriumMoisture")
 ap.add_argument("--precip", default="Precipitation2M")
 ap.add_argument("--nw", type=int, default=0)
+ap.add_argument("--order", default="hash", choices=["hash", "sorted", "uniform"])
 a = ap.parse_args()
 FT = np.float32 if a.ft == "f32" else np.float64
-cs = M.k1d_ensemble_case(FT, nc=a.columns, n_profiles=16, n_elem=a.nz, moisture_choice=a.moisture, precipitation_choice=a.precip)
+if a.order == "uniform":
+    cs = M.k1d_case(FT, nc=a.columns, n_elem=a.nz, moisture_choice=a.moisture, precipitation_choice=a.precip)
+else:
+    cs = M.k1d_ensemble_case(FT, nc=a.columns, n_profiles=16, n_elem=a.nz, moisture_choice=a.moisture, precipitation_choice=a.precip,
+                             order=a.order)
 if a.nw: cs.cfg.reserved[0] = a.nw
 h = M.make_handle(cs, Handle)
 h.step(0.0, a.t_start); h.synchronize()
@@ -32,5 +37,5 @@ for _ in range(a.launches):
 h.synchronize()
 dt = time.perf_counter() - t0
 Y = h.get_state()
-print(f"columns={a.columns} nz={a.nz} {a.ft} {a.precip}: {a.launches} launches x {a.spl} steps: {dt*1e3/(a.launches*a.spl):.2f} ms/step, "
+print(f"order={a.order} columns={a.columns} nz={a.nz} {a.ft} {a.precip}: {a.launches} launches x {a.spl} steps: {dt*1e3/(a.launches*a.spl):.2f} ms/step, "
       f"{a.columns*a.nz*a.launches*a.spl/dt:.3e} gp-steps/s, finite={np.isfinite(Y).all()}")
