@@ -199,6 +199,7 @@ def run_ours(args):
     # ---------------- device-resident timing (value)
     sampler = ClockSampler(local)
     sampler.start()
+    time.sleep(1.0)  # let nvidia-smi finish initialising (it briefly holds driver locks) before the timed region
     n_launch = (args.steps + spl - 1) // spl
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(n_launch + 1)]
     l0 = h.launch_count
