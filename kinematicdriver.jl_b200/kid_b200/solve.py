@@ -1,0 +1,137 @@
+"""`ODE.solve` replacement and the driver entry points of the reference, on top of libkid_cuda.so.
+
+Mirrors (reference):
+  ODE.solve(problem, ODE.SSPRK33(); dt, saveat[, callback])   run_KiD_simulation.jl:159-166, run_box_simulation.jl:84-85
+  CO.simulation_output(aux, t) / condition_io / affect_io!      src/Common/netcdf_io.jl:144-194
+  run_KiD_simulation / run_box_simulation / run_K2D_simulation  test/experiments/*/
+
+The state stays on the device between save times; at every save time the state (and, if a callback asks for them, the
+aux fields) is downloaded once.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import k2d as K2
+from . import model as M
+from .lib import AUX_FIELDS, Handle
+
+
+@dataclass
+class ODESolution:
+    """What the reference's consumers read from the OrdinaryDiffEq solution: `.t` and `.u`
+    (run_box_simulation.jl:88-94, calibration/KiDUtils.jl:332-357)."""
+    t: list = field(default_factory=list)
+    u: list = field(default_factory=list)   # each [nc, nvars, nz]
+    var_names: tuple = ()
+    handle: object = None
+
+    def variable(self, name: str) -> np.ndarray:
+        """[n_saved, nc, nz] series of one prognostic variable."""
+        i = self.var_names.index(name)
+        return np.stack([u[:, i, :] for u in self.u])
+
+
+class OutputCadence:
+    """condition_io of src/Common/netcdf_io.jl:176-185, including its self-mutating accumulator: dt_io starts at
+    TS.dt_io, grows by dt every step and fires (and resets to 0) when it exceeds `output_interval`, or at t≈t_max."""
+
+    def __init__(self, TS: M.TimeStepping, output_interval: float = 1.0):
+        self.TS, self.interval = TS, output_interval
+        self.dt_io = TS.dt_io
+
+    def __call__(self, t: float) -> bool:
+        self.dt_io += self.TS.dt
+        if self.dt_io > self.interval:
+            self.dt_io = 0.0
+            return True
+        return abs(t - self.TS.t_max) < 1e-14 * max(1.0, abs(self.TS.t_max))
+
+
+def simulation_output(handle, t: float, fields=None) -> dict:
+    """The aux fields `CO.simulation_output(aux, t)` appends to the NetCDF file (netcdf_io.jl:144-170) plus the
+    `ql_max` time series entry, read from the device at time t."""
+    out = {f: handle.get_aux(t, f) for f in (fields or AUX_FIELDS)}
+    out["ql_max"] = float(np.max(out["q_liq"])) if "q_liq" in out else handle.reduce_max(t, "q_liq")
+    return out
+
+
+def solve(case: M.Case, tspan=None, dt: float | None = None, saveat: float | None = None, callback=None,
+          condition=None, backend=Handle, handle=None) -> ODESolution:
+    """ODE.solve(ODEProblem(rhs!, Y, tspan, aux), SSPRK33(); dt, saveat, callback).
+
+    saveat: save interval (the state at t0, every multiple of saveat and t_end is returned, as OrdinaryDiffEq does).
+    callback(handle, t): called after a step when condition(t) is true (DiscreteCallback(condition_io, affect_io!));
+    with a callback the device advances step by step between its firings.
+    """
+    TS = case.meta.get("TS")
+    dt = float(dt if dt is not None else case.cfg.dt)
+    if abs(dt - case.cfg.dt) > 0:
+        raise ValueError("dt differs from the dt the case was built with (it enters every limiter: TS.dt)")
+    t0, t_end = tspan if tspan is not None else (0.0, TS.t_max)
+    saveat = float(saveat if saveat is not None else (TS.dt_io if TS else t_end - t0))
+    h = handle or M.make_handle(case, backend)
+    sol = ODESolution(var_names=case.var_names, handle=h)
+    nsteps = int(round((t_end - t0) / dt))
+    save_every = max(1, int(round(saveat / dt)))
+    sol.t.append(t0)
+    sol.u.append(h.get_state())
+    done = 0
+    while done < nsteps:
+        nxt = min(nsteps, (done // save_every + 1) * save_every)
+        if callback is None:
+            h.step(t0 + done * dt, nxt - done)
+            done = nxt
+        else:
+            while done < nxt:
+                h.step(t0 + done * dt, 1)
+                done += 1
+                t = t0 + done * dt
+                if condition is None or condition(t):
+                    callback(h, t)
+        sol.t.append(t0 + done * dt)
+        sol.u.append(h.get_state())
+    return sol
+
+
+# ------------------------------------------------------------------ drivers
+def run_KiD_simulation(FT, opts: dict | None = None, nc: int = 1, output: bool = False, backend=Handle):
+    """test/experiments/KiD_driver/run_KiD_simulation.jl:13-166 (minus NetCDF/plots): returns (solution, outputs)."""
+    opts = dict(opts or {})
+    FT = {"Float64": np.float64, "Float32": np.float32}.get(opts.pop("FLOAT_TYPE", None), FT)
+    opts.pop("plotting_flag", None)
+    case = M.k1d_case(FT, nc=nc, **opts)
+    TS = case.meta["TS"]
+    outputs = []
+    cb = cond = None
+    if output:
+        cond = OutputCadence(TS)
+        cb = lambda h, t: outputs.append((t, simulation_output(h, t)))  # noqa: E731
+    h = M.make_handle(case, backend)
+    if output:
+        outputs.append((0.0, simulation_output(h, 0.0)))
+    o = case.meta["opts"]
+    sol = solve(case, (o["t_ini"], o["t_end"]), dt=TS.dt, saveat=TS.dt_io, callback=cb, condition=cond, handle=h)
+    return sol, outputs
+
+
+def run_box_simulation(FT, opts: dict | None = None, nc: int = 1, backend=Handle):
+    """test/experiments/box_driver/run_box_simulation.jl:12-124 (minus plots)."""
+    o = dict(qt=1e-3, Nd=1e8, k=2.0, rhod=1.22, precipitation_choice="Precipitation2M", rain_formation_choice="SB2006",
+             dt=1.0, dt_output=30.0, t_ini=0.0, t_end=3600.0, microphys_params={})
+    o.update(opts or {})
+    case = M.box_case(FT, nc=nc, precipitation_choice=o["precipitation_choice"],
+                      rain_formation_choice=o["rain_formation_choice"], qt=o["qt"], Nd=o["Nd"], k=o["k"], rhod=o["rhod"],
+                      dt=o["dt"], dt_output=o["dt_output"], t_ini=o["t_ini"], t_end=o["t_end"],
+                      microphys_params=o["microphys_params"])
+    return solve(case, (o["t_ini"], o["t_end"]), dt=o["dt"], saveat=o["dt_output"], backend=backend)
+
+
+def run_K2D_simulation(FT, opts: dict | None = None, backend=Handle):
+    """test/experiments/Ki2D_driver/run_kinematic2d_simulations.jl:15-171 (single-domain, minus NetCDF/plots)."""
+    o = dict(opts or {})
+    case = K2.k2d_case(FT, **o)
+    oo = case.meta["opts"]
+    return solve(case, (oo["t_ini"], oo["t_end"]), dt=oo["dt"], saveat=oo["dt_output"], backend=backend)
