@@ -63,6 +63,8 @@ struct kid_handle {
     int steps_per_launch = 0;
     int64_t launches = 0;
     std::vector<double> params;
+    DevParams<float> prm_f{};   // the shared parameter set, passed to every launch as a kernel argument
+    DevParams<double> prm_d{};
     bool params_set = false, profiles_set = false, state_set = false;
     int C = 32, NW = 1;
     // K2D
@@ -221,8 +223,8 @@ int check_ready(kid_handle* h) {
         // (re)evaluate the time-invariant profile constants after params or profiles changed; a shared profile
         // with per-column thermodynamic parameter sets is not supported (the constants would differ per column)
         cudaError_t e;
-        if (h->f64) e = h->lt->consts_d(make_args<double>(h, 0.0, 0, 0, 0), (double*)h->ps_liq, (double*)h->ps_mix, h->stream);
-        else e = h->lt->consts_f(make_args<float>(h, 0.0, 0, 0, 0), (float*)h->ps_liq, (float*)h->ps_mix, h->stream);
+        if (h->f64) e = h->lt->consts_d(make_args<double>(h, 0.0, 0, 0, 0), h->prm_d, (double*)h->ps_liq, (double*)h->ps_mix, h->stream);
+        else e = h->lt->consts_f(make_args<float>(h, 0.0, 0, 0, 0), h->prm_f, (float*)h->ps_liq, (float*)h->ps_mix, h->stream);
         if (e != cudaSuccess) return fail(std::string("profile_consts_kernel launch: ") + cudaGetErrorString(e));
         h->launches++;
         h->consts_dirty = false;
@@ -259,11 +261,11 @@ int launch_tile(kid_handle* h, double t0, int nsteps, int diag_mode, int field, 
     if (h->f64) {
         auto a = make_args<double>(h, t0, nsteps, diag_mode, field);
         a.update_prev = update_prev;
-        e = h->lt->k1d_d(h->cfg.moisture, diag_mode != 0, a, h->stream);
+        e = h->lt->k1d_d(h->cfg.moisture, diag_mode != 0, a, h->prm_d, h->stream);
     } else {
         auto a = make_args<float>(h, t0, nsteps, diag_mode, field);
         a.update_prev = update_prev;
-        e = h->lt->k1d_f(h->cfg.moisture, diag_mode != 0, a, h->stream);
+        e = h->lt->k1d_f(h->cfg.moisture, diag_mode != 0, a, h->prm_f, h->stream);
     }
     if (e != cudaSuccess) return fail(std::string("k1d_tile_kernel launch: ") + cudaGetErrorString(e));
     h->launches++;
@@ -271,8 +273,8 @@ int launch_tile(kid_handle* h, double t0, int nsteps, int diag_mode, int field, 
 }
 int launch_box(kid_handle* h, double t0, int nsteps) {
     cudaError_t e;
-    if (h->f64) e = h->lt->box_d(h->cfg.moisture, make_args<double>(h, t0, nsteps, 0, 0), h->stream);
-    else e = h->lt->box_f(h->cfg.moisture, make_args<float>(h, t0, nsteps, 0, 0), h->stream);
+    if (h->f64) e = h->lt->box_d(h->cfg.moisture, make_args<double>(h, t0, nsteps, 0, 0), h->prm_d, h->stream);
+    else e = h->lt->box_f(h->cfg.moisture, make_args<float>(h, t0, nsteps, 0, 0), h->prm_f, h->stream);
     if (e != cudaSuccess) return fail(std::string("box_step_kernel launch: ") + cudaGetErrorString(e));
     h->launches++;
     return 0;
@@ -459,12 +461,12 @@ int kid_set_params(kid_handle_t* h, const double* params, int32_t nparams, int32
             w1[c] = params[size_t(idx[c]) * KID_NPARAMS + KID_P_kid_w1];
             nd[c] = params[size_t(idx[c]) * KID_NPARAMS + KID_P_com_prescribed_Nd];
         }
-        // set 0 also goes to the __constant__ block: it serves the profile constants of a SHARED profile
+        // set 0 also becomes the shared kernel-argument set: it serves the profile constants of a SHARED profile
         // (thermodynamic parameters must then be common to all sets)
         if (h->f64) {
             std::vector<DevParams<double>> sets(nsets);
             for (int i = 0; i < nsets; ++i) fill_dev_params(sets[i], params + size_t(i) * KID_NPARAMS);
-            KID_CUDA(h->lt->upload_params_d(sets[0], h->stream));
+            h->prm_d = sets[0];
             KID_CUDA(cudaMalloc(&h->prm_sets, sets.size() * sizeof(sets[0])));
             KID_CUDA(cudaMemcpyAsync(h->prm_sets, sets.data(), sets.size() * sizeof(sets[0]), cudaMemcpyHostToDevice, h->stream));
             KID_CUDA(cudaStreamSynchronize(h->stream));
@@ -473,7 +475,7 @@ int kid_set_params(kid_handle_t* h, const double* params, int32_t nparams, int32
         } else {
             std::vector<DevParams<float>> sets(nsets);
             for (int i = 0; i < nsets; ++i) fill_dev_params(sets[i], params + size_t(i) * KID_NPARAMS);
-            KID_CUDA(h->lt->upload_params_f(sets[0], h->stream));
+            h->prm_f = sets[0];
             KID_CUDA(cudaMalloc(&h->prm_sets, sets.size() * sizeof(sets[0])));
             KID_CUDA(cudaMemcpyAsync(h->prm_sets, sets.data(), sets.size() * sizeof(sets[0]), cudaMemcpyHostToDevice, h->stream));
             KID_CUDA(cudaStreamSynchronize(h->stream));
@@ -486,16 +488,8 @@ int kid_set_params(kid_handle_t* h, const double* params, int32_t nparams, int32
         return 0;
     }
     if (choose_tile(h)) return 1;
-    if (h->f64) {
-        DevParams<double> P;
-        fill_dev_params(P, params);
-        KID_CUDA(h->lt->upload_params_d(P, h->stream));
-    } else {
-        DevParams<float> P;
-        fill_dev_params(P, params);
-        KID_CUDA(h->lt->upload_params_f(P, h->stream));
-    }
-    KID_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->f64) fill_dev_params(h->prm_d, params);
+    else fill_dev_params(h->prm_f, params);
     // per-column scalars default to the table values
     if (upload_columns(h, h->w1, nullptr, params[KID_P_kid_w1])) return 1;
     if (upload_columns(h, h->Nd, nullptr, params[KID_P_com_prescribed_Nd])) return 1;

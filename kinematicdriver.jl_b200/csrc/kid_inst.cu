@@ -7,52 +7,31 @@
 namespace kid {
 namespace {
 
-__constant__ DevParams<float> c_prm_f;
-__constant__ DevParams<double> c_prm_d;
-
-template <class FT> struct ConstPrm;
-template <> struct ConstPrm<float> {
-    static constexpr bool per_column = false;
-    static __device__ __forceinline__ const DevParams<float>& get() { return c_prm_f; }
-};
-template <> struct ConstPrm<double> {
-    static constexpr bool per_column = false;
-    static __device__ __forceinline__ const DevParams<double>& get() { return c_prm_d; }
-};
-// per-column parameter sets (calibration ensembles): staged in shared memory by the kernels
-template <class FT> struct ColumnPrm {
-    static constexpr bool per_column = true;
-    static __device__ __forceinline__ const DevParams<FT>& get();  // never called
-};
-
-cudaError_t upload_f(const DevParams<float>& p, cudaStream_t s) {
-    return cudaMemcpyToSymbolAsync(c_prm_f, &p, sizeof(p), 0, cudaMemcpyHostToDevice, s);
-}
-cudaError_t upload_d(const DevParams<double>& p, cudaStream_t s) {
-    return cudaMemcpyToSymbolAsync(c_prm_d, &p, sizeof(p), 0, cudaMemcpyHostToDevice, s);
-}
+// parameter source tags: one set shared by all columns (kernel argument) or per-column sets (shared memory)
+template <class FT> struct ConstPrm { static constexpr bool per_column = false; };
+template <class FT> struct ColumnPrm { static constexpr bool per_column = true; };
 
 template <class FT, int MOIST, bool DIAG, class PRM>
-cudaError_t launch_tile_p(const KArgs<FT>& a, cudaStream_t s) {
+cudaError_t launch_tile_p(const KArgs<FT>& a, const DevParams<FT>& P, cudaStream_t s) {
     auto kern = k1d_tile_kernel<FT, MOIST, KID_PRECIP, DIAG, PRM>;
     size_t smem = k1d_tile_smem_bytes<FT, MOIST, KID_PRECIP>(a.nz, a.C, PRM::per_column);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     dim3 block(a.C, a.NW), grid((a.nc + a.C - 1) / a.C);
-    kern<<<grid, block, smem, s>>>(a);
+    kern<<<grid, block, smem, s>>>(a, P);
     return cudaGetLastError();
 }
 template <class FT, int MOIST, bool DIAG>
-cudaError_t launch_tile(const KArgs<FT>& a, cudaStream_t s) {
-    return a.prm_sets ? launch_tile_p<FT, MOIST, DIAG, ColumnPrm<FT>>(a, s) : launch_tile_p<FT, MOIST, DIAG, ConstPrm<FT>>(a, s);
+cudaError_t launch_tile(const KArgs<FT>& a, const DevParams<FT>& P, cudaStream_t s) {
+    return a.prm_sets ? launch_tile_p<FT, MOIST, DIAG, ColumnPrm<FT>>(a, P, s) : launch_tile_p<FT, MOIST, DIAG, ConstPrm<FT>>(a, P, s);
 }
 template <class FT>
-cudaError_t k1d(int moisture, bool diag, const KArgs<FT>& a, cudaStream_t s) {
-    if (moisture == KID_MOIST_EQ) return diag ? launch_tile<FT, KID_MOIST_EQ, true>(a, s) : launch_tile<FT, KID_MOIST_EQ, false>(a, s);
-    return diag ? launch_tile<FT, KID_MOIST_NONEQ, true>(a, s) : launch_tile<FT, KID_MOIST_NONEQ, false>(a, s);
+cudaError_t k1d(int moisture, bool diag, const KArgs<FT>& a, const DevParams<FT>& P, cudaStream_t s) {
+    if (moisture == KID_MOIST_EQ) return diag ? launch_tile<FT, KID_MOIST_EQ, true>(a, P, s) : launch_tile<FT, KID_MOIST_EQ, false>(a, P, s);
+    return diag ? launch_tile<FT, KID_MOIST_NONEQ, true>(a, P, s) : launch_tile<FT, KID_MOIST_NONEQ, false>(a, P, s);
 }
 template <class FT, int MOIST, class PRM>
-cudaError_t box_p(const KArgs<FT>& a, cudaStream_t s) {
+cudaError_t box_p(const KArgs<FT>& a, const DevParams<FT>& P, cudaStream_t s) {
     const int bs = PRM::per_column ? 64 : 128;
     const size_t smem = PRM::per_column ? size_t(bs) * sizeof(DevParams<FT>) : 0;
     auto kern = box_step_kernel<FT, MOIST, KID_PRECIP, PRM>;
@@ -61,23 +40,23 @@ cudaError_t box_p(const KArgs<FT>& a, cudaStream_t s) {
         if (e != cudaSuccess) return e;
     }
     dim3 block(bs), grid((a.nc + bs - 1) / bs);
-    kern<<<grid, block, smem, s>>>(a);
+    kern<<<grid, block, smem, s>>>(a, P);
     return cudaGetLastError();
 }
 template <class FT>
-cudaError_t box(int moisture, const KArgs<FT>& a, cudaStream_t s) {
+cudaError_t box(int moisture, const KArgs<FT>& a, const DevParams<FT>& P, cudaStream_t s) {
     if (moisture == KID_MOIST_EQ)
-        return a.prm_sets ? box_p<FT, KID_MOIST_EQ, ColumnPrm<FT>>(a, s) : box_p<FT, KID_MOIST_EQ, ConstPrm<FT>>(a, s);
-    return a.prm_sets ? box_p<FT, KID_MOIST_NONEQ, ColumnPrm<FT>>(a, s) : box_p<FT, KID_MOIST_NONEQ, ConstPrm<FT>>(a, s);
+        return a.prm_sets ? box_p<FT, KID_MOIST_EQ, ColumnPrm<FT>>(a, P, s) : box_p<FT, KID_MOIST_EQ, ConstPrm<FT>>(a, P, s);
+    return a.prm_sets ? box_p<FT, KID_MOIST_NONEQ, ColumnPrm<FT>>(a, P, s) : box_p<FT, KID_MOIST_NONEQ, ConstPrm<FT>>(a, P, s);
 }
 template <class FT>
-cudaError_t consts(const KArgs<FT>& a, FT* ps_liq, FT* ps_mix, cudaStream_t s) {
+cudaError_t consts(const KArgs<FT>& a, const DevParams<FT>& P, FT* ps_liq, FT* ps_mix, cudaStream_t s) {
     const int ncol = a.prof_per_column ? a.nc : 1;
     dim3 block(128), grid((ncol + 127) / 128, a.nz);
     if (a.prm_sets && a.prof_per_column)
-        profile_consts_kernel<FT, ColumnPrm<FT>><<<grid, block, 0, s>>>(a.T, ps_liq, ps_mix, a.nz, a.nc, a.ncp, 1, a.prm_sets, a.col_to_set);
+        profile_consts_kernel<FT, ColumnPrm<FT>><<<grid, block, 0, s>>>(a.T, ps_liq, ps_mix, a.nz, a.nc, a.ncp, 1, a.prm_sets, a.col_to_set, P);
     else
-        profile_consts_kernel<FT, ConstPrm<FT>><<<grid, block, 0, s>>>(a.T, ps_liq, ps_mix, a.nz, a.nc, a.ncp, a.prof_per_column, nullptr, nullptr);
+        profile_consts_kernel<FT, ConstPrm<FT>><<<grid, block, 0, s>>>(a.T, ps_liq, ps_mix, a.nz, a.nc, a.ncp, a.prof_per_column, nullptr, nullptr, P);
     return cudaGetLastError();
 }
 template <class FT>
@@ -86,7 +65,7 @@ size_t smem_bytes(int moisture, int nz, int C, bool pcp) {
                                     : k1d_tile_smem_bytes<FT, KID_MOIST_NONEQ, KID_PRECIP>(nz, C, pcp);
 }
 
-const LaunchTable table = {upload_f, upload_d, k1d<float>, k1d<double>, box<float>, box<double>,
+const LaunchTable table = {k1d<float>, k1d<double>, box<float>, box<double>,
                            consts<float>, consts<double>, smem_bytes<float>, smem_bytes<double>};
 }  // namespace
 

@@ -193,7 +193,8 @@ inline size_t k1d_tile_smem_bytes(int nz, int C, bool per_column_params = false)
 }
 
 template <class FT, int MOIST, int PRECIP, bool DIAG, class PRMSRC>
-__global__ void __launch_bounds__(tile_max_threads<FT>(), 1) k1d_tile_kernel(const KArgs<FT> A) {
+__global__ void __launch_bounds__(tile_max_threads<FT>(), 1)
+k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared) {
     using L = Lay<MOIST, PRECIP>;
     using M = Mth<FT>;
     constexpr int NV = L::NV;
@@ -228,7 +229,9 @@ __global__ void __launch_bounds__(tile_max_threads<FT>(), 1) k1d_tile_kernel(con
         }
         Pp = sp + c;
     } else {
-        Pp = &PRMSRC::get();
+        // the shared set travels as a kernel argument: it sits in the constant bank (FFMA operands come straight from
+        // it) and, unlike a __constant__ symbol, belongs to this launch only — handles never see each other's values
+        Pp = &Pshared;
     }
     const DevParams<FT>& P = *Pp;
     // shared-memory indices stay 32-bit: (variable, level) plane stride sV, level stride C
@@ -510,7 +513,7 @@ __global__ void __launch_bounds__(tile_max_threads<FT>(), 1) k1d_tile_kernel(con
 // One thread per box, the whole state in registers for all nsteps x 3 stages
 // (src/BoxModel/ode_utils.jl:10-22: zero -> thermo -> precip -> precip sources).
 template <class FT, int MOIST, int PRECIP, class PRMSRC>
-__global__ void __launch_bounds__(128) box_step_kernel(const KArgs<FT> A) {
+__global__ void __launch_bounds__(128) box_step_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared) {
     using L = Lay<MOIST, PRECIP>;
     constexpr int NV = L::NV;
     const int gc = blockIdx.x * blockDim.x + threadIdx.x;
@@ -521,7 +524,7 @@ __global__ void __launch_bounds__(128) box_step_kernel(const KArgs<FT> A) {
         if (gc < A.nc) sp[threadIdx.x] = A.prm_sets[A.col_to_set[gc]];
         Pp = sp + threadIdx.x;
     } else {
-        Pp = &PRMSRC::get();
+        Pp = &Pshared;
     }
     const DevParams<FT>& P = *Pp;
     if (gc >= A.nc) return;
@@ -560,13 +563,14 @@ __global__ void __launch_bounds__(128) box_step_kernel(const KArgs<FT> A) {
 // p_sat,liq(T) and p_sat,mixed(T) per grid point (full-accuracy pow/exp; evaluated once per upload)
 template <class FT, class PRMSRC>
 __global__ void profile_consts_kernel(const FT* __restrict__ T, FT* __restrict__ ps_liq, FT* __restrict__ ps_mix, int nz, int nc,
-                                      int ncp, int per_column, const DevParams<FT>* prm_sets, const int* col_to_set) {
+                                      int ncp, int per_column, const DevParams<FT>* prm_sets, const int* col_to_set,
+                                      const __grid_constant__ DevParams<FT> Pshared) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
     if (c >= (per_column ? nc : 1)) return;
     const DevParams<FT>* Pp;
     if constexpr (PRMSRC::per_column) Pp = prm_sets + col_to_set[c];
-    else Pp = &PRMSRC::get();
+    else Pp = &Pshared;
     TD<FT, DevParams<FT>> td(*Pp);
     const size_t i = per_column ? size_t(k) * ncp + c : size_t(k);
     const FT t = T[i];

@@ -9,16 +9,14 @@
 namespace kid {
 
 struct LaunchTable {
-    cudaError_t (*upload_params_f)(const DevParams<float>&, cudaStream_t);
-    cudaError_t (*upload_params_d)(const DevParams<double>&, cudaStream_t);
-    // K1D / col_sed / (diag of) Box: tile kernel.  diag = false: step; true: rhs / aux mode
-    // the parameter source (shared __constant__ block or per-column sets) is picked from args.prm_sets
-    cudaError_t (*k1d_f)(int moisture, bool diag, const KArgs<float>&, cudaStream_t);
-    cudaError_t (*k1d_d)(int moisture, bool diag, const KArgs<double>&, cudaStream_t);
-    cudaError_t (*box_f)(int moisture, const KArgs<float>&, cudaStream_t);
-    cudaError_t (*box_d)(int moisture, const KArgs<double>&, cudaStream_t);
-    cudaError_t (*consts_f)(const KArgs<float>&, float* ps_liq, float* ps_mix, cudaStream_t);
-    cudaError_t (*consts_d)(const KArgs<double>&, double* ps_liq, double* ps_mix, cudaStream_t);
+    // K1D / col_sed / (diag of) Box: tile kernel.  diag = false: step; true: rhs / aux mode.
+    // The shared parameter set is a kernel argument; per-column sets (args.prm_sets != null) are staged in shared memory.
+    cudaError_t (*k1d_f)(int moisture, bool diag, const KArgs<float>&, const DevParams<float>&, cudaStream_t);
+    cudaError_t (*k1d_d)(int moisture, bool diag, const KArgs<double>&, const DevParams<double>&, cudaStream_t);
+    cudaError_t (*box_f)(int moisture, const KArgs<float>&, const DevParams<float>&, cudaStream_t);
+    cudaError_t (*box_d)(int moisture, const KArgs<double>&, const DevParams<double>&, cudaStream_t);
+    cudaError_t (*consts_f)(const KArgs<float>&, const DevParams<float>&, float* ps_liq, float* ps_mix, cudaStream_t);
+    cudaError_t (*consts_d)(const KArgs<double>&, const DevParams<double>&, double* ps_liq, double* ps_mix, cudaStream_t);
     size_t (*k1d_smem_f)(int moisture, int nz, int C, bool per_column_params);
     size_t (*k1d_smem_d)(int moisture, int nz, int C, bool per_column_params);
 };

@@ -430,3 +430,20 @@ def test_per_column_parameter_sets_box(FT):
     e = errors(Yg, Yo, cs.var_names)
     for v, err in e.items():
         assert err <= (1e-8 if FT == np.float64 else (5e-2 if v.startswith("N_") else 5e-3)), (v, err, e)
+
+
+def test_handles_with_different_parameters_do_not_interfere():
+    """Distinct handles are independent (the reference's calibration runs one simulation per thread with separate aux,
+    calibration/OptimizationUtils.jl:206): the parameter set travels with each launch, not in a global symbol."""
+    a_case = M.box_case(np.float32, nc=33, precipitation_choice="Precipitation2M", qt=1.5e-3)
+    b_case = M.box_case(np.float32, nc=33, precipitation_choice="Precipitation2M", qt=1.5e-3,
+                        microphys_params={"SB2006_collection_kernel_coeff_kcc": 2 * 4.44e9})
+    alone = M.make_handle(a_case, Handle)
+    alone.step(0.0, 300)
+    ref = alone.get_state()
+    a, b = M.make_handle(a_case, Handle), M.make_handle(b_case, Handle)  # b created (and its params set) after a
+    for s in range(0, 300, 50):  # interleaved launches
+        a.step(float(s), 50)
+        b.step(float(s), 50)
+    assert np.array_equal(a.get_state(), ref)
+    assert not np.array_equal(b.get_state(), ref)
