@@ -66,22 +66,72 @@ precip_enum(ps) = error("$(typeof(ps).name.name) is not on the device hot path o
 # already built (thermo_params, air_params, activation_params, kid_params, common_params, the style
 # structs).  `param_table` must list the names in the enum order of kid_params.h; the values are
 # whatever the reference structs hold (already of type FT), widened to Float64.
-function param_table(aux, moisture, precip)::Vector{Float64}
-    tp, ap, act, kp, cp = aux.thermo_params, aux.air_params, aux.activation_params, aux.kid_params, aux.common_params
+function param_table(aux, moisture, precip; fcc_scale = 1.0)::Vector{Float64}
+    tp, ap, act, cp = aux.thermo_params, aux.air_params, aux.activation_params, aux.common_params
+    kp = hasproperty(aux, :kid_params) ? aux.kid_params : nothing
     TDP = CO.TD.Parameters
+    FT = eltype(tp)
+    z(n) = zeros(Float64, n)
     v = Float64[]
-    # td_*
+    # td_* (16), air_* (3), arg_* (12)
     append!(v, Float64[TDP.T_0(tp), TDP.MSLP(tp), TDP.press_triple(tp), TDP.T_triple(tp), TDP.T_freeze(tp),
                        TDP.T_icenuc(tp), TDP.pow_icenuc(tp), TDP.R_d(tp), TDP.R_v(tp), TDP.cp_d(tp), TDP.cp_v(tp),
                        TDP.cp_l(tp), TDP.cp_i(tp), TDP.LH_v0(tp), TDP.LH_s0(tp), TDP.grav(tp)])
-    # air_*, arg_*, kid_*, com_*
     append!(v, Float64[ap.K_therm, ap.D_vapor, ap.ν_air])
     append!(v, Float64[act.σ, act.M_w, act.R, act.ρ_w, act.ρ_i, act.g, act.f1, act.f2, act.g1, act.g2, act.p1, act.p2])
-    append!(v, Float64[kp.w1, kp.t1, kp.r_dry, kp.std_dry, kp.κ, cp.prescribed_Nd])
-    # ... the remaining blocks (ne_*, p0m_*, rain_*, snow_*, ice_*, ce_*, rf_*, sb_*, num_fcc_scale) are filled the
-    # same way from moisture.liquid/ice, precip.params, precip.rain/snow/ice/ce/rain_formation/sedimentation;
-    # see kid_b200/parameters.py::flatten_params for the field-by-field map.
-    error("param_table: complete the struct-field map for the CloudMicrophysics version in use")
+    # kid_* (5), com_prescribed_Nd
+    append!(v, kp === nothing ? z(5) : Float64[kp.w1, kp.t1, kp.r_dry, kp.std_dry, kp.κ])
+    push!(v, Float64(cp.prescribed_Nd))
+    # ne_tau_relax_liq / ice
+    append!(v, moisture isa CO.NonEquilibriumMoisture ? Float64[moisture.liquid.τ_relax, moisture.ice.τ_relax] : z(2))
+    # p0m_tau_precip, qc_0, S_0
+    append!(v, precip isa CO.Precipitation0M ? Float64[precip.params.τ_precip, precip.params.qc_0, precip.params.S_0] : z(3))
+    if precip isa CO.Precipitation1M
+        r, sn, ic, ce, sed = precip.rain, precip.snow, precip.ice, precip.ce, precip.sedimentation
+        append!(v, Float64[r.acnv1M.τ, r.acnv1M.q_threshold, r.acnv1M.k,
+                           r.mass.r0, r.mass.m0, r.mass.me, r.mass.Δm, r.mass.χm,
+                           r.area.a0, r.area.ae, r.area.Δa, r.area.χa, r.pdf.n0, r.vent.a, r.vent.b,
+                           sed.rain.χv, sed.rain.ve, sed.rain.Δv, sed.rain.C_drag, sed.rain.ρw])
+        append!(v, Float64[sn.acnv1M.τ, sn.acnv1M.q_threshold, sn.acnv1M.k,
+                           sn.mass.r0, sn.mass.m0, sn.mass.me, sn.mass.Δm, sn.mass.χm,
+                           sn.area.a0, sn.area.ae, sn.area.Δa, sn.area.χa, sn.pdf.μ, sn.pdf.ν, sn.vent.a, sn.vent.b,
+                           sed.snow.χv, sed.snow.v0, sed.snow.ve, sed.snow.Δv])
+        append!(v, Float64[ic.mass.r0, ic.mass.m0, ic.mass.me, ic.mass.Δm, ic.mass.χm, ic.pdf.n0, ic.r_ice_snow])
+        append!(v, Float64[ce.e_lcl_rai, ce.e_lcl_sno, ce.e_icl_rai, ce.e_icl_sno, ce.e_rai_sno])
+        rf = precip.rain_formation
+        slots = z(11)
+        if rf isa CMP.KK2000
+            slots[1:4] = Float64[rf.acnv.A, rf.acnv.a, rf.acnv.b, rf.acnv.c]; slots[9:11] = Float64[rf.accr.A, rf.accr.a, rf.accr.b]
+        elseif rf isa CMP.B1994
+            slots[1:8] = Float64[rf.acnv.C, rf.acnv.a, rf.acnv.b, rf.acnv.c, rf.acnv.N_0, rf.acnv.d_low, rf.acnv.d_high, rf.acnv.k]
+            slots[9] = rf.accr.A
+        elseif rf isa CMP.TC1980
+            slots[1:7] = Float64[rf.acnv.a, rf.acnv.b, rf.acnv.D, rf.acnv.r_0, rf.acnv.me_liq, rf.acnv.m0_liq_coeff, rf.acnv.k]
+            slots[9] = rf.accr.A
+        elseif rf isa CMP.LD2004
+            slots[1:4] = Float64[rf.R_6C_0, rf.E_0, rf.ρ_w, rf.k]
+        elseif rf isa CMP.VarTimescaleAcnv
+            slots[1:2] = Float64[rf.τ, rf.α]
+        end
+        append!(v, slots)
+    else
+        append!(v, z(20 + 20 + 7 + 5 + 11))
+    end
+    if precip isa CO.Precipitation2M
+        sb, vel = precip.rain_formation, precip.sedimentation
+        limited = hasproperty(sb.pdf_r, :N0_min)
+        append!(v, Float64[sb.acnv.kcc, sb.acnv.x_star, sb.acnv.ρ0, sb.acnv.A, sb.acnv.a, sb.acnv.b,
+                           sb.accr.kcr, sb.accr.τ0, sb.accr.c, sb.self.krr, sb.self.κrr, sb.self.d,
+                           sb.brek.Deq, sb.brek.Dr_th, sb.brek.kbr, sb.brek.κbr,
+                           sb.evap.av, sb.evap.bv, sb.evap.α, sb.evap.β, sb.numadj.τ,
+                           sb.pdf_c.νc, sb.pdf_c.xc_min, sb.pdf_c.xc_max, sb.pdf_r.xr_min, sb.pdf_r.xr_max,
+                           limited ? sb.pdf_r.N0_min : 0, limited ? sb.pdf_r.N0_max : 0,
+                           limited ? sb.pdf_r.λ_min : 0, limited ? sb.pdf_r.λ_max : 0, sb.pdf_r.ρw,
+                           vel.aR, vel.bR, vel.cR, vel.ρ0])
+    else
+        append!(v, z(35))
+    end
+    push!(v, Float64(fcc_scale))  # num_fcc_scale
     return v
 end
 
