@@ -301,7 +301,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--columns", type=int, default=1 << 20, help="columns per GPU")
-    ap.add_argument("--steps-per-launch", type=int, default=4)
+    ap.add_argument("--steps-per-launch", type=int, default=10)
     ap.add_argument("--t-start", type=int, default=480, help="model time [s] at which the timed window starts")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample length (0 = skip)")
     ap.add_argument("--order", default="sorted", choices=["sorted", "hash"], help="storage order of the ensemble members")

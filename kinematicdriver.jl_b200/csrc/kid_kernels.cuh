@@ -117,10 +117,9 @@ __host__ __device__ constexpr AdvVar adv_entry(int i) {
 }
 
 // prescribed momentum flux ρw(t), src/K1DModel/tendency.jl:208-210 (evaluated in double, rounded to FT)
-template <class FT>
-KID_DEV FT rho_w_of_t(FT t, FT w1, FT t1) {
-    return (t < t1) ? FT(double(w1) * sin(M_PI * double(t) / double(t1))) : FT(0);
-}
+KID_DEV double rho_w_of_t(double t, double w1, double t1) { return (t < t1) ? w1 * sin(M_PI * t / t1) : 0.0; }
+// Float32: w1·sin(π t/t1) with sinpif (< 2 ulp) instead of a double-precision sine per thread and stage
+KID_DEV float rho_w_of_t(float t, float w1, float t1) { return (t < t1) ? w1 * sinpif(t / t1) : 0.0f; }
 
 // SSPRK33 stage combine exactly as OrdinaryDiffEq's perform_step! writes it
 template <class FT>
@@ -259,6 +258,7 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
     const bool with_adv = (A.model == KID_MODEL_K1D || A.model == KID_MODEL_K1D_COL_SED) || k2d;
     const bool stale_Naer = (A.model == KID_MODEL_BOX || A.model == KID_MODEL_K1D_COL_SED) && A.aux_Naer != nullptr;
     const FT dt = A.dt, dz = A.dz;
+    const FT inv_dt = FT(1) / dt, inv_dz = FT(1) / dz;
     const int nstage_total = DIAG ? 1 : 3 * A.nsteps;
 
 #pragma unroll 1
@@ -398,7 +398,7 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                     if (k1d) act_Nl = (A.sw.local_activation || k == cbk) ? acts[kidx(k)] : FT(0);
                 }
                 Sources<FT> src;
-                point_source_tendencies<FT, MOIST, PRECIP>(P, A.sw, a, Ndc, dt, k1d, act_Nl, src, tend);
+                point_source_tendencies<FT, MOIST, PRECIP>(P, A.sw, a, Ndc, inv_dt, k1d, act_Nl, src, tend);
 
                 if (with_adv) {
                     const bool has_up = (k + 1 < nz);
@@ -439,22 +439,22 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                         const FT yk = y[e.idx];
                         const FT yu = has_up ? (up_own ? Ys[sidx(e.idx, k + 1)] : hi[i]) : FT(0);
                         const FT w = wv[e.vel];
-                        const FT Fup = has_up ? w * ((yu + yk) / FT(2)) : FT(0);
+                        const FT Fup = has_up ? w * ((yu + yk) * FT(0.5)) : FT(0);
                         const FT Cup = has_up ? M::abs(w) * (yu - yk) : FT(0);
                         FT D, fc;
                         if (k == 0) {
                             const FT y2 = Ys[sidx(e.idx, 2)];
                             const FT w2 = wv2[e.vel];
-                            if (e.bot == BC_SET) D = (Fup - surf_flux[e.botval]) / dz;
-                            else D = (w2 * ((y2 + yu) / FT(2)) - Fup) / dz;
-                            fc = P.num_fcc_scale * (M::abs(w2) * (y2 - yu) - Cup) / dz;
+                            if (e.bot == BC_SET) D = (Fup - surf_flux[e.botval]) * inv_dz;
+                            else D = (w2 * ((y2 + yu) * FT(0.5)) - Fup) * inv_dz;
+                            fc = P.num_fcc_scale * (M::abs(w2) * (y2 - yu) - Cup) * inv_dz;
                         } else if (k == nz - 1) {
-                            if (top_bc == BC_SET) D = (FT(0) - Flo[i]) / dz;
+                            if (top_bc == BC_SET) D = (FT(0) - Flo[i]) * inv_dz;
                             else D = edge[(2 * i) * C + c];
                             fc = edge[(2 * i + 1) * C + c];
                         } else {
-                            D = (Fup - Flo[i]) / dz;
-                            fc = P.num_fcc_scale * (Cup - Clo[i]) / dz;
+                            D = (Fup - Flo[i]) * inv_dz;
+                            fc = P.num_fcc_scale * (Cup - Clo[i]) * inv_dz;
                             if (k == nz - 2) {
                                 edge[(2 * i) * C + c] = D;
                                 edge[(2 * i + 1) * C + c] = fc;
@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(128) box_step_kernel(const KArgs<FT> A, const 
             thermo_point<FT, MOIST, PRECIP>(P, y, rho_dry, T, psl, psm, a);
             if (A.aux_Naer) a.N_aer = Naer_aux;
             Sources<FT> src;
-            point_source_tendencies<FT, MOIST, PRECIP>(P, A.sw, a, Ndc, dt, false, FT(0), src, tend);
+            point_source_tendencies<FT, MOIST, PRECIP>(P, A.sw, a, Ndc, FT(1) / dt, false, FT(0), src, tend);
 #pragma unroll
             for (int v = 0; v < NV; ++v) y[v] = ssprk33_combine(stage, u[v], y[v], dt, tend[v]);
         }
