@@ -232,8 +232,8 @@ int check_ready(kid_handle* h) {
     return 0;
 }
 
-// tile geometry: the largest power-of-two number of columns per CTA whose tile fits in
-// shared memory, and as many level chunks as 512 threads / 3 levels per chunk allow
+// tile geometry: the largest power-of-two number of columns per CTA whose tile fits in shared memory, and as
+// many levels per round (threads per column) as the thread budget allows
 int choose_tile(kid_handle* h) {
     int dev = 0, max_smem = 0;
     KID_CUDA(cudaGetDevice(&dev));
@@ -249,7 +249,7 @@ int choose_tile(kid_handle* h) {
     size_t s = h->f64 ? h->lt->k1d_smem_d(moist, nz, C, pcp) : h->lt->k1d_smem_f(moist, nz, C, pcp);
     if (s > size_t(max_smem)) return fail("column too tall for one shared-memory tile (nz too large)");
     int maxt = h->f64 ? tile_max_threads<double>() : tile_max_threads<float>();
-    int NW = std::max(1, std::min(maxt / C, nz / 3));
+    int NW = std::max(2, std::min(maxt / C, nz));
     if (h->cfg.reserved[0] > 0) NW = std::max(1, std::min(NW, int(h->cfg.reserved[0])));  // tuning override
     h->C = C;
     h->NW = NW;

@@ -187,7 +187,7 @@ inline size_t k1d_tile_smem_bytes(int nz, int C, bool per_column_params = false)
     nfl += size_t(2) * nz * C;                 // rho_dry, T
     if (L::has_pr) nfl += size_t(2) * nz * C;  // vt1, vt2
     if (L::is2m) nfl += size_t(nz) * C;        // activation rate
-    nfl += size_t(2) * NADV * C;               // top-extrapolation scratch
+    nfl += size_t(4) * NADV * C;               // round-boundary stash [2 parities][2 levels][NADV]
     return nfl * sizeof(FT) + size_t(2) * C * sizeof(int);
 }
 
@@ -202,7 +202,10 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
     const int c = threadIdx.x, j = threadIdx.y;
     const int gc = blockIdx.x * C + c;
     const bool active = gc < A.nc;
-    const int k0 = (j * nz) / NW, k1 = ((j + 1) * nz) / NW;
+    // level assignment: in round r thread (c, j) works on level r·NW + j.  A round is a block of NW consecutive
+    // levels handled by NW different warps at the same time, so every warp carries one level of the cloudy part of
+    // the column and one of the clear part: the work is balanced across warps and there is no serial sweep.
+    const int R = (nz + NW - 1) / NW;
     const size_t plane = size_t(nz) * ncp;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -213,10 +216,10 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
     FT* vt1s = nullptr; FT* vt2s = nullptr; FT* acts = nullptr;
     if constexpr (L::has_pr) { vt1s = nxt; vt2s = nxt + size_t(nz) * C; nxt += size_t(2) * nz * C; }
     if constexpr (L::is2m) { acts = nxt; nxt += size_t(nz) * C; }
-    FT* edge = nxt;                            // [2*NADV][C]
-    int* cb = reinterpret_cast<int*>(edge + size_t(2) * NADV * C);  // [2][C]
-    // parameters: the shared __constant__ block, or this column's own set staged in shared memory as
-    // [column][word] with an odd word count (conflict-free when the 32 lanes read the same field)
+    FT* stash = nxt;                           // [2][2][NADV][C]: old values of the last two levels of a block
+    int* cb = reinterpret_cast<int*>(stash + size_t(4) * NADV * C);  // [2][C]
+    // parameters: the shared set (kernel argument, constant bank), or this column's own set staged in shared memory
+    // as [column][word] with an odd word count (conflict-free when the 32 lanes read the same field)
     const DevParams<FT>* Pp;
     if constexpr (PRMSRC::per_column) {
         size_t off = (reinterpret_cast<size_t>(cb + 2 * C) + 15) & ~size_t(15);
@@ -241,7 +244,7 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
     // ---- load the tile (coalesced: lanes = neighbouring columns)
     FT w1c = 0, qsurf = 0, Ndc = 0;
     if (active) {
-        for (int k = k0; k < k1; ++k) {
+        for (int k = j; k < nz; k += NW) {
 #pragma unroll
             for (int v = 0; v < NV; ++v) Ys[sidx(v, k)] = A.Y[v * plane + size_t(k) * ncp + gc];
             size_t pi = A.prof_per_column ? size_t(k) * ncp + gc : size_t(k);
@@ -280,12 +283,12 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
             return FT(wxd * sin(M_PI / A.height * (A.z_min + double(dz) * kface)));
         };
 
-        // ---- pass 1 (pointwise): terminal velocities and activation rate of the own levels
+        // ---- pass 1 (pointwise): terminal velocities and activation rate of this thread's levels
         if constexpr (L::has_pr) {
             if (active) {
                 int first = INT_MAX;
 #pragma unroll 1
-                for (int k = k0; k < k1; ++k) {
+                for (int k = j; k < nz; k += NW) {
                     FT y[NV];
 #pragma unroll
                     for (int v = 0; v < NV; ++v) y[v] = Ys[sidx(v, k)];
@@ -298,8 +301,6 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                     vt2s[kidx(k)] = v2;
                     if constexpr (L::is2m) {
                         FT S_Nl = FT(0);
-                        // non-local activation keeps only the LOWEST activating level, so once this thread has a
-                        // candidate its higher levels can never be selected: skip their ARG evaluation
                         FT q_rai_act = a.q_rai, N_liq_act = a.N_liq, N_rai_act = a.N_rai;
                         if (k2d) {
                             // K2D calls activation BEFORE precompute_aux_precip! (K2DModel/ode_utils.jl:43-44): it
@@ -314,6 +315,8 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                                 A.prev_aux[2 * plane + pi] = a.N_rai;
                             }
                         }
+                        // non-local activation keeps only the LOWEST activating level, so once this thread has a
+                        // candidate its higher levels can never be selected: skip their ARG evaluation
                         if (k1d && (A.sw.local_activation || first == INT_MAX || k2d)) {
                             FT p = pressure_point<FT, MOIST, PRECIP>(P, a);
                             FT rw_c = k2d ? (rwf(k + 1) + rwf(k)) / FT(2) : rw;  // InterpolateF2C
@@ -333,62 +336,102 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
             }
             __syncthreads();
         }
-
-        // ---- halo pre-read: everything owned by the neighbouring chunks that the sweep needs
-        FT lo[NADV], hi[NADV];
-        FT lo_rd = 0, hi_rd = 0, lo_v1 = 0, hi_v1 = 0, lo_v2 = 0, hi_v2 = 0;
         int cbk = INT_MAX;
-#pragma unroll
-        for (int i = 0; i < NADV; ++i) lo[i] = hi[i] = FT(0);
-        if (active && with_adv) {
-            static_for<0, NADV>([&](auto I) {
-                constexpr int i = decltype(I)::value;
-                constexpr int vi = adv_entry<MOIST, PRECIP>(i).idx;
-                if (k0 > 0) lo[i] = Ys[sidx(vi, k0 - 1)];
-                if (k1 < nz) hi[i] = Ys[sidx(vi, k1)];
-            });
-            if (k0 > 0) lo_rd = rds[kidx(k0 - 1)];
-            if (k1 < nz) hi_rd = rds[kidx(k1)];
-            if constexpr (L::has_pr) {
-                if (k0 > 0) { lo_v1 = vt1s[kidx(k0 - 1)]; lo_v2 = vt2s[kidx(k0 - 1)]; }
-                if (k1 < nz) { hi_v1 = vt1s[kidx(k1)]; hi_v2 = vt2s[kidx(k1)]; }
-            }
-        }
         if constexpr (L::is2m) {
             cbk = cb[par * C + c];
-            if (j == 0) cb[(par ^ 1) * C + c] = INT_MAX;
+            if (j == 0) cb[(par ^ 1) * C + c] = INT_MAX;  // next stage's slot; its last readers passed the barrier above
         }
-        __syncthreads();
+        const FT surf_flux[3] = {FT(0), rw * qsurf, rw * Ndc * (FT(1) - qsurf) / FT(1.225)};  // ρw0 = 0 in K2D
 
-        // ---- pass 2: sources + stencil + stage combine, sweeping the own levels upward
-        if (active) {
-            FT Flo[NADV], Clo[NADV];
+        // ---- pass 2: rounds over blocks of NW levels.  READ phase: every thread gathers the OLD neighbours of its
+        // level and turns them into the advective tendency; barrier; WRITE phase: sources + stage combine, in place.
+#pragma unroll 1
+        for (int r = 0; r < R; ++r) {
+            const int k = r * NW + j;
+            const int kb = r * NW;  // first level of this block: lower levels were overwritten in earlier rounds
+            const bool valid = active && k < nz;
+            FT y[NV], adv[NADV];
 #pragma unroll
-            for (int i = 0; i < NADV; ++i) Flo[i] = Clo[i] = FT(0);
-            const FT surf_flux[3] = {FT(0), rw * qsurf, rw * Ndc * (FT(1) - qsurf) / FT(1.225)};  // ρw0 = 0 in K2D
-            if (with_adv && k0 > 0 && k0 < k1) {
-                // faces below the chunk: velocity and fluxes from the pre-read halo
-                FT rho_k = rds[kidx(k0)] + Ys[sidx(L::tot, k0)];
-                FT rho_l = lo_rd + lo[0];
-                FT wa = rwf(k0) / ((rho_k + rho_l) / FT(2));
-                FT wv[3] = {wa, wa, wa};
-                if constexpr (L::has_pr) {
-                    wv[1] = wa - (vt1s[kidx(k0)] + lo_v1) / FT(2);
-                    wv[2] = wa - (vt2s[kidx(k0)] + lo_v2) / FT(2);
-                }
+            for (int i = 0; i < NADV; ++i) adv[i] = FT(0);
+            if (valid) {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) y[v] = Ys[sidx(v, k)];
+            }
+            if (valid && with_adv) {
+                // old value of advected variable i (state index vi) at level kk: this block and above are untouched,
+                // the two levels below the block come from the stash written by the previous round
+                auto old = [&](int vi, int i, int kk) -> FT {
+                    if (kk >= kb) return Ys[sidx(vi, kk)];
+                    return stash[(((r & 1) * 2 + (kb - 1 - kk)) * NADV + i) * C + c];
+                };
+                auto rho_at = [&](int kk) -> FT { return rds[kidx(kk)] + old(L::tot, 0, kk); };
+                // velocities (air, air - vt1, air - vt2) at face f between cells f-1 and f
+                auto face_w = [&](int f, FT rho_a, FT rho_b, FT* wv) {
+                    FT wa = rwf(f) / ((rho_a + rho_b) / FT(2));
+                    wv[0] = wv[1] = wv[2] = wa;
+                    if constexpr (L::has_pr) {
+                        wv[1] = wa - (vt1s[kidx(f)] + vt1s[kidx(f - 1)]) / FT(2);
+                        wv[2] = wa - (vt2s[kidx(f)] + vt2s[kidx(f - 1)]) / FT(2);
+                    }
+                };
+                const bool has_lo = k > 0, has_up = k + 1 < nz;
+                const FT rho_k = rds[kidx(k)] + y[L::tot];
+                FT w_lo[3] = {0, 0, 0}, w_up[3] = {0, 0, 0}, w_x[3] = {0, 0, 0};  // w_x: face 2 (k = 0) or nz-2 (k = nz-1)
+                FT rho_u = FT(0), rho_l = FT(0);
+                if (has_up) { rho_u = rho_at(k + 1); face_w(k + 1, rho_u, rho_k, w_up); }
+                if (has_lo) { rho_l = rho_at(k - 1); face_w(k, rho_k, rho_l, w_lo); }
+                if (k == 0) face_w(2, rho_at(2), rho_u, w_x);
+                if (k == nz - 1) face_w(nz - 2, rho_l, rho_at(nz - 3), w_x);
                 static_for<0, NADV>([&](auto I) {
                     constexpr int i = decltype(I)::value;
                     constexpr AdvVar e = adv_entry<MOIST, PRECIP>(i);
-                    FT yk = Ys[sidx(e.idx, k0)];
-                    Flo[i] = wv[e.vel] * ((yk + lo[i]) / FT(2));
-                    Clo[i] = M::abs(wv[e.vel]) * (yk - lo[i]);
+                    // K2D (K2DModel/tendency.jl:114-213): N_liq and N_aer are not advected, the precipitation
+                    // divergence extrapolates at BOTH ends, q_tot always gets the flux correction
+                    if (k2d && (e.idx == L::Nl || e.idx == L::Na)) return;
+                    const int top_bc = (k2d && e.vel != VEL_AIR) ? BC_EXTRAP : e.top;
+                    const FT yk = y[e.idx];
+                    const FT yu = has_up ? old(e.idx, i, k + 1) : FT(0);
+                    const FT yl = has_lo ? old(e.idx, i, k - 1) : FT(0);
+                    const FT wu = w_up[e.vel], wl = w_lo[e.vel];
+                    const FT Fup = wu * ((yu + yk) * FT(0.5)), Cup = M::abs(wu) * (yu - yk);
+                    const FT Flo = wl * ((yk + yl) * FT(0.5)), Clo = M::abs(wl) * (yk - yl);
+                    FT D, fc;
+                    if (k == 0) {  // bottom cell: SetValue flux, or the stencil of cell 1 (Extrapolate)
+                        const FT y2 = old(e.idx, i, 2);
+                        const FT w2 = w_x[e.vel];
+                        if (e.bot == BC_SET) D = (Fup - surf_flux[e.botval]) * inv_dz;
+                        else D = (w2 * ((y2 + yu) * FT(0.5)) - Fup) * inv_dz;
+                        fc = P.num_fcc_scale * (M::abs(w2) * (y2 - yu) - Cup) * inv_dz;
+                    } else if (k == nz - 1) {  // top cell: SetValue(0) flux, or the stencil of cell nz-2
+                        const FT yll = old(e.idx, i, nz - 3);
+                        const FT wll = w_x[e.vel];
+                        if (top_bc == BC_SET) D = (FT(0) - Flo) * inv_dz;
+                        else D = (Flo - wll * ((yl + yll) * FT(0.5))) * inv_dz;
+                        fc = P.num_fcc_scale * (Clo - M::abs(wll) * (yl - yll)) * inv_dz;
+                    } else {
+                        D = (Fup - Flo) * inv_dz;
+                        fc = P.num_fcc_scale * (Cup - Clo) * inv_dz;
+                    }
+                    const bool fcc_on = (e.fcc == FCC_ALWAYS) || A.sw.qtot_flux_correction || k2d;
+                    FT a_i = -D;
+                    if (fcc_on) a_i += fc;
+                    adv[i] = a_i;
+                    if (e.to_tot && k2d)  // S is DSS'd on its own before it is added to ρq_tot and its own variable
+                        A.outS[size_t(e.vel == VEL_VT1 ? 0 : 1) * plane + size_t(k) * ncp + gc] = a_i;
                 });
+                // the next round needs the OLD values of this block's last two levels
+                if (kb + NW < nz && j >= NW - 2) {
+                    static_for<0, NADV>([&](auto I) {
+                        constexpr int i = decltype(I)::value;
+                        constexpr int vi = adv_entry<MOIST, PRECIP>(i).idx;
+                        stash[((((r + 1) & 1) * 2 + (NW - 1 - j)) * NADV + i) * C + c] = y[vi];
+                    });
+                }
             }
-#pragma unroll 1
-            for (int k = k0; k < k1; ++k) {
-                FT y[NV], tend[NV];
-#pragma unroll
-                for (int v = 0; v < NV; ++v) y[v] = Ys[sidx(v, k)];
+            __syncthreads();  // every thread of the tile has read its old neighbours
+
+            if (valid) {
+                FT tend[NV];
                 Point<FT> a;
                 const size_t ppi = A.prof_per_column ? size_t(k) * ncp + gc : size_t(k);
                 thermo_point<FT, MOIST, PRECIP>(P, y, rds[kidx(k)], Ts[kidx(k)], A.ps_liq[ppi], A.ps_mix[ppi], a);
@@ -399,83 +442,19 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                 }
                 Sources<FT> src;
                 point_source_tendencies<FT, MOIST, PRECIP>(P, A.sw, a, Ndc, inv_dt, k1d, act_Nl, src, tend);
-
                 if (with_adv) {
-                    const bool has_up = (k + 1 < nz);
-                    const bool up_own = (k + 1 < k1);
-                    // upper face k+1/2 (and k+3/2 for the bottom cell, which copies cell 1's stencil)
-                    FT wv[3] = {FT(0), FT(0), FT(0)}, wv2[3] = {FT(0), FT(0), FT(0)};
-                    FT v1k = FT(0), v2k = FT(0);
-                    if constexpr (L::has_pr) { v1k = vt1s[kidx(k)]; v2k = vt2s[kidx(k)]; }
-                    if (has_up) {
-                        FT rho_u = (up_own ? rds[kidx(k + 1)] : hi_rd) + (up_own ? Ys[sidx(L::tot, k + 1)] : hi[0]);
-                        FT wa = rwf(k + 1) / ((rho_u + a.rho) / FT(2));
-                        wv[0] = wv[1] = wv[2] = wa;
-                        if constexpr (L::has_pr) {
-                            FT v1u = up_own ? vt1s[kidx(k + 1)] : hi_v1;
-                            FT v2u = up_own ? vt2s[kidx(k + 1)] : hi_v2;
-                            wv[1] = wa - (v1u + v1k) / FT(2);
-                            wv[2] = wa - (v2u + v2k) / FT(2);
-                        }
-                        if (k == 0) {
-                            FT rho_2 = rds[kidx(2)] + Ys[sidx(L::tot, 2)];
-                            FT wa2 = rwf(2) / ((rho_2 + rho_u) / FT(2));
-                            wv2[0] = wv2[1] = wv2[2] = wa2;
-                            if constexpr (L::has_pr) {
-                                wv2[1] = wa2 - (vt1s[kidx(2)] + vt1s[kidx(1)]) / FT(2);
-                                wv2[2] = wa2 - (vt2s[kidx(2)] + vt2s[kidx(1)]) / FT(2);
-                            }
-                        }
-                    }
                     FT S_tot = FT(0);
                     bool any_S = false;
                     static_for<0, NADV>([&](auto I) {
                         constexpr int i = decltype(I)::value;
                         constexpr AdvVar e = adv_entry<MOIST, PRECIP>(i);
-                        // K2D (K2DModel/tendency.jl:114-213): N_liq and N_aer are not advected, the precipitation
-                        // divergence extrapolates at BOTH ends, q_tot always gets the flux correction
-                        if (k2d && (e.idx == L::Nl || e.idx == L::Na)) return;
-                        const int top_bc = (k2d && e.vel != VEL_AIR) ? BC_EXTRAP : e.top;
-                        const FT yk = y[e.idx];
-                        const FT yu = has_up ? (up_own ? Ys[sidx(e.idx, k + 1)] : hi[i]) : FT(0);
-                        const FT w = wv[e.vel];
-                        const FT Fup = has_up ? w * ((yu + yk) * FT(0.5)) : FT(0);
-                        const FT Cup = has_up ? M::abs(w) * (yu - yk) : FT(0);
-                        FT D, fc;
-                        if (k == 0) {
-                            const FT y2 = Ys[sidx(e.idx, 2)];
-                            const FT w2 = wv2[e.vel];
-                            if (e.bot == BC_SET) D = (Fup - surf_flux[e.botval]) * inv_dz;
-                            else D = (w2 * ((y2 + yu) * FT(0.5)) - Fup) * inv_dz;
-                            fc = P.num_fcc_scale * (M::abs(w2) * (y2 - yu) - Cup) * inv_dz;
-                        } else if (k == nz - 1) {
-                            if (top_bc == BC_SET) D = (FT(0) - Flo[i]) * inv_dz;
-                            else D = edge[(2 * i) * C + c];
-                            fc = edge[(2 * i + 1) * C + c];
-                        } else {
-                            D = (Fup - Flo[i]) * inv_dz;
-                            fc = P.num_fcc_scale * (Cup - Clo[i]) * inv_dz;
-                            if (k == nz - 2) {
-                                edge[(2 * i) * C + c] = D;
-                                edge[(2 * i + 1) * C + c] = fc;
-                            }
-                        }
-                        Flo[i] = Fup;
-                        Clo[i] = Cup;
-                        const bool fcc_on = (e.fcc == FCC_ALWAYS) || A.sw.qtot_flux_correction || k2d;
                         if (e.to_tot) {
-                            FT S = -D;
-                            S += fc;
-                            if (k2d) {  // S is DSS'd on its own before it is added to ρq_tot and its own variable
-                                A.outS[size_t(e.vel == VEL_VT1 ? 0 : 1) * plane + size_t(k) * ncp + gc] = S;
-                                return;
-                            }
-                            tend[e.idx] += S;
-                            S_tot = any_S ? S_tot + S : S;
+                            if (k2d) return;
+                            tend[e.idx] += adv[i];
+                            S_tot = any_S ? S_tot + adv[i] : adv[i];
                             any_S = true;
                         } else {
-                            tend[e.idx] += -D;
-                            if (fcc_on) tend[e.idx] += fc;
+                            tend[e.idx] += adv[i];
                         }
                     });
                     if (any_S) tend[L::tot] += S_tot;
@@ -503,8 +482,8 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                 }
             }
         }
-        // next stage's pass 1 only touches own levels of Ys and writes vt/act arrays, whose
-        // neighbours were pre-read above; a barrier is still needed when there is no pass 1
+        // the next stage's pass 1 only reads this thread's own levels and writes vt/act entries whose readers have all
+        // passed the last round's barrier; without a pass 1 the next READ phase needs the new neighbours: barrier
         if constexpr (!L::has_pr) __syncthreads();
     }
 }
