@@ -284,6 +284,7 @@ def run_ours(args):
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_gp_step": BYTES_PER_GP_STEP,
                          "kernel": "k1d_tile_kernel<float,NonEq,2M>", "avg_launch_ms": avg_launch_ms,
+                         "launch_ms": [round(x, 3) for x in launch_ms], "timed_region_ms": ms_total,
                          "note": "the fused kernel is FP32/MUFU-pipe bound, not HBM bound: see profiles/ for pipe utilisation"},
             "cpu_baseline": cpu,
         }
