@@ -187,7 +187,7 @@ inline size_t k1d_tile_smem_bytes(int nz, int C, bool per_column_params = false)
     nfl += size_t(2) * nz * C;                 // rho_dry, T
     if (L::has_pr) nfl += size_t(2) * nz * C;  // vt1, vt2
     if (L::is2m) nfl += size_t(nz) * C;        // activation rate
-    nfl += size_t(4) * NADV * C;               // round-boundary stash [2 parities][2 levels][NADV]
+    nfl += size_t(4) * L::NV * C;              // round-boundary stash [2 parities][2 levels][NV]
     return nfl * sizeof(FT) + size_t(2) * C * sizeof(int);
 }
 
@@ -216,8 +216,8 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
     FT* vt1s = nullptr; FT* vt2s = nullptr; FT* acts = nullptr;
     if constexpr (L::has_pr) { vt1s = nxt; vt2s = nxt + size_t(nz) * C; nxt += size_t(2) * nz * C; }
     if constexpr (L::is2m) { acts = nxt; nxt += size_t(nz) * C; }
-    FT* stash = nxt;                           // [2][2][NADV][C]: old values of the last two levels of a block
-    int* cb = reinterpret_cast<int*>(stash + size_t(4) * NADV * C);  // [2][C]
+    FT* stash = nxt;                           // [2][2][NV][C]: old values of the last two levels of a block
+    int* cb = reinterpret_cast<int*>(stash + size_t(4) * NV * C);  // [2][C]
     // parameters: the shared set (kernel argument, constant bank), or this column's own set staged in shared memory
     // as [column][word] with an odd word count (conflict-free when the 32 lanes read the same field)
     const DevParams<FT>* Pp;
@@ -358,13 +358,17 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                 for (int v = 0; v < NV; ++v) y[v] = Ys[sidx(v, k)];
             }
             if (valid && with_adv) {
-                // old value of advected variable i (state index vi) at level kk: this block and above are untouched,
-                // the two levels below the block come from the stash written by the previous round
-                auto old = [&](int vi, int i, int kk) -> FT {
+                // OLD values of the neighbouring levels: this block and everything above it are still untouched; the
+                // two levels below the block were overwritten by the previous round and come from its stash.  The
+                // source of level k-1 is fixed per thread and round (j is warp-uniform): a base pointer + variable stride.
+                auto old = [&](int vi, int kk) -> FT {  // generic form, used by the boundary cells only
                     if (kk >= kb) return Ys[sidx(vi, kk)];
-                    return stash[(((r & 1) * 2 + (kb - 1 - kk)) * NADV + i) * C + c];
+                    return stash[(((r & 1) * 2 + (kb - 1 - kk)) * NV + vi) * C + c];
                 };
-                auto rho_at = [&](int kk) -> FT { return rds[kidx(kk)] + old(L::tot, 0, kk); };
+                const FT* up_p = Ys + (k + 1) * C + c;  // + vi * sV
+                const FT* lo_p = (j > 0) ? Ys + (k - 1) * C + c : stash + ((r & 1) * 2) * NV * C + c;
+                const int lo_s = (j > 0) ? sV : C;
+                auto rho_at = [&](int kk) -> FT { return rds[kidx(kk)] + old(L::tot, kk); };
                 // velocities (air, air - vt1, air - vt2) at face f between cells f-1 and f
                 auto face_w = [&](int f, FT rho_a, FT rho_b, FT* wv) {
                     FT wa = rwf(f) / ((rho_a + rho_b) / FT(2));
@@ -378,8 +382,8 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                 const FT rho_k = rds[kidx(k)] + y[L::tot];
                 FT w_lo[3] = {0, 0, 0}, w_up[3] = {0, 0, 0}, w_x[3] = {0, 0, 0};  // w_x: face 2 (k = 0) or nz-2 (k = nz-1)
                 FT rho_u = FT(0), rho_l = FT(0);
-                if (has_up) { rho_u = rho_at(k + 1); face_w(k + 1, rho_u, rho_k, w_up); }
-                if (has_lo) { rho_l = rho_at(k - 1); face_w(k, rho_k, rho_l, w_lo); }
+                if (has_up) { rho_u = rds[kidx(k + 1)] + up_p[L::tot * sV]; face_w(k + 1, rho_u, rho_k, w_up); }
+                if (has_lo) { rho_l = rds[kidx(k - 1)] + lo_p[L::tot * lo_s]; face_w(k, rho_k, rho_l, w_lo); }
                 if (k == 0) face_w(2, rho_at(2), rho_u, w_x);
                 if (k == nz - 1) face_w(nz - 2, rho_l, rho_at(nz - 3), w_x);
                 static_for<0, NADV>([&](auto I) {
@@ -390,20 +394,20 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                     if (k2d && (e.idx == L::Nl || e.idx == L::Na)) return;
                     const int top_bc = (k2d && e.vel != VEL_AIR) ? BC_EXTRAP : e.top;
                     const FT yk = y[e.idx];
-                    const FT yu = has_up ? old(e.idx, i, k + 1) : FT(0);
-                    const FT yl = has_lo ? old(e.idx, i, k - 1) : FT(0);
+                    const FT yu = has_up ? up_p[e.idx * sV] : FT(0);
+                    const FT yl = has_lo ? lo_p[e.idx * lo_s] : FT(0);
                     const FT wu = w_up[e.vel], wl = w_lo[e.vel];
                     const FT Fup = wu * ((yu + yk) * FT(0.5)), Cup = M::abs(wu) * (yu - yk);
                     const FT Flo = wl * ((yk + yl) * FT(0.5)), Clo = M::abs(wl) * (yk - yl);
                     FT D, fc;
                     if (k == 0) {  // bottom cell: SetValue flux, or the stencil of cell 1 (Extrapolate)
-                        const FT y2 = old(e.idx, i, 2);
+                        const FT y2 = Ys[sidx(e.idx, 2)];
                         const FT w2 = w_x[e.vel];
                         if (e.bot == BC_SET) D = (Fup - surf_flux[e.botval]) * inv_dz;
                         else D = (w2 * ((y2 + yu) * FT(0.5)) - Fup) * inv_dz;
                         fc = P.num_fcc_scale * (M::abs(w2) * (y2 - yu) - Cup) * inv_dz;
                     } else if (k == nz - 1) {  // top cell: SetValue(0) flux, or the stencil of cell nz-2
-                        const FT yll = old(e.idx, i, nz - 3);
+                        const FT yll = old(e.idx, nz - 3);
                         const FT wll = w_x[e.vel];
                         if (top_bc == BC_SET) D = (FT(0) - Flo) * inv_dz;
                         else D = (Flo - wll * ((yl + yll) * FT(0.5))) * inv_dz;
@@ -424,7 +428,7 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                     static_for<0, NADV>([&](auto I) {
                         constexpr int i = decltype(I)::value;
                         constexpr int vi = adv_entry<MOIST, PRECIP>(i).idx;
-                        stash[((((r + 1) & 1) * 2 + (NW - 1 - j)) * NADV + i) * C + c] = y[vi];
+                        stash[((((r + 1) & 1) * 2 + (NW - 1 - j)) * NV + vi) * C + c] = y[vi];
                     });
                 }
             }
