@@ -226,21 +226,26 @@ def run_ours(args):
     value = gp_steps_total / (ms_max * 1e-3)
 
     # ---------------- end-to-end through the host API with pinned host buffers (e2e)
+    # The user-facing call for a large ensemble: the columns go through `nchunks` handles (one CUDA stream each), so the
+    # H2D upload, the K steps and the D2H download of different chunks overlap (kid_set_state_async / kid_step /
+    # kid_get_state_async).  Everything — copies included — is inside the timed region.
+    from kid_b200.solve import PipelinedEnsemble
     Yh = torch.empty(case.Y0.shape, dtype=torch.float32).pin_memory()
     Yn = Yh.numpy()
     h.get_state(Yn)  # developed state as the "user's" host input
+    pipe = PipelinedEnsemble(case, nchunks=args.e2e_chunks)
+    pipe.set_steps_per_launch(spl)
     e2e_steps = args.steps
+    Yw = torch.empty(case.Y0.shape, dtype=torch.float32).pin_memory().numpy()
+    Yw[...] = Yn
+    pipe.solve(Yw, t, spl)  # warm the chunk handles (first launch of each, pinned-page first touch)
+    del Yw
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.perf_counter()
-    e0.record(stream)
-    h.set_state(Yn)                     # H2D from pinned host memory
-    h.step(t, e2e_steps)                # the solve between two save times
-    h.get_state(Yn)                     # D2H of the result
-    e1.record(stream)
-    barrier()
+    pipe.solve(Yn, t, e2e_steps)
     wall = time.perf_counter() - w0
-    e2e_ms = max(e0.elapsed_time(e1), wall * 1e3)
+    barrier()
+    e2e_ms = wall * 1e3  # several streams: the host wall clock around the synchronised call is the measure
     te = torch.tensor([e2e_ms], dtype=torch.float64, device=f"cuda:{local}")
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -278,7 +283,7 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": state_bytes / e2e_steps,
                     "d2h_bytes_per_step": state_bytes / e2e_steps,
-                    "call": f"set_state(pinned host) + step({e2e_steps}) + get_state(pinned host), per rank"},
+                    "call": f"PipelinedEnsemble.solve: {args.e2e_chunks} column chunks x [set_state_async(pinned) + step({e2e_steps}) + get_state_async(pinned)], per rank"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
@@ -305,6 +310,7 @@ def main():
     ap.add_argument("--steps-per-launch", type=int, default=10)
     ap.add_argument("--t-start", type=int, default=480, help="model time [s] at which the timed window starts")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample length (0 = skip)")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="column chunks (handles/streams) of the end-to-end pipelined call")
     ap.add_argument("--order", default="sorted", choices=["sorted", "hash"], help="storage order of the ensemble members")
     args = ap.parse_args()
     global ORDER

@@ -141,6 +141,11 @@ int kid_set_column_scalar(kid_handle_t* h, int32_t which, const void* values);
  * (aux N_aer in BoxModel / col_sed; previous-call q_rai,N_liq,N_rai in K2D). */
 int kid_set_state(kid_handle_t* h, const void* Y);
 int kid_get_state(kid_handle_t* h, void* Y);
+/* asynchronous variants for PINNED host buffers: the copy is only enqueued on the handle's stream, so uploads and
+ * downloads of one handle overlap the kernels of other handles (column chunks of a large ensemble pipelined through
+ * several handles).  The buffer must stay valid and untouched until kid_synchronize(h) returns. */
+int kid_set_state_async(kid_handle_t* h, const void* Y_pinned);
+int kid_get_state_async(kid_handle_t* h, void* Y_pinned);
 
 /* replaces: ODE.solve!(integrator) between two save/callback times: advances
  * the device-resident state by nsteps SSPRK33 steps of size dt starting at

@@ -137,7 +137,7 @@ int to_device_layout(kid_handle* h, const void* host, void* dev, int nv) {
     return 0;
 }
 // device [nv][nz][ncp] -> host [nc][nv][nz]
-int to_host_layout(kid_handle* h, const void* dev, void* host, int nv) {
+int to_host_layout(kid_handle* h, const void* dev, void* host, int nv, bool sync = true) {
     const int nc = h->cfg.nc, nz = h->cfg.nz;
     size_t bytes = size_t(nc) * nv * nz * h->fsz;
     if (ensure_staging(h, bytes)) return 1;
@@ -149,7 +149,7 @@ int to_host_layout(kid_handle* h, const void* dev, void* host, int nv) {
     KID_CUDA(cudaGetLastError());
     h->launches++;
     KID_CUDA(cudaMemcpyAsync(host, h->staging, bytes, cudaMemcpyDeviceToHost, h->stream));
-    KID_CUDA(cudaStreamSynchronize(h->stream));
+    if (sync) KID_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
@@ -533,7 +533,15 @@ int kid_set_column_scalar(kid_handle_t* h, int32_t which, const void* values) {
     return fail("invalid column scalar id");
 }
 
-int kid_set_state(kid_handle_t* h, const void* Y) {
+static int set_state_impl(kid_handle_t* h, const void* Y, bool sync);
+int kid_set_state(kid_handle_t* h, const void* Y) { return set_state_impl(h, Y, true); }
+int kid_set_state_async(kid_handle_t* h, const void* Y) { return set_state_impl(h, Y, false); }
+int kid_get_state_async(kid_handle_t* h, void* Y) {
+    if (!h || !Y) return fail("null argument");
+    if (!h->state_set) return fail("kid_set_state has not been called");
+    return to_host_layout(h, h->Y, Y, h->nv, false);
+}
+static int set_state_impl(kid_handle_t* h, const void* Y, bool sync) {
     if (!h || !Y) return fail("null argument");
     if (to_device_layout(h, Y, h->Y, h->nv)) return 1;
     // aux.microph_variables.N_aer is built from the initial profile and never refreshed by
@@ -556,7 +564,7 @@ int kid_set_state(kid_handle_t* h, const void* Y) {
         KID_CUDA(cudaGetLastError());
         h->launches++;
     }
-    KID_CUDA(cudaStreamSynchronize(h->stream));
+    if (sync) KID_CUDA(cudaStreamSynchronize(h->stream));
     h->state_set = true;
     return 0;
 }

@@ -91,6 +91,8 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         "kid_set_column_scalar": (C.c_int, [H, C.c_int32, C.c_void_p]),
         "kid_set_state": (C.c_int, [H, C.c_void_p]),
         "kid_get_state": (C.c_int, [H, C.c_void_p]),
+        "kid_set_state_async": (C.c_int, [H, C.c_void_p]),
+        "kid_get_state_async": (C.c_int, [H, C.c_void_p]),
         "kid_step": (C.c_int, [H, C.c_double, C.c_int32]),
         "kid_set_steps_per_launch": (C.c_int, [H, C.c_int32]),
         "kid_rhs": (C.c_int, [H, C.c_double, C.c_void_p]),
@@ -185,6 +187,15 @@ class Handle:
             out = np.empty((self.cfg.nc, self.nvars, self.cfg.nz), dtype=self.dtype)
         self._check(self.lib.kid_get_state(self._h, _ptr(out)))
         return out
+
+    def set_state_async(self, Y_pinned: np.ndarray):
+        """Enqueue the upload only; Y_pinned must be page-locked, C-contiguous FLOAT_TYPE and stay untouched until synchronize()."""
+        assert Y_pinned.dtype == self.dtype and Y_pinned.flags.c_contiguous
+        self._check(self.lib.kid_set_state_async(self._h, _ptr(Y_pinned)))
+
+    def get_state_async(self, out_pinned: np.ndarray):
+        assert out_pinned.dtype == self.dtype and out_pinned.flags.c_contiguous
+        self._check(self.lib.kid_get_state_async(self._h, _ptr(out_pinned)))
 
     def rhs(self, t: float) -> np.ndarray:
         out = np.empty((self.cfg.nc, self.nvars, self.cfg.nz), dtype=self.dtype)

@@ -135,3 +135,45 @@ def run_K2D_simulation(FT, opts: dict | None = None, backend=Handle):
     case = K2.k2d_case(FT, **o)
     oo = case.meta["opts"]
     return solve(case, (oo["t_ini"], oo["t_end"]), dt=oo["dt"], saveat=oo["dt_output"], backend=backend)
+
+
+class PipelinedEnsemble:
+    """A large ensemble split into column chunks, one handle (and CUDA stream) per chunk: the upload of chunk i+1 and
+    the download of chunk i-1 overlap the stepping of chunk i.  Host arrays must be page-locked (pinned)."""
+
+    def __init__(self, case: M.Case, nchunks: int = 4, backend=Handle):
+        import copy
+        nc = case.cfg.nc
+        edges = np.linspace(0, nc, nchunks + 1).astype(int)
+        edges = (edges // 32) * 32
+        edges[-1] = nc
+        self.ranges = [(int(a), int(b)) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+        self.handles = []
+        pc = np.ndim(case.ρ_dry) == 2
+        for a, b in self.ranges:
+            cfg = copy.copy(case.cfg)
+            cfg.nc = b - a
+            sub = M.Case(cfg=cfg, params=case.params, ρ_dry=case.ρ_dry[a:b] if pc else case.ρ_dry,
+                         T=case.T[a:b] if pc else case.T, Y0=case.Y0[a:b], var_names=case.var_names,
+                         col_scalars={k: np.asarray(v)[a:b] for k, v in case.col_scalars.items()},
+                         column_to_set=None if case.column_to_set is None else case.column_to_set[a:b])
+            self.handles.append(M.make_handle(sub, backend))
+
+    def set_steps_per_launch(self, n: int):
+        for h in self.handles:
+            h.set_steps_per_launch(n)
+
+    def solve(self, Y_pinned: np.ndarray, t0: float, nsteps: int):
+        """In place: Y_pinned[column, variable, level] holds the state at t0 on entry and at t0 + nsteps·dt on return."""
+        for (a, b), h in zip(self.ranges, self.handles):
+            view = Y_pinned[a:b]
+            h.set_state_async(view)
+            h.step(t0, nsteps)
+            h.get_state_async(view)
+        for h in self.handles:
+            h.synchronize()
+        return Y_pinned
+
+    @property
+    def launch_count(self):
+        return sum(h.launch_count for h in self.handles)

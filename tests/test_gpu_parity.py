@@ -447,3 +447,18 @@ def test_handles_with_different_parameters_do_not_interfere():
         b.step(float(s), 50)
     assert np.array_equal(a.get_state(), ref)
     assert not np.array_equal(b.get_state(), ref)
+
+
+def test_pipelined_ensemble_matches_single_handle():
+    """Column chunks on several handles/streams with asynchronous pinned transfers give the same bits as one handle."""
+    import torch
+    from kid_b200.solve import PipelinedEnsemble
+    cs = M.k1d_ensemble_case(np.float32, nc=200, n_profiles=3, n_elem=32, moisture_choice="NonEquilibriumMoisture",
+                             precipitation_choice="Precipitation2M")
+    one = M.make_handle(cs, Handle)
+    one.step(0.0, 120)
+    ref = one.get_state()
+    Yp = torch.from_numpy(cs.Y0.copy()).pin_memory().numpy()
+    pipe = PipelinedEnsemble(cs, nchunks=3)
+    pipe.solve(Yp, 0.0, 120)
+    assert np.array_equal(Yp, ref)
