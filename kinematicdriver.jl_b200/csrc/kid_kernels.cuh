@@ -191,14 +191,18 @@ inline size_t k1d_tile_smem_bytes(int nz, int C, bool per_column_params = false)
     return nfl * sizeof(FT) + size_t(2) * C * sizeof(int);
 }
 
-template <class FT, int MOIST, int PRECIP, bool DIAG, class PRMSRC>
+// FIXNZ > 0: the tile shape is a compile-time constant (nz = FIXNZ levels, C = tile_fixed_columns<FT>() columns,
+// NW = tile_max_threads / C level-warps), so every shared-memory offset folds into an immediate; FIXNZ = 0: any shape.
+template <class FT> constexpr int tile_fixed_columns() { return sizeof(FT) == 4 ? 32 : 16; }
+template <class FT, int MOIST, int PRECIP, bool DIAG, class PRMSRC, int FIXNZ = 0>
 __global__ void __launch_bounds__(tile_max_threads<FT>(), 1)
 k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared) {
     using L = Lay<MOIST, PRECIP>;
     using M = Mth<FT>;
     constexpr int NV = L::NV;
     constexpr int NADV = adv_count<MOIST, PRECIP>();
-    const int nz = A.nz, C = A.C, NW = A.NW, ncp = A.ncp;
+    const int nz = FIXNZ ? FIXNZ : A.nz, C = FIXNZ ? tile_fixed_columns<FT>() : A.C;
+    const int NW = FIXNZ ? tile_max_threads<FT>() / tile_fixed_columns<FT>() : A.NW, ncp = A.ncp;
     const int c = threadIdx.x, j = threadIdx.y;
     const int gc = blockIdx.x * C + c;
     const bool active = gc < A.nc;
