@@ -183,11 +183,10 @@ inline size_t k1d_tile_smem_bytes(int nz, int C, bool per_column_params = false)
     using L = Lay<MOIST, PRECIP>;
     constexpr int NADV = adv_count<MOIST, PRECIP>();
     if (per_column_params) return k1d_tile_smem_bytes<FT, MOIST, PRECIP>(nz, C, false) + size_t(C) * sizeof(DevParams<FT>) + 16;
-    size_t nfl = size_t(L::NV) * nz * C;       // Ys
+    size_t nfl = size_t(L::NV) * (nz + 4) * C;  // Ys: nz levels + 4 stash rows [2 parities][2 levels] per variable
     nfl += size_t(2) * nz * C;                 // rho_dry, T
     if (L::has_pr) nfl += size_t(2) * nz * C;  // vt1, vt2
     if (L::is2m) nfl += size_t(nz) * C;        // activation rate
-    nfl += size_t(4) * L::NV * C;              // round-boundary stash [2 parities][2 levels][NV]
     return nfl * sizeof(FT) + size_t(2) * C * sizeof(int);
 }
 
@@ -213,15 +212,17 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
     const size_t plane = size_t(nz) * ncp;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    FT* Ys = reinterpret_cast<FT*>(smem_raw);  // [NV][nz][C]
-    FT* rds = Ys + size_t(NV) * nz * C;        // [nz][C]
+    // [NV][nz + 4][C]: rows nz..nz+3 of every variable plane are the round-boundary stash (old values of the last two
+    // levels of the previous block, two parities), so a neighbour in the stash and a neighbour in the tile are reached
+    // with the SAME variable stride
+    FT* Ys = reinterpret_cast<FT*>(smem_raw);
+    FT* rds = Ys + size_t(NV) * (nz + 4) * C;  // [nz][C]
     FT* Ts = rds + size_t(nz) * C;
     FT* nxt = Ts + size_t(nz) * C;
     FT* vt1s = nullptr; FT* vt2s = nullptr; FT* acts = nullptr;
     if constexpr (L::has_pr) { vt1s = nxt; vt2s = nxt + size_t(nz) * C; nxt += size_t(2) * nz * C; }
     if constexpr (L::is2m) { acts = nxt; nxt += size_t(nz) * C; }
-    FT* stash = nxt;                           // [2][2][NV][C]: old values of the last two levels of a block
-    int* cb = reinterpret_cast<int*>(stash + size_t(4) * NV * C);  // [2][C]
+    int* cb = reinterpret_cast<int*>(nxt);     // [2][C]
     // parameters: the shared set (kernel argument, constant bank), or this column's own set staged in shared memory
     // as [column][word] with an odd word count (conflict-free when the 32 lanes read the same field)
     const DevParams<FT>* Pp;
@@ -241,7 +242,7 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
     }
     const DevParams<FT>& P = *Pp;
     // shared-memory indices stay 32-bit: (variable, level) plane stride sV, level stride C
-    const int sV = nz * C;
+    const int sV = (nz + 4) * C;
     auto sidx = [&](int v, int k) { return v * sV + k * C + c; };
     auto kidx = [&](int k) { return k * C + c; };
 
@@ -354,42 +355,42 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
             const int k = r * NW + j;
             const int kb = r * NW;  // first level of this block: lower levels were overwritten in earlier rounds
             const bool valid = active && k < nz;
-            FT y[NV], adv[NADV];
+            FT adv[NADV];
 #pragma unroll
             for (int i = 0; i < NADV; ++i) adv[i] = FT(0);
-            if (valid) {
-#pragma unroll
-                for (int v = 0; v < NV; ++v) y[v] = Ys[sidx(v, k)];
-            }
             if (valid && with_adv) {
-                // OLD values of the neighbouring levels: this block and everything above it are still untouched; the
-                // two levels below the block were overwritten by the previous round and come from its stash.  The
-                // source of level k-1 is fixed per thread and round (j is warp-uniform): a base pointer + variable stride.
-                auto old = [&](int vi, int kk) -> FT {  // generic form, used by the boundary cells only
-                    if (kk >= kb) return Ys[sidx(vi, kk)];
-                    return stash[(((r & 1) * 2 + (kb - 1 - kk)) * NV + vi) * C + c];
-                };
-                const FT* up_p = Ys + (k + 1) * C + c;  // + vi * sV
-                const FT* lo_p = (j > 0) ? Ys + (k - 1) * C + c : stash + ((r & 1) * 2) * NV * C + c;
-                const int lo_s = (j > 0) ? sV : C;
-                auto rho_at = [&](int kk) -> FT { return rds[kidx(kk)] + old(L::tot, kk); };
-                // velocities (air, air - vt1, air - vt2) at face f between cells f-1 and f
-                auto face_w = [&](int f, FT rho_a, FT rho_b, FT* wv) {
-                    FT wa = rwf(f) / ((rho_a + rho_b) / FT(2));
-                    wv[0] = wv[1] = wv[2] = wa;
-                    if constexpr (L::has_pr) {
-                        wv[1] = wa - (vt1s[kidx(f)] + vt1s[kidx(f - 1)]) / FT(2);
-                        wv[2] = wa - (vt2s[kidx(f)] + vt2s[kidx(f - 1)]) / FT(2);
-                    }
-                };
-                const bool has_lo = k > 0, has_up = k + 1 < nz;
-                const FT rho_k = rds[kidx(k)] + y[L::tot];
-                FT w_lo[3] = {0, 0, 0}, w_up[3] = {0, 0, 0}, w_x[3] = {0, 0, 0};  // w_x: face 2 (k = 0) or nz-2 (k = nz-1)
-                FT rho_u = FT(0), rho_l = FT(0);
-                if (has_up) { rho_u = rds[kidx(k + 1)] + up_p[L::tot * sV]; face_w(k + 1, rho_u, rho_k, w_up); }
-                if (has_lo) { rho_l = rds[kidx(k - 1)] + lo_p[L::tot * lo_s]; face_w(k, rho_k, rho_l, w_lo); }
-                if (k == 0) face_w(2, rho_at(2), rho_u, w_x);
-                if (k == nz - 1) face_w(nz - 2, rho_l, rho_at(nz - 3), w_x);
+                // The boundary cells take the stencil of their inner neighbour (Extrapolate: the tendency of cell 0 is
+                // that of cell 1, of cell nz-1 that of cell nz-2; the flux correction always extrapolates), so every
+                // thread evaluates ONE stencil, centred on kc; a SetValue boundary only swaps the two face fluxes of D.
+                const bool is_bot = (k == 0), is_top = (k == nz - 1);
+                const int kc = is_bot ? 1 : (is_top ? nz - 2 : k);
+                // OLD values: this block and everything above it are still untouched; the two levels below the block
+                // were overwritten by the previous round and sit in the stash rows nz + 2·(r & 1) + {0: kb-1, 1: kb-2}
+                auto row = [&](int kk) { return (kk >= kb) ? kk : nz + 2 * (r & 1) + (kb - 1 - kk); };
+                const FT* c_p = Ys + row(kc) * C + c;      // + variable · sV
+                const FT* l_p = Ys + row(kc - 1) * C + c;
+                const FT* u_p = Ys + (kc + 1) * C + c;
+                // face velocities (air, air - vt1, air - vt2) of faces kc (lower) and kc+1 (upper), pre-multiplied:
+                // wh = w / (2 dz) for the centred flux, aw = fcc_scale |w| / dz for the first-order correction
+                FT wh_lo[3], wh_up[3], aw_lo[3], aw_up[3];
+                {
+                    const FT rho_c = rds[kidx(kc)] + c_p[L::tot * sV];
+                    const FT rho_l = rds[kidx(kc - 1)] + l_p[L::tot * sV];
+                    const FT rho_u = rds[kidx(kc + 1)] + u_p[L::tot * sV];
+                    const FT half_inv_dz = FT(0.5) * inv_dz, fs = P.num_fcc_scale * inv_dz;
+                    auto face_w = [&](int f, FT rho_a, FT rho_b, FT* wh, FT* aw) {
+                        const FT wa = rwf(f) / ((rho_a + rho_b) * FT(0.5));
+                        FT wv[3] = {wa, wa, wa};
+                        if constexpr (L::has_pr) {
+                            wv[1] = wa - (vt1s[kidx(f)] + vt1s[kidx(f - 1)]) * FT(0.5);
+                            wv[2] = wa - (vt2s[kidx(f)] + vt2s[kidx(f - 1)]) * FT(0.5);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) { wh[q] = wv[q] * half_inv_dz; aw[q] = M::abs(wv[q]) * fs; }
+                    };
+                    face_w(kc + 1, rho_u, rho_c, wh_up, aw_up);
+                    face_w(kc, rho_c, rho_l, wh_lo, aw_lo);
+                }
                 static_for<0, NADV>([&](auto I) {
                     constexpr int i = decltype(I)::value;
                     constexpr AdvVar e = adv_entry<MOIST, PRECIP>(i);
@@ -397,31 +398,16 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                     // divergence extrapolates at BOTH ends, q_tot always gets the flux correction
                     if (k2d && (e.idx == L::Nl || e.idx == L::Na)) return;
                     const int top_bc = (k2d && e.vel != VEL_AIR) ? BC_EXTRAP : e.top;
-                    const FT yk = y[e.idx];
-                    const FT yu = has_up ? up_p[e.idx * sV] : FT(0);
-                    const FT yl = has_lo ? lo_p[e.idx * lo_s] : FT(0);
-                    const FT wu = w_up[e.vel], wl = w_lo[e.vel];
-                    const FT Fup = wu * ((yu + yk) * FT(0.5)), Cup = M::abs(wu) * (yu - yk);
-                    const FT Flo = wl * ((yk + yl) * FT(0.5)), Clo = M::abs(wl) * (yk - yl);
-                    FT D, fc;
-                    if (k == 0) {  // bottom cell: SetValue flux, or the stencil of cell 1 (Extrapolate)
-                        const FT y2 = Ys[sidx(e.idx, 2)];
-                        const FT w2 = w_x[e.vel];
-                        if (e.bot == BC_SET) D = (Fup - surf_flux[e.botval]) * inv_dz;
-                        else D = (w2 * ((y2 + yu) * FT(0.5)) - Fup) * inv_dz;
-                        fc = P.num_fcc_scale * (M::abs(w2) * (y2 - yu) - Cup) * inv_dz;
-                    } else if (k == nz - 1) {  // top cell: SetValue(0) flux, or the stencil of cell nz-2
-                        const FT yll = old(e.idx, nz - 3);
-                        const FT wll = w_x[e.vel];
-                        if (top_bc == BC_SET) D = (FT(0) - Flo) * inv_dz;
-                        else D = (Flo - wll * ((yl + yll) * FT(0.5))) * inv_dz;
-                        fc = P.num_fcc_scale * (Clo - M::abs(wll) * (yl - yll)) * inv_dz;
-                    } else {
-                        D = (Fup - Flo) * inv_dz;
-                        fc = P.num_fcc_scale * (Cup - Clo) * inv_dz;
+                    const FT yk = c_p[e.idx * sV], yu = u_p[e.idx * sV], yl = l_p[e.idx * sV];
+                    const FT Fup = wh_up[e.vel] * (yu + yk), Flo = wh_lo[e.vel] * (yk + yl);  // face fluxes / dz
+                    const FT fc = aw_up[e.vel] * (yu - yk) - aw_lo[e.vel] * (yk - yl);
+                    FT Aup = Fup, Alo = Flo;
+                    if (e.bot == BC_SET) {  // bottom cell: (flux at face 1 - prescribed surface flux) / dz
+                        if (is_bot) { Aup = Flo; Alo = surf_flux[e.botval] * inv_dz; }
                     }
+                    if (is_top && top_bc == BC_SET) { Aup = FT(0); Alo = Fup; }  // top cell: (0 - flux at face nz-1) / dz
                     const bool fcc_on = (e.fcc == FCC_ALWAYS) || A.sw.qtot_flux_correction || k2d;
-                    FT a_i = -D;
+                    FT a_i = Alo - Aup;
                     if (fcc_on) a_i += fc;
                     adv[i] = a_i;
                     if (e.to_tot && k2d)  // S is DSS'd on its own before it is added to ρq_tot and its own variable
@@ -432,14 +418,16 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                     static_for<0, NADV>([&](auto I) {
                         constexpr int i = decltype(I)::value;
                         constexpr int vi = adv_entry<MOIST, PRECIP>(i).idx;
-                        stash[((((r + 1) & 1) * 2 + (NW - 1 - j)) * NV + vi) * C + c] = y[vi];
+                        Ys[vi * sV + (nz + 2 * ((r + 1) & 1) + (NW - 1 - j)) * C + c] = Ys[sidx(vi, k)];
                     });
                 }
             }
             __syncthreads();  // every thread of the tile has read its old neighbours
 
             if (valid) {
-                FT tend[NV];
+                FT y[NV], tend[NV];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) y[v] = Ys[sidx(v, k)];
                 Point<FT> a;
                 const size_t ppi = A.prof_per_column ? size_t(k) * ncp + gc : size_t(k);
                 thermo_point<FT, MOIST, PRECIP>(P, y, rds[kidx(k)], Ts[kidx(k)], A.ps_liq[ppi], A.ps_mix[ppi], a);
