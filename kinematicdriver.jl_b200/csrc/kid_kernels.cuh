@@ -275,6 +275,8 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
         const int par = it & 1;
         const FT tn = FT(A.t0 + double(step) * double(dt));
         const FT ts = stage_time(stage, tn, dt);
+        const FT rk_b = stage == 0 ? FT(1) : (stage == 1 ? FT(0.25) : FT(2) / FT(3));
+        const FT rk_a = FT(1) - rk_b, rk_c = rk_b * dt;
         // K1D: ρw(t) uniform over the column (K1DModel/tendency.jl:240-248).  K2D: ρw(x, z_face, t) from the
         // stream function (K2DModel/tendency.jl:4-9), evaluated in double and rounded like the reference's map
         FT rw = (k1d && !k2d) ? rho_w_of_t(ts, w1c, FT(P.kid_t1)) : FT(0);
@@ -401,18 +403,34 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                     const FT yk = c_p[e.idx * sV], yu = u_p[e.idx * sV], yl = l_p[e.idx * sV];
                     const FT Fup = wh_up[e.vel] * (yu + yk), Flo = wh_lo[e.vel] * (yk + yl);  // face fluxes / dz
                     const FT fc = aw_up[e.vel] * (yu - yk) - aw_lo[e.vel] * (yk - yl);
-                    FT Aup = Fup, Alo = Flo;
-                    if (e.bot == BC_SET) {  // bottom cell: (flux at face 1 - prescribed surface flux) / dz
-                        if (is_bot) { Aup = Flo; Alo = surf_flux[e.botval] * inv_dz; }
-                    }
-                    if (is_top && top_bc == BC_SET) { Aup = FT(0); Alo = Fup; }  // top cell: (0 - flux at face nz-1) / dz
                     const bool fcc_on = (e.fcc == FCC_ALWAYS) || A.sw.qtot_flux_correction || k2d;
-                    FT a_i = Alo - Aup;
+                    FT a_i = Flo - Fup;
                     if (fcc_on) a_i += fc;
                     adv[i] = a_i;
-                    if (e.to_tot && k2d)  // S is DSS'd on its own before it is added to ρq_tot and its own variable
-                        A.outS[size_t(e.vel == VEL_VT1 ? 0 : 1) * plane + size_t(k) * ncp + gc] = a_i;
                 });
+                // SetValue boundaries (two warps of the tile, warp-uniform branch): one face flux of D is prescribed
+                if (is_bot || is_top) {
+                    static_for<0, NADV>([&](auto I) {
+                        constexpr int i = decltype(I)::value;
+                        constexpr AdvVar e = adv_entry<MOIST, PRECIP>(i);
+                        if (k2d && (e.idx == L::Nl || e.idx == L::Na)) return;
+                        const int top_bc = (k2d && e.vel != VEL_AIR) ? BC_EXTRAP : e.top;
+                        const bool set_bot = is_bot && e.bot == BC_SET, set_top = is_top && top_bc == BC_SET;
+                        if (!set_bot && !set_top) return;
+                        const FT yk = c_p[e.idx * sV], yu = u_p[e.idx * sV], yl = l_p[e.idx * sV];
+                        const FT Fup = wh_up[e.vel] * (yu + yk), Flo = wh_lo[e.vel] * (yk + yl);
+                        // bottom cell: (flux at face 1 - surface flux) / dz; top cell: (0 - flux at face nz-1) / dz
+                        const FT D = set_bot ? Flo - surf_flux[e.botval] * inv_dz : FT(0) - Fup;
+                        adv[i] += (Fup - Flo) - D;  // replace the divergence, keep the flux correction
+                    });
+                }
+                if (k2d) {  // S is DSS'd on its own before it is added to ρq_tot and its own variable
+                    static_for<0, NADV>([&](auto I) {
+                        constexpr int i = decltype(I)::value;
+                        constexpr AdvVar e = adv_entry<MOIST, PRECIP>(i);
+                        if (e.to_tot) A.outS[size_t(e.vel == VEL_VT1 ? 0 : 1) * plane + size_t(k) * ncp + gc] = adv[i];
+                    });
+                }
                 // the next round needs the OLD values of this block's last two levels
                 if (kb + NW < nz && j >= NW - 2) {
                     static_for<0, NADV>([&](auto I) {
@@ -467,13 +485,15 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                             P, A.field, a, src, v1, v2, act_Nl, A.sw.open_system_activation != 0);
                     }
                 } else {
+                    // SSPRK33 as a convex combination  u_new = a·u^n + b·(y + dt·f(y)),  (a, b) = (0, 1), (3/4, 1/4),
+                    // (1/3, 2/3): OrdinaryDiffEq's (3u + y + dt k)/4 and (u + 2y + 2dt k)/3 with the division folded in
+                    FT* gY = A.Y + size_t(k) * ncp + gc;
 #pragma unroll
                     for (int v = 0; v < NV; ++v) {
-                        const size_t gi = v * plane + size_t(k) * ncp + gc;
-                        FT u = (stage == 0) ? y[v] : A.Y[gi];
-                        FT yn = ssprk33_combine(stage, u, y[v], dt, tend[v]);
+                        const FT u = (stage == 0) ? y[v] : gY[v * plane];
+                        const FT yn = rk_a * u + (rk_b * y[v] + rk_c * tend[v]);
                         Ys[sidx(v, k)] = yn;
-                        if (stage == 2) A.Y[gi] = yn;
+                        if (stage == 2) gY[v * plane] = yn;
                     }
                 }
             }
