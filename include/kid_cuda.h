@@ -78,6 +78,17 @@ enum kid_aux_field {
     KID_NAUX
 };
 
+/* observables of CO.get_variable_data_from_ODE (src/Common/helper_functions.jl:98-191), in the order of its
+ * if-chain: "qt","ql","qr","qv","qlr","rt","rl","rr","rv","rlr","Nl","Nr","Na","rho",
+ * "rain averaged terminal velocity","rainrate".  "Z_top" needs CloudMicrophysics' radar reflectivity: not available. */
+enum kid_obs_var {
+    KID_OBS_QT = 0, KID_OBS_QL, KID_OBS_QR, KID_OBS_QV, KID_OBS_QLR,
+    KID_OBS_RT, KID_OBS_RL, KID_OBS_RR, KID_OBS_RV, KID_OBS_RLR,
+    KID_OBS_NL, KID_OBS_NR, KID_OBS_NA, KID_OBS_RHO, KID_OBS_RAIN_VT, KID_OBS_RAINRATE,
+    KID_NOBS
+};
+#define KID_MAX_OBS_VARS 16
+
 typedef struct kid_config {
     int32_t abi_version;     /* = KID_ABI_VERSION */
     int32_t params_version;  /* = KID_PARAMS_VERSION */
@@ -164,6 +175,22 @@ int kid_rhs(kid_handle_t* h, double t, void* dY_out);
 int kid_get_aux(kid_handle_t* h, double t, int32_t field, void* out);
 /* replaces: maximum(aux.microph_variables.q_liq) (netcdf_io.jl:166) */
 int kid_reduce_max(kid_handle_t* h, double t, int32_t field, double* out);
+
+/* replaces: ODEsolution2Gvector (calibration/KiDUtils.jl:329-376) fed by get_variable_data_from_ODE: the calibration
+ * G vector is accumulated on the device, one row per column (ensemble member x case), so only the filtered
+ * observables ever cross PCIe.
+ *   kid_obs_configure: nvars observables (enum kid_obs_var), variable j averaged over blocks of
+ *       nz_per_filtered_cell[j] levels (must divide nz; 1 = unfiltered) and over nt_per_filtered_cell snapshots per
+ *       time cell; nt_filtered time cells.  Row length n_out = nt_filtered * sum_j nz / nz_per_filtered_cell[j],
+ *       ordered [time cell][variable][filtered level] like the reference's outputs vector.  Zeroes the accumulator.
+ *   kid_obs_accumulate: add the observables of the CURRENT device state to time cell `time_cell`
+ *       (call it at every saveat time of make_filter_props: nt_per_filtered_cell times per cell).
+ *   kid_obs_get: download the accumulator, nc rows of n_out Float64 values (the reference's outputs are Float64).
+ * Without filtering (apply = false): nz_per = 1, nt_per = 1 and one time cell per saved time. */
+int kid_obs_configure(kid_handle_t* h, int32_t nvars, const int32_t* var_ids, const int32_t* nz_per_filtered_cell,
+                      int32_t nt_filtered, int32_t nt_per_filtered_cell, int64_t* n_out);
+int kid_obs_accumulate(kid_handle_t* h, int32_t time_cell);
+int kid_obs_get(kid_handle_t* h, double* G);
 
 /* K2D domain decomposition: the caller (one process per GPU) exchanges the
  * packed edge-node tendencies of its first/last element with its periodic

@@ -73,6 +73,12 @@ struct kid_handle {
     int Nq = 0, nfields = 0;
     K2DField fields[KID_MAX_DSS];
     double gll_x[KID_MAX_NQ], gll_w[KID_MAX_NQ], gll_D[KID_MAX_NQ * KID_MAX_NQ];
+    // calibration observables (kid_obs_*)
+    double* obsG = nullptr;
+    unsigned long long* red = nullptr;
+    int obs_nvars = 0, obs_nt_filtered = 0, obs_nt_per = 1;
+    int64_t obs_n_out = 0;
+    int obs_var[KID_MAX_OBS], obs_per[KID_MAX_OBS], obs_off[KID_MAX_OBS + 1];
     int i_tot = 0, i_liq = -1, i_ice = -1, i_rai = -1, i_sno = -1, i_Nl = -1, i_Nr = -1, i_Na = -1;
 };
 
@@ -353,6 +359,28 @@ int k2d_setup(kid_handle* h) {
     return 0;
 }
 
+template <class FT>
+int obs_launch(kid_handle_t* h, int time_cell) {
+    ObsArgs<FT> a{};
+    a.Y = (const FT*)h->Y;
+    a.rho_dry = (const FT*)h->rho_dry;
+    a.G = h->obsG;
+    a.prm_sets = (const DevParams<FT>*)h->prm_sets;
+    a.col_to_set = (const int*)h->col_to_set;
+    a.nz = h->cfg.nz; a.nc = h->cfg.nc; a.ncp = h->ncp; a.prof_per_column = h->prof_per_column;
+    a.nvars = h->obs_nvars; a.n_out = int(h->obs_n_out); a.nt_filtered = h->obs_nt_filtered; a.time_cell = time_cell;
+    for (int j = 0; j < h->obs_nvars; ++j) { a.var_id[j] = h->obs_var[j]; a.nz_per_cell[j] = h->obs_per[j]; a.out_offset[j] = h->obs_off[j]; }
+    a.out_offset[h->obs_nvars] = h->obs_off[h->obs_nvars];
+    a.weight = 1.0 / double(h->obs_nt_per);
+    a.sw = h->sw;
+    cudaError_t e;
+    if constexpr (sizeof(FT) == 8) e = h->lt->obs_d(h->cfg.moisture, a, h->prm_d, h->stream);
+    else e = h->lt->obs_f(h->cfg.moisture, a, h->prm_f, h->stream);
+    if (e != cudaSuccess) return fail(std::string("obs_accumulate_kernel: ") + cudaGetErrorString(e));
+    h->launches++;
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -429,6 +457,7 @@ int kid_create(const kid_config_t* cfg, kid_handle_t** out) {
 }
 
 void kid_destroy(kid_handle_t* h) {
+    if (h) { if (h->obsG) cudaFree(h->obsG); if (h->red) cudaFree(h->red); }
     if (!h) return;
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void* p : {h->ps_liq, h->ps_mix, h->prm_sets, h->col_to_set, h->Y, h->rho_dry, h->T, h->w1, h->q_surf, h->Nd, h->aux_Naer, h->out, h->staging, h->U, h->S,
@@ -636,13 +665,78 @@ int kid_get_aux(kid_handle_t* h, double t, int32_t field, void* out) {
 int kid_reduce_max(kid_handle_t* h, double t, int32_t field, double* out) {
     if (check_ready(h)) return 1;
     if (!out) return fail("null argument");
-    size_t n = size_t(h->cfg.nc) * h->cfg.nz;
-    std::vector<char> buf(n * h->fsz);
-    if (kid_get_aux(h, t, field, buf.data())) return 1;
-    double m = -1e300;
-    if (h->f64) for (size_t i = 0; i < n; ++i) m = std::max(m, ((double*)buf.data())[i]);
-    else for (size_t i = 0; i < n; ++i) m = std::max(m, double(((float*)buf.data())[i]));
-    *out = m;
+    if (field < 0 || field >= KID_NAUX) return fail("invalid aux field id");
+    if (ensure_out(h, state_elems(h) * h->fsz)) return 1;
+    if (launch_tile(h, t, 1, 2, field)) return 1;  // the field, [nz][ncp] on the device
+    if (!h->red) KID_CUDA(cudaMalloc(&h->red, sizeof(unsigned long long)));
+    KID_CUDA(cudaMemsetAsync(h->red, 0, sizeof(unsigned long long), h->stream));  // 0 orders below every double
+    const int nz = h->cfg.nz, nc = h->cfg.nc;
+    const int blocks = int(std::min<size_t>(1184, (size_t(nz) * h->ncp + 255) / 256));
+    if (h->f64) field_max_kernel<double><<<blocks, 256, 0, h->stream>>>((const double*)h->out, nz, nc, h->ncp, h->red);
+    else field_max_kernel<float><<<blocks, 256, 0, h->stream>>>((const float*)h->out, nz, nc, h->ncp, h->red);
+    KID_CUDA(cudaGetLastError());
+    h->launches++;
+    unsigned long long bits = 0;
+    KID_CUDA(cudaMemcpyAsync(&bits, h->red, sizeof(bits), cudaMemcpyDeviceToHost, h->stream));
+    KID_CUDA(cudaStreamSynchronize(h->stream));
+    *out = from_ordered_bits(bits);
+    return 0;
+}
+
+int kid_obs_configure(kid_handle_t* h, int32_t nvars, const int32_t* var_ids, const int32_t* nz_per_filtered_cell,
+                      int32_t nt_filtered, int32_t nt_per_filtered_cell, int64_t* n_out) {
+    if (!h || !var_ids) return fail("null argument");
+    if (h->cfg.model == KID_MODEL_K2D) return fail("kid_obs_*: K1D / Box handles only");
+    if (nvars < 1 || nvars > KID_MAX_OBS) return fail("kid_obs_configure: 1..16 observables");
+    if (nt_filtered < 1 || nt_per_filtered_cell < 1) return fail("kid_obs_configure: nt_filtered, nt_per_filtered_cell >= 1");
+    const int nz = h->cfg.nz;
+    const bool neq = h->cfg.moisture == KID_MOIST_NONEQ;
+    const bool has_pr = h->cfg.precip == KID_PRECIP_1M || h->cfg.precip == KID_PRECIP_2M;
+    const bool is2m = h->cfg.precip == KID_PRECIP_2M;
+    int off = 0;
+    for (int j = 0; j < nvars; ++j) {
+        const int v = var_ids[j], per = nz_per_filtered_cell ? nz_per_filtered_cell[j] : 1;
+        if (v < 0 || v >= KID_NOBS) return fail("kid_obs_configure: unknown observable id");
+        if (per < 1 || nz % per != 0) return fail("kid_obs_configure: nz_per_filtered_cell must divide nz");
+        // the reference reads u.ρq_liq / u.ρq_rai / u.N_*: a style without that field is an error there too
+        const bool needs_liq = v == KID_OBS_QL || v == KID_OBS_QV || v == KID_OBS_QLR || v == KID_OBS_RL || v == KID_OBS_RV || v == KID_OBS_RLR;
+        const bool needs_rai = v == KID_OBS_QR || v == KID_OBS_QLR || v == KID_OBS_RR || v == KID_OBS_RLR || v == KID_OBS_RAIN_VT || v == KID_OBS_RAINRATE;
+        const bool needs_N = v == KID_OBS_NL || v == KID_OBS_NR || v == KID_OBS_NA;
+        if (needs_liq && !neq) return fail("observable needs ρq_liq: NonEquilibriumMoisture only");
+        if (needs_rai && !has_pr) return fail("observable needs ρq_rai: Precipitation1M / Precipitation2M only");
+        if (needs_N && !is2m) return fail("observable needs N_liq/N_rai/N_aer: Precipitation2M only");
+        h->obs_var[j] = v;
+        h->obs_per[j] = per;
+        h->obs_off[j] = off;
+        off += nz / per;
+    }
+    h->obs_off[nvars] = off;
+    h->obs_nvars = nvars;
+    h->obs_nt_filtered = nt_filtered;
+    h->obs_nt_per = nt_per_filtered_cell;
+    h->obs_n_out = int64_t(off);
+    if (h->obsG) cudaFree(h->obsG);
+    h->obsG = nullptr;
+    const size_t bytes = size_t(h->cfg.nc) * nt_filtered * off * sizeof(double);
+    KID_CUDA(cudaMalloc(&h->obsG, bytes));
+    KID_CUDA(cudaMemsetAsync(h->obsG, 0, bytes, h->stream));
+    if (n_out) *n_out = int64_t(nt_filtered) * off;
+    return 0;
+}
+
+int kid_obs_accumulate(kid_handle_t* h, int32_t time_cell) {
+    if (check_ready(h)) return 1;
+    if (!h->obsG) return fail("kid_obs_accumulate: call kid_obs_configure first");
+    if (time_cell < 0 || time_cell >= h->obs_nt_filtered) return fail("kid_obs_accumulate: time cell out of range");
+    return h->f64 ? obs_launch<double>(h, time_cell) : obs_launch<float>(h, time_cell);
+}
+
+int kid_obs_get(kid_handle_t* h, double* G) {
+    if (!h || !G) return fail("null argument");
+    if (!h->obsG) return fail("kid_obs_get: call kid_obs_configure first");
+    const size_t bytes = size_t(h->cfg.nc) * h->obs_nt_filtered * h->obs_n_out * sizeof(double);
+    KID_CUDA(cudaMemcpyAsync(G, h->obsG, bytes, cudaMemcpyDeviceToHost, h->stream));
+    KID_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

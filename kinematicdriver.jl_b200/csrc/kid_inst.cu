@@ -67,13 +67,20 @@ cudaError_t consts(const KArgs<FT>& a, const DevParams<FT>& P, FT* ps_liq, FT* p
     return cudaGetLastError();
 }
 template <class FT>
+cudaError_t obs(int moisture, const ObsArgs<FT>& a, const DevParams<FT>& P, cudaStream_t s) {
+    dim3 block(128), grid((a.nc + 127) / 128, a.n_out);
+    if (moisture == KID_MOIST_EQ) obs_accumulate_kernel<FT, KID_MOIST_EQ, KID_PRECIP><<<grid, block, 0, s>>>(a, P);
+    else obs_accumulate_kernel<FT, KID_MOIST_NONEQ, KID_PRECIP><<<grid, block, 0, s>>>(a, P);
+    return cudaGetLastError();
+}
+template <class FT>
 size_t smem_bytes(int moisture, int nz, int C, bool pcp) {
     return moisture == KID_MOIST_EQ ? k1d_tile_smem_bytes<FT, KID_MOIST_EQ, KID_PRECIP>(nz, C, pcp)
                                     : k1d_tile_smem_bytes<FT, KID_MOIST_NONEQ, KID_PRECIP>(nz, C, pcp);
 }
 
 const LaunchTable table = {k1d<float>, k1d<double>, box<float>, box<double>,
-                           consts<float>, consts<double>, smem_bytes<float>, smem_bytes<double>};
+                           consts<float>, consts<double>, obs<float>, obs<double>, smem_bytes<float>, smem_bytes<double>};
 }  // namespace
 
 #define KID_CAT2(a, b) a##b

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "kid_diag.cuh"
 #include "kid_kernels.cuh"
 
 namespace kid {
@@ -17,6 +18,8 @@ struct LaunchTable {
     cudaError_t (*box_d)(int moisture, const KArgs<double>&, const DevParams<double>&, cudaStream_t);
     cudaError_t (*consts_f)(const KArgs<float>&, const DevParams<float>&, float* ps_liq, float* ps_mix, cudaStream_t);
     cudaError_t (*consts_d)(const KArgs<double>&, const DevParams<double>&, double* ps_liq, double* ps_mix, cudaStream_t);
+    cudaError_t (*obs_f)(int moisture, const ObsArgs<float>&, const DevParams<float>&, cudaStream_t);
+    cudaError_t (*obs_d)(int moisture, const ObsArgs<double>&, const DevParams<double>&, cudaStream_t);
     size_t (*k1d_smem_f)(int moisture, int nz, int C, bool per_column_params);
     size_t (*k1d_smem_d)(int moisture, int nz, int C, bool per_column_params);
 };

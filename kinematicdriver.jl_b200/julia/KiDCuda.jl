@@ -183,4 +183,31 @@ function solve(moisture, precip, Y, aux, tspan; model::Symbol, dt, saveat, nz, z
     end
 end
 
+# ------------------------------------------------------------------ calibration observables on the device
+const OBS_NAMES = ["qt", "ql", "qr", "qv", "qlr", "rt", "rl", "rr", "rv", "rlr", "Nl", "Nr", "Na", "rho",
+                   "rain averaged terminal velocity", "rainrate"]   # enum kid_obs_var
+
+"""
+    obs_configure(h, variables, filter) / obs_accumulate(h, time_cell) / obs_get(h, nc)
+
+Device replacement of `ODEsolution2Gvector(ODEsol, aux, precip, variables[, filter])` (calibration/KiDUtils.jl:329-376):
+call `obs_accumulate` at every `filter["saveat_t"]` time instead of saving the state; `obs_get` returns the G vectors,
+one column per simulated column.
+"""
+function obs_configure(h::Ptr{Cvoid}, variables::Vector{String}, filter::Dict)
+    ids = Int32[findfirst(==(v), OBS_NAMES) - 1 for v in variables]
+    per = Int32.(filter["nz_per_filtered_cell"])
+    n_out = Ref{Int64}(0)
+    check(ccall((:kid_obs_configure, libkid), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Int32}, Int32, Int32, Ref{Int64}),
+                h, length(ids), ids, per, filter["nt_filtered"], filter["nt_per_filtered_cell"], n_out))
+    return n_out[]
+end
+obs_accumulate(h::Ptr{Cvoid}, time_cell::Integer) =
+    check(ccall((:kid_obs_accumulate, libkid), Cint, (Ptr{Cvoid}, Int32), h, time_cell))
+function obs_get(h::Ptr{Cvoid}, n_out::Integer, nc::Integer)
+    G = zeros(Float64, n_out, nc)
+    check(ccall((:kid_obs_get, libkid), Cint, (Ptr{Cvoid}, Ptr{Float64}), h, G))
+    return G
+end
+
 end # module

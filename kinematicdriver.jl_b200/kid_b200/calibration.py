@@ -1,0 +1,145 @@
+"""Calibration forward map on the device: `run_dyn_model` / `run_ensembles` of the reference, batched.
+
+Mirrors (reference):
+  make_filter_props                         calibration/HelperFuncs.jl:21-47
+  ODEsolution2Gvector (both methods)        calibration/KiDUtils.jl:329-376
+  run_KiD / run_KiD_multiple_cases          calibration/KiDUtils.jl:45-151
+  run_ensembles                             calibration/OptimizationUtils.jl:197-211
+
+The reference maps one parameter vector to one G vector per call and threads over ensemble members on the CPU; here
+every (ensemble member, case) pair is one COLUMN of a single device ensemble — members differ by their parameter set,
+cases by (w1, p0, Nd) — and the G vectors are accumulated on the device (kid_obs_*), so one batch of launches serves a
+whole EKI iteration and only the filtered observables are downloaded.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import initial_condition as IC
+from . import model as M
+from . import parameters as PR
+from .lib import COL_PRESCRIBED_ND, COL_Q_SURF, COL_W1, Handle
+
+
+def make_filter_props(n_z, t_calib, apply: bool = False, nz_per_filtered_cell=None, nt_per_filtered_cell: int = 1) -> dict:
+    """calibration/HelperFuncs.jl:21-47."""
+    n_z = np.asarray(n_z, dtype=int)
+    per = np.ones_like(n_z) if nz_per_filtered_cell is None else np.asarray(nz_per_filtered_cell, dtype=int)
+    if np.any(n_z % per != 0):
+        raise AssertionError("n_z must be divisible by nz_per_filtered_cell")
+    t_calib = np.asarray(t_calib, dtype=float)
+    saveat = []
+    for i in range(len(t_calib) - 1):
+        dt = (t_calib[i + 1] - t_calib[i]) / nt_per_filtered_cell
+        saveat.extend(np.linspace(t_calib[i] + dt / 2, t_calib[i + 1] - dt / 2, nt_per_filtered_cell))
+    return {"apply": apply, "nz_per_filtered_cell": per, "nt_per_filtered_cell": int(nt_per_filtered_cell),
+            "nz_unfiltered": n_z, "nz_filtered": n_z // per, "nt_filtered": len(t_calib) - 1,
+            "saveat_t": np.asarray(saveat)}
+
+
+def _step_index(t: float, t_ini: float, dt: float) -> int:
+    n = (t - t_ini) / dt
+    if abs(n - round(n)) > 1e-9 * max(1.0, abs(n)):
+        raise NotImplementedError(
+            f"save time {t} is not a multiple of dt={dt} after t_ini={t_ini}: the reference would interpolate the dense "
+            "ODE output there; the device path saves at step boundaries only")
+    return int(round(n))
+
+
+def solve_gvector(case: M.Case, variables, t_calib, filter: dict | None = None, t_ini: float = 0.0, backend=Handle,
+                  handle=None) -> np.ndarray:
+    """ODE.solve(..., saveat) + ODEsolution2Gvector for every column of `case`; returns [nc, n_out] Float64.
+
+    filter["apply"] false (or filter None): the state is observed at the times t_calib (KiDUtils.jl:329-340).
+    filter["apply"] true: at filter["saveat_t"], averaged over nt_per_filtered_cell snapshots and blocks of
+    nz_per_filtered_cell levels (KiDUtils.jl:342-376)."""
+    h = handle or M.make_handle(case, backend)
+    dt = float(case.cfg.dt)
+    if filter is not None and filter["apply"]:
+        times = np.asarray(filter["saveat_t"], dtype=float)
+        nt_per = int(filter["nt_per_filtered_cell"])
+        n_cells = int(filter["nt_filtered"])
+        per = np.asarray(filter["nz_per_filtered_cell"], dtype=np.int32)
+    else:
+        times = np.asarray(t_calib, dtype=float)
+        nt_per, n_cells, per = 1, len(times), None
+    h.obs_configure(list(variables), per, n_cells, nt_per)
+    done = 0
+    for i, t in enumerate(times):
+        n = _step_index(float(t), t_ini, dt)
+        if n < done:
+            raise ValueError("save times must be non-decreasing")
+        if n > done:
+            h.step(t_ini + done * dt, n - done)
+            done = n
+        h.obs_accumulate(i // nt_per)
+    return h.obs_get()
+
+
+def kid_calibration_case(FT, model_settings: dict, cases: list[dict], u: np.ndarray, u_names: list[str]) -> M.Case:
+    """All (ensemble member, case) simulations of one `run_ensembles` call as the columns of ONE device ensemble.
+
+    u: [n_params, n_ensemble] (the reference's layout); cases: dicts with w1, p0, Nd (config["observations"]["cases"]).
+    Column index = member * n_cases + case.  Each case has its own hydrostatic profile (p0 enters ρ_ivp), each member
+    its own parameter set (update_parameters!, KiDUtils.jl:378-382)."""
+    u = np.atleast_2d(np.asarray(u, dtype=np.float64))
+    if u.shape[0] != len(u_names):
+        raise ValueError("u must be [n_params, n_ensemble]")
+    n_ens, n_cases = u.shape[1], len(cases)
+    ms = dict(model_settings)
+    model = {"KiD": M.MODEL_K1D, "KiD_col_sed": M.MODEL_K1D_COL_SED}[ms.get("model", "KiD")]
+    kw = {k: ms[k] for k in ("moisture_choice", "precipitation_choice", "rain_formation_scheme_choice",
+                             "sedimentation_scheme_choice", "z_min", "z_max", "n_elem", "dt", "t_end", "t1",
+                             "precip_sources", "precip_sinks", "open_system_activation", "local_activation",
+                             "qtot_flux_correction", "r_dry", "std_dry", "kappa", "toml_overrides") if k in ms}
+    if "rain_formation_choice" in ms:
+        kw["rain_formation_scheme_choice"] = ms["rain_formation_choice"]
+    if "sedimentation_choice" in ms:
+        kw["sedimentation_scheme_choice"] = ms["sedimentation_choice"]
+    if "κ" in ms:
+        kw["kappa"] = ms["κ"]
+    per_case = [M.k1d_case(FT, nc=1, model=model, w1=c["w1"], p0=c["p0"], prescribed_Nd=c["Nd"], **kw) for c in cases]
+    base = per_case[0]
+    nc = n_ens * n_cases
+    col_case = np.arange(nc) % n_cases
+    col_member = np.arange(nc) // n_cases
+    import copy
+    cfg = copy.copy(base.cfg)
+    cfg.nc = nc
+    FTt = np.dtype(FT).type
+    ens = M.Case(cfg=cfg, params=base.params,
+                 ρ_dry=np.stack([per_case[i].ρ_dry for i in col_case]).astype(FTt),
+                 T=np.stack([per_case[i].T for i in col_case]).astype(FTt),
+                 Y0=np.concatenate([per_case[i].Y0 for i in col_case]).astype(FTt), var_names=base.var_names,
+                 col_scalars={COL_W1: np.array([cases[i]["w1"] for i in col_case], dtype=FTt),
+                              COL_PRESCRIBED_ND: np.array([cases[i]["Nd"] for i in col_case], dtype=FTt),
+                              COL_Q_SURF: np.array([per_case[i].col_scalars[COL_Q_SURF][0] for i in col_case], dtype=FTt)},
+                 z_centers=base.z_centers, meta=dict(base.meta, cases=cases, col_case=col_case, col_member=col_member))
+    overrides = [{name: float(u[p, m]) for p, name in enumerate(u_names)} for m in range(n_ens)]
+    return M.with_parameter_sets(ens, overrides, column_to_set=col_member)
+
+
+def run_ensembles(u, u_names, config: dict, n_ensemble: int | None = None, FT=np.float64, backend=Handle) -> list:
+    """calibration/OptimizationUtils.jl:197-211 without the ReferenceStatistics transform (a host-side linear map):
+    returns [G(u[:, i]) for i in 1:n_ensemble], each the concatenation over the cases (KiDUtils.jl:45-81)."""
+    u = np.atleast_2d(np.asarray(u, dtype=np.float64))
+    n_ensemble = u.shape[1] if n_ensemble is None else n_ensemble
+    ms = config["model"]
+    cases = config["observations"]["cases"]
+    variables = config["observations"]["data_names"]
+    fcfg = ms["filter"]
+    t_calib = cases[0].get("t_cal", ms["t_calib"])
+    if any(not np.array_equal(c.get("t_cal", ms["t_calib"]), t_calib) for c in cases):
+        raise NotImplementedError("per-case t_cal: run the cases with different calibration times in separate calls")
+    filt = make_filter_props(fcfg["nz_unfiltered"], t_calib, apply=fcfg["apply"],
+                             nz_per_filtered_cell=fcfg.get("nz_per_filtered_cell"),
+                             nt_per_filtered_cell=fcfg.get("nt_per_filtered_cell", 1))
+    case = kid_calibration_case(FT, ms, cases, u[:, :n_ensemble], list(u_names))
+    G = solve_gvector(case, variables, t_calib, filt, t_ini=float(ms.get("t_ini", 0.0)), backend=backend)
+    n_cases = len(cases)
+    return [G[m * n_cases:(m + 1) * n_cases].reshape(-1) for m in range(n_ensemble)]
+
+
+def run_dyn_model(u, u_names, config: dict, FT=np.float64, backend=Handle) -> np.ndarray:
+    """calibration/KiDUtils.jl:10-43 with RS = nothing: the G vector of one parameter vector."""
+    return run_ensembles(np.asarray(u, dtype=np.float64).reshape(-1, 1), u_names, config, 1, FT=FT, backend=backend)[0]

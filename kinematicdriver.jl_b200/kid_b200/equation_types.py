@@ -143,3 +143,9 @@ def state_variable_names(moisture, precip) -> tuple[str, ...]:
     if precip.kid_enum == PRECIP_2M:
         names += ["N_liq", "N_rai", "N_aer"]
     return tuple(names)
+
+
+def state_variable_names_by_enum(moisture_enum: int, precip_enum: int) -> tuple[str, ...]:
+    """Same, from the C-ABI enums of a kid_config_t."""
+    from types import SimpleNamespace
+    return state_variable_names(SimpleNamespace(kid_enum=moisture_enum), SimpleNamespace(kid_enum=precip_enum))

@@ -31,6 +31,10 @@ AUX_FIELDS = [
     "cloud_sources.q_liq", "cloud_sources.q_ice",
 ]
 AUX_ID = {n: i for i, n in enumerate(AUX_FIELDS)}
+# enum kid_obs_var: the names get_variable_data_from_ODE accepts (src/Common/helper_functions.jl:98-191)
+OBS_VARS = ["qt", "ql", "qr", "qv", "qlr", "rt", "rl", "rr", "rv", "rlr", "Nl", "Nr", "Na", "rho",
+            "rain averaged terminal velocity", "rainrate"]
+OBS_ID = {n: i for i, n in enumerate(OBS_VARS)}
 
 
 class KidConfig(C.Structure):
@@ -98,6 +102,10 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         "kid_rhs": (C.c_int, [H, C.c_double, C.c_void_p]),
         "kid_get_aux": (C.c_int, [H, C.c_double, C.c_int32, C.c_void_p]),
         "kid_reduce_max": (C.c_int, [H, C.c_double, C.c_int32, C.POINTER(C.c_double)]),
+        "kid_obs_configure": (C.c_int, [H, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.c_int32,
+                                        C.POINTER(C.c_int64)]),
+        "kid_obs_accumulate": (C.c_int, [H, C.c_int32]),
+        "kid_obs_get": (C.c_int, [H, C.POINTER(C.c_double)]),
         "kid_k2d_stage_begin": (C.c_int, [H, C.c_double, C.c_int32]),
         "kid_k2d_edge_buffers": (C.c_int, [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
@@ -213,6 +221,28 @@ class Handle:
         v = C.c_double()
         self._check(self.lib.kid_reduce_max(self._h, float(t), fid, C.byref(v)))
         return v.value
+
+    # ---- calibration observables accumulated on the device (ODEsolution2Gvector)
+    def obs_configure(self, variables, nz_per_filtered_cell=None, nt_filtered: int = 1, nt_per_filtered_cell: int = 1) -> int:
+        ids = np.asarray([OBS_ID[v] if isinstance(v, str) else int(v) for v in variables], dtype=np.int32)
+        per = np.ones(len(ids), dtype=np.int32) if nz_per_filtered_cell is None else np.asarray(nz_per_filtered_cell, dtype=np.int32)
+        if per.shape != ids.shape:
+            raise ValueError("nz_per_filtered_cell needs one entry per variable")
+        n_out = C.c_int64()
+        self._check(self.lib.kid_obs_configure(self._h, len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)),
+                                               per.ctypes.data_as(C.POINTER(C.c_int32)), int(nt_filtered),
+                                               int(nt_per_filtered_cell), C.byref(n_out)))
+        self._obs_n_out = int(n_out.value)
+        return self._obs_n_out
+
+    def obs_accumulate(self, time_cell: int):
+        self._check(self.lib.kid_obs_accumulate(self._h, int(time_cell)))
+
+    def obs_get(self) -> np.ndarray:
+        """[nc, n_out] Float64: row c is the G vector of column c, ordered [time cell][variable][filtered level]."""
+        out = np.empty((self.cfg.nc, self._obs_n_out), dtype=np.float64)
+        self._check(self.lib.kid_obs_get(self._h, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
 
     # ---- stepping
     def step(self, t0: float, nsteps: int):

@@ -151,3 +151,91 @@ def gll(Nq):
     x = np.empty(Nq); w = np.empty(Nq); D = np.empty((Nq, Nq))
     load().kidoracle_gll(Nq, _ptr(x), _ptr(w), _ptr(D))
     return x, w, D
+
+
+class OracleEnsembleHandle:
+    """Handle surface of lib.Handle for a multi-parameter-set ensemble, on top of one OracleHandle per set, plus the
+    obs_* calls (numpy restatement in oracle/diagnostics.py).  Lets the CPU tests drive kid_b200.calibration."""
+
+    def __init__(self, cfg: KidConfig):
+        self.cfg, self.dtype = cfg, dtype_of(cfg.float_type)
+        self._subs, self._cols = [], []
+        self._pending = {}
+
+    # configuration is recorded and replayed into the per-set handles once the parameter table is known
+    def set_params(self, table, column_to_set=None):
+        import copy
+        t = np.atleast_2d(np.asarray(table, dtype=np.float64))
+        c2s = np.zeros(self.cfg.nc, dtype=int) if column_to_set is None else np.asarray(column_to_set)
+        for s in range(t.shape[0]):
+            cols = np.where(c2s == s)[0]
+            if cols.size == 0:
+                continue
+            cfg = copy.copy(self.cfg)
+            cfg.nc = int(cols.size)
+            h = OracleHandle(cfg)
+            h.set_params(t[s])
+            self._subs.append(h)
+            self._cols.append(cols)
+        self.nvars = self._subs[0].nvars
+
+    def set_profiles(self, ρ_dry, T):
+        self._rho_dry = np.asarray(ρ_dry, dtype=self.dtype)
+        for h, cols in zip(self._subs, self._cols):
+            h.set_profiles(ρ_dry[cols] if np.ndim(ρ_dry) == 2 else ρ_dry, T[cols] if np.ndim(T) == 2 else T)
+
+    def set_column_scalar(self, which, values):
+        for h, cols in zip(self._subs, self._cols):
+            h.set_column_scalar(which, None if values is None else np.broadcast_to(np.asarray(values), (self.cfg.nc,))[cols])
+
+    def set_state(self, Y):
+        for h, cols in zip(self._subs, self._cols):
+            h.set_state(np.asarray(Y)[cols])
+
+    def get_state(self, out=None):
+        out = np.empty((self.cfg.nc, self.nvars, self.cfg.nz), dtype=self.dtype) if out is None else out
+        for h, cols in zip(self._subs, self._cols):
+            out[cols] = h.get_state()
+        return out
+
+    def get_aux(self, t, field):
+        out = np.empty((self.cfg.nc, self.cfg.nz), dtype=self.dtype)
+        for h, cols in zip(self._subs, self._cols):
+            out[cols] = h.get_aux(t, field)
+        return out
+
+    def step(self, t0, nsteps):
+        for h in self._subs:
+            h.step(t0, nsteps)
+        self._t = t0 + nsteps * self.cfg.dt
+
+    def synchronize(self):
+        pass
+
+    def obs_configure(self, variables, nz_per_filtered_cell=None, nt_filtered=1, nt_per_filtered_cell=1):
+        from kid_b200 import equation_types as ET  # names of the state variables of this style
+        self._var_names = ET.state_variable_names_by_enum(self.cfg.moisture, self.cfg.precip)
+        self._obs_vars = list(variables)
+        nz = self.cfg.nz
+        per = np.ones(len(variables), dtype=int) if nz_per_filtered_cell is None else np.asarray(nz_per_filtered_cell)
+        self._obs_per, self._obs_ntp = per, nt_per_filtered_cell
+        self._obs_off = np.concatenate([[0], np.cumsum(nz // per)])
+        self._obs_G = np.zeros((self.cfg.nc, nt_filtered, int(self._obs_off[-1])))
+        self._t = getattr(self, "_t", 0.0)
+        return nt_filtered * int(self._obs_off[-1])
+
+    def obs_accumulate(self, time_cell):
+        from . import diagnostics as OD
+        Y = self.get_state()
+        need_vt = any("rain" in v for v in self._obs_vars)
+        vt = self.get_aux(self._t, "term_vel_rai") if need_vt else None
+        for c in range(self.cfg.nc):
+            u = {n: Y[c, i] for i, n in enumerate(self._var_names)}
+            rd = self._rho_dry[c] if self._rho_dry.ndim == 2 else self._rho_dry
+            for j, var in enumerate(self._obs_vars):
+                x = np.asarray(OD.get_variable_data_from_ODE(u, rd, var, None if vt is None else vt[c]), dtype=np.float64)
+                cell = x.reshape(-1, self._obs_per[j]).mean(axis=1)
+                self._obs_G[c, time_cell, self._obs_off[j]:self._obs_off[j + 1]] += cell / self._obs_ntp
+
+    def obs_get(self):
+        return self._obs_G.reshape(self.cfg.nc, -1).copy()

@@ -1,0 +1,59 @@
+"""Host logic of kid_b200.calibration (filter bookkeeping, (member, case) -> column mapping, save-time handling),
+driven on the CPU through the oracle backend."""
+import numpy as np
+import pytest
+
+from kid_b200 import calibration as CAL
+from kid_b200 import model as M
+from oracle import diagnostics as OD
+from oracle.oracle import OracleEnsembleHandle
+
+
+def test_make_filter_props_matches_reference_bookkeeping():
+    f = CAL.make_filter_props([128, 128], [0.0, 600.0, 1200.0], apply=True, nz_per_filtered_cell=[2, 4], nt_per_filtered_cell=3)
+    assert list(f["nz_filtered"]) == [64, 32] and f["nt_filtered"] == 2
+    assert np.allclose(f["saveat_t"], [100, 300, 500, 700, 900, 1100])  # midpoints of the sub-intervals
+    with pytest.raises(AssertionError):
+        CAL.make_filter_props([128], [0.0, 1.0], nz_per_filtered_cell=[3])
+    g = CAL.make_filter_props([16], [0.0, 10.0])
+    assert list(g["nz_per_filtered_cell"]) == [1] and np.allclose(g["saveat_t"], [5.0])
+
+
+def test_filtered_gvector_with_unit_cells_is_the_unfiltered_one():
+    rng = np.random.default_rng(1)
+    nz = 8
+    states = [{"ρq_tot": rng.uniform(1e-3, 1e-2, nz), "ρq_liq": rng.uniform(0, 1e-3, nz), "ρq_rai": rng.uniform(0, 1e-4, nz)}
+              for _ in range(3)]
+    rd = rng.uniform(0.9, 1.2, nz)
+    variables = ["qt", "rl", "rlr", "rho"]
+    filt = CAL.make_filter_props([nz] * 4, [0.0, 1.0, 2.0, 3.0], apply=True)
+    a = OD.gvector_unfiltered(states, rd, variables)
+    b = OD.gvector_filtered(states, rd, variables, filt)
+    assert np.allclose(a, b, rtol=1e-15)
+
+
+def test_save_times_off_the_step_grid_are_refused():
+    case = M.k1d_case(np.float64, nc=1, n_elem=8, moisture_choice="NonEquilibriumMoisture", precipitation_choice="Precipitation1M", dt=2.0)
+    with pytest.raises(NotImplementedError):
+        CAL.solve_gvector(case, ["qt"], [3.0], backend=OracleEnsembleHandle)
+
+
+def test_run_ensembles_on_the_oracle_backend():
+    config = {
+        "model": dict(model="KiD", moisture_choice="NonEquilibriumMoisture", precipitation_choice="Precipitation1M",
+                      n_elem=12, dt=5.0, t_end=200.0, t_calib=[0.0, 100.0, 200.0],
+                      filter=dict(apply=True, nz_unfiltered=[12, 12], nz_per_filtered_cell=[2, 3], nt_per_filtered_cell=2)),
+        "observations": dict(data_names=["rlr", "rainrate"],
+                             cases=[dict(w1=2.0, p0=100000.0, Nd=1e8), dict(w1=1.5, p0=99000.0, Nd=5e7)]),
+    }
+    u_names = ["rain_terminal_velocity_size_relation_coefficient_chiv", "rain_cross_section_size_relation_coefficient_chia"]
+    u = np.array([[1.0, 0.6], [1.0, 2.0]])
+    G = CAL.run_ensembles(u, u_names, config, 2, backend=OracleEnsembleHandle)
+    assert len(G) == 2 and G[0].shape == (2 * 2 * (6 + 4),) and np.isfinite(np.stack(G)).all()
+    case = CAL.kid_calibration_case(np.float64, config["model"], config["observations"]["cases"], u, u_names)
+    assert list(case.meta["col_member"]) == [0, 0, 1, 1] and list(case.meta["col_case"]) == [0, 1, 0, 1]
+    assert case.params.shape[0] == 2 and case.ρ_dry.shape == (4, 12)
+    assert not np.allclose(case.ρ_dry[0], case.ρ_dry[1])  # p0 enters the hydrostatic profile
+    # member 0 / case 0 is the plain single-column run
+    single = CAL.run_dyn_model(u[:, 0], u_names, config, backend=OracleEnsembleHandle)
+    assert np.array_equal(single, G[0])

@@ -1,0 +1,117 @@
+"""Device-side calibration observables (kid_obs_*) and the batched run_ensembles against the numpy restatement of
+get_variable_data_from_ODE / ODEsolution2Gvector applied to downloaded states."""
+import numpy as np
+import pytest
+
+from kid_b200 import calibration as CAL
+from kid_b200 import model as M
+from kid_b200.lib import Handle, KidCudaError
+from oracle import diagnostics as OD
+from oracle.oracle import OracleHandle
+
+pytestmark = pytest.mark.gpu
+
+VARS_2M = ["rho", "qt", "ql", "qr", "qv", "qlr", "rt", "rl", "rr", "rv", "rlr", "Nl", "Nr", "Na",
+           "rain averaged terminal velocity", "rainrate"]
+
+
+def _reference_states(case, times, FT):
+    """States at the save times from the device (stepping parity is covered elsewhere) and v_t from the C++ oracle."""
+    h = M.make_handle(case, Handle)
+    o = M.make_handle(case, OracleHandle)
+    states, vts, done = [], [], 0
+    for t in times:
+        n = int(round(t / case.cfg.dt))
+        if n > done:
+            h.step(done * case.cfg.dt, n - done)
+            done = n
+        Y = h.get_state()
+        o.set_state(Y)
+        states.append(Y)
+        vts.append(o.get_aux(t, "term_vel_rai"))
+    return states, vts
+
+
+def _column_dicts(case, states, c):
+    return [{n: Y[c, i, :] for i, n in enumerate(case.var_names)} for Y in states]
+
+
+@pytest.mark.parametrize("FT,rtol", [(np.float64, 1e-7), (np.float32, 2e-3)])
+def test_gvector_unfiltered_matches_restated_reference(FT, rtol):
+    case = M.k1d_ensemble_case(FT, nc=5, n_profiles=2, n_elem=32, moisture_choice="NonEquilibriumMoisture",
+                               precipitation_choice="Precipitation2M")
+    times = [300.0, 600.0, 900.0]
+    G = CAL.solve_gvector(case, VARS_2M, times)
+    states, vts = _reference_states(case, times, FT)
+    assert G.shape == (5, len(times) * len(VARS_2M) * 32)
+    for c in range(5):
+        rd = case.ρ_dry[c] if case.ρ_dry.ndim == 2 else case.ρ_dry
+        ref = OD.gvector_unfiltered(_column_dicts(case, states, c), rd, VARS_2M, [v[c] for v in vts])
+        # per variable block: relative to the block's scale (v_t differs from the oracle at the rhs tolerance)
+        g, r = G[c].reshape(len(times), len(VARS_2M), 32), ref.reshape(len(times), len(VARS_2M), 32)
+        for j, name in enumerate(VARS_2M):
+            scale = np.abs(r[:, j]).max() + 1e-300
+            tol = rtol if "rain" in name else (1e-12 if FT is np.float64 else 1e-6)
+            assert np.abs(g[:, j] - r[:, j]).max() <= tol * scale, (name, c)
+
+
+def test_gvector_filtered_matches_restated_reference():
+    FT = np.float64
+    case = M.k1d_ensemble_case(FT, nc=3, n_profiles=2, n_elem=32, moisture_choice="NonEquilibriumMoisture",
+                               precipitation_choice="Precipitation1M")
+    variables = ["rho", "ql", "qr", "rainrate"]
+    filt = CAL.make_filter_props([32] * 4, [0.0, 400.0, 800.0, 1200.0], apply=True, nz_per_filtered_cell=[1, 2, 4, 8],
+                                 nt_per_filtered_cell=2)
+    assert np.allclose(filt["saveat_t"], [100, 300, 500, 700, 900, 1100])
+    G = CAL.solve_gvector(case, variables, None, filt)
+    states, vts = _reference_states(case, filt["saveat_t"], FT)
+    for c in range(3):
+        rd = case.ρ_dry[c] if case.ρ_dry.ndim == 2 else case.ρ_dry
+        ref = OD.gvector_filtered(_column_dicts(case, states, c), rd, variables, filt, [v[c] for v in vts])
+        assert G[c].shape == ref.shape == (3 * (32 + 16 + 8 + 4),)
+        assert np.abs(G[c] - ref).max() <= 1e-7 * np.abs(ref).max()
+
+
+def test_observable_missing_in_style_is_an_error():
+    case = M.k1d_case(np.float64, nc=1, n_elem=16, moisture_choice="EquilibriumMoisture", precipitation_choice="Precipitation0M")
+    h = M.make_handle(case, Handle)
+    with pytest.raises(KidCudaError):
+        h.obs_configure(["ql"])
+    with pytest.raises(KidCudaError):
+        h.obs_configure(["rainrate"])
+    assert h.obs_configure(["qt", "rho"]) == 32
+
+
+def test_run_ensembles_batched_equals_member_by_member():
+    """(member, case) -> column mapping: the batched ensemble returns what separate single-simulation runs return."""
+    FT = np.float64
+    config = {
+        "model": dict(model="KiD", moisture_choice="NonEquilibriumMoisture", precipitation_choice="Precipitation1M",
+                      n_elem=24, dt=2.0, t_end=600.0, t_calib=[0.0, 300.0, 600.0],
+                      filter=dict(apply=True, nz_unfiltered=[24, 24], nz_per_filtered_cell=[2, 3], nt_per_filtered_cell=3)),
+        "observations": dict(data_names=["rlr", "rainrate"],
+                             cases=[dict(w1=2.0, p0=100000.0, Nd=1e8), dict(w1=1.5, p0=99000.0, Nd=5e7)]),
+    }
+    u_names = ["rain_terminal_velocity_size_relation_coefficient_chiv", "rain_cross_section_size_relation_coefficient_chia"]
+    u = np.array([[1.0, 0.6, 1.4], [1.0, 2.0, 0.7]])
+    G = CAL.run_ensembles(u, u_names, config, 3, FT=FT)
+    assert len(G) == 3 and G[0].shape == (2 * 2 * (12 + 8),)
+    assert not np.allclose(G[0], G[1]) and np.isfinite(np.stack(G)).all()
+    for m in range(3):
+        single = CAL.run_dyn_model(u[:, m], u_names, config, FT=FT)
+        assert np.array_equal(single, G[m])
+    # the first member/case is the plain default simulation with that case's scalars
+    plain = M.k1d_case(FT, nc=1, moisture_choice="NonEquilibriumMoisture", precipitation_choice="Precipitation1M",
+                       n_elem=24, dt=2.0, t_end=600.0, w1=2.0, p0=100000.0, prescribed_Nd=1e8)
+    filt = CAL.make_filter_props([24, 24], [0.0, 300.0, 600.0], apply=True, nz_per_filtered_cell=[2, 3], nt_per_filtered_cell=3)
+    Gp = CAL.solve_gvector(plain, ["rlr", "rainrate"], None, filt)
+    assert np.allclose(Gp[0], G[0][:Gp.shape[1]], rtol=1e-12, atol=0)
+
+
+def test_reduce_max_on_device_matches_downloaded_field():
+    case = M.k1d_ensemble_case(np.float32, nc=70, n_profiles=4, n_elem=32, moisture_choice="NonEquilibriumMoisture",
+                               precipitation_choice="Precipitation2M")
+    h = M.make_handle(case, Handle)
+    h.step(0.0, 400)
+    for f in ("q_liq", "N_liq", "precip_sources.q_rai", "term_vel_rai"):
+        assert h.reduce_max(400.0, f) == float(np.max(h.get_aux(400.0, f)))
