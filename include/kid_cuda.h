@@ -173,6 +173,17 @@ int kid_rhs(kid_handle_t* h, double t, void* dY_out);
  * field is evaluated from the current state at time t (what the FSAL rhs call
  * leaves in aux).  out: nc x nz values, level fastest. */
 int kid_get_aux(kid_handle_t* h, double t, int32_t field, void* out);
+/* several fields from ONE rhs evaluation.  out: nc x nfields x nz values ([column][field][level]). */
+int kid_get_aux_many(kid_handle_t* h, double t, int32_t nfields, const int32_t* fields, void* out);
+/* replaces: the DiscreteCallback(condition_io, affect_io!) output path (netcdf_io.jl:176-194) at its default cadence
+ * (every 2nd step): the fields are evaluated on the compute stream and downloaded by a second stream from
+ * double-buffered staging, so the following kid_step launches overlap the PCIe transfer.  out_pinned (page-locked,
+ * layout of kid_get_aux_many) is valid after kid_output_wait; at most two outputs are in flight. */
+int kid_output_enqueue(kid_handle_t* h, double t, int32_t nfields, const int32_t* fields, void* out_pinned);
+int kid_output_wait(kid_handle_t* h);
+/* page-locked host memory for the *_async / kid_output_enqueue calls (cudaHostAlloc / cudaFreeHost) */
+void* kid_host_alloc(size_t bytes);
+void kid_host_free(void* p);
 /* replaces: maximum(aux.microph_variables.q_liq) (netcdf_io.jl:166) */
 int kid_reduce_max(kid_handle_t* h, double t, int32_t field, double* out);
 

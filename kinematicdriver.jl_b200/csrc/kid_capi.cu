@@ -73,6 +73,14 @@ struct kid_handle {
     int Nq = 0, nfields = 0;
     K2DField fields[KID_MAX_DSS];
     double gll_x[KID_MAX_NQ], gll_w[KID_MAX_NQ], gll_D[KID_MAX_NQ * KID_MAX_NQ];
+    // aux output: fields of the next diag launch; asynchronous double-buffered download (kid_output_*)
+    int diag_nfields = 1, diag_fields[KID_NAUX];
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    void* ostage[2] = {nullptr, nullptr};
+    size_t ostage_bytes[2] = {0, 0};
+    bool ev_used[2] = {false, false};
+    int obuf = 0;
     // calibration observables (kid_obs_*)
     double* obsG = nullptr;
     unsigned long long* red = nullptr;
@@ -183,6 +191,8 @@ KArgs<FT> make_args(kid_handle* h, double t0, int nsteps, int diag_mode, int fie
     a.C = h->C;
     a.NW = h->NW;
     a.diag_mode = diag_mode;
+    a.nfields = (diag_mode == 2) ? h->diag_nfields : 0;
+    for (int f = 0; f < a.nfields; ++f) a.fields[f] = h->diag_fields[f];
     a.field = field;
     a.dt = FT(h->cfg.dt);
     a.dz = FT((h->cfg.z_max - h->cfg.z_min) / h->cfg.nz);
@@ -263,6 +273,7 @@ int choose_tile(kid_handle* h) {
 }
 
 int launch_tile(kid_handle* h, double t0, int nsteps, int diag_mode, int field, int update_prev = 0) {
+    if (diag_mode == 2 && field >= 0) { h->diag_nfields = 1; h->diag_fields[0] = field; }  // field < 0: h->diag_fields preset
     cudaError_t e;
     if (h->f64) {
         auto a = make_args<double>(h, t0, nsteps, diag_mode, field);
@@ -457,7 +468,16 @@ int kid_create(const kid_config_t* cfg, kid_handle_t** out) {
 }
 
 void kid_destroy(kid_handle_t* h) {
-    if (h) { if (h->obsG) cudaFree(h->obsG); if (h->red) cudaFree(h->red); }
+    if (h) {
+        if (h->obsG) cudaFree(h->obsG);
+        if (h->red) cudaFree(h->red);
+        if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+        for (int b = 0; b < 2; ++b) {
+            if (h->ostage[b]) cudaFree(h->ostage[b]);
+            if (h->ev_ready[b]) cudaEventDestroy(h->ev_ready[b]);
+            if (h->ev_done[b]) cudaEventDestroy(h->ev_done[b]);
+        }
+    }
     if (!h) return;
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void* p : {h->ps_liq, h->ps_mix, h->prm_sets, h->col_to_set, h->Y, h->rho_dry, h->T, h->w1, h->q_surf, h->Nd, h->aux_Naer, h->out, h->staging, h->U, h->S,
@@ -660,6 +680,78 @@ int kid_get_aux(kid_handle_t* h, double t, int32_t field, void* out) {
     if (ensure_out(h, state_elems(h) * h->fsz)) return 1;
     if (launch_tile(h, t, 1, 2, field)) return 1;
     return to_host_layout(h, h->out, out, 1);
+}
+
+static int set_diag_fields(kid_handle_t* h, int32_t nfields, const int32_t* fields) {
+    if (nfields < 1 || nfields > KID_NAUX || !fields) return fail("aux output: 1..KID_NAUX field ids");
+    for (int f = 0; f < nfields; ++f) {
+        if (fields[f] < 0 || fields[f] >= KID_NAUX) return fail("invalid aux field id");
+        h->diag_fields[f] = fields[f];
+    }
+    h->diag_nfields = nfields;
+    return 0;
+}
+
+int kid_get_aux_many(kid_handle_t* h, double t, int32_t nfields, const int32_t* fields, void* out) {
+    if (check_ready(h)) return 1;
+    if (!out) return fail("null argument");
+    if (set_diag_fields(h, nfields, fields)) return 1;
+    if (ensure_out(h, std::max(state_elems(h), size_t(nfields) * h->cfg.nz * h->ncp) * h->fsz)) return 1;
+    if (launch_tile(h, t, 1, 2, -1)) return 1;
+    return to_host_layout(h, h->out, out, nfields);
+}
+
+int kid_output_enqueue(kid_handle_t* h, double t, int32_t nfields, const int32_t* fields, void* out_pinned) {
+    if (check_ready(h)) return 1;
+    if (!out_pinned) return fail("null argument");
+    if (set_diag_fields(h, nfields, fields)) return 1;
+    const int nc = h->cfg.nc, nz = h->cfg.nz;
+    if (!h->copy_stream) {
+        KID_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            KID_CUDA(cudaEventCreateWithFlags(&h->ev_ready[b], cudaEventDisableTiming));
+            KID_CUDA(cudaEventCreateWithFlags(&h->ev_done[b], cudaEventDisableTiming));
+        }
+    }
+    const int b = h->obuf;
+    h->obuf ^= 1;
+    const size_t bytes = size_t(nc) * nfields * nz * h->fsz;
+    // the staging buffer is reused every second output: the compute stream waits for its previous download
+    if (h->ev_used[b]) KID_CUDA(cudaStreamWaitEvent(h->stream, h->ev_done[b], 0));
+    if (h->ostage_bytes[b] < bytes) {
+        if (h->ostage[b]) { KID_CUDA(cudaStreamSynchronize(h->copy_stream)); cudaFree(h->ostage[b]); }
+        h->ostage[b] = nullptr; h->ostage_bytes[b] = 0;
+        KID_CUDA(cudaMalloc(&h->ostage[b], bytes));
+        h->ostage_bytes[b] = bytes;
+    }
+    if (ensure_out(h, std::max(state_elems(h), size_t(nfields) * nz * h->ncp) * h->fsz)) return 1;
+    if (launch_tile(h, t, 1, 2, -1)) return 1;
+    dim3 block(32, 8), grid((h->ncp + 31) / 32, (nfields * nz + 31) / 32);
+    if (h->f64)
+        device_to_host_layout<double><<<grid, block, 0, h->stream>>>((const double*)h->out, (double*)h->ostage[b], nc, h->ncp, nfields, nz);
+    else
+        device_to_host_layout<float><<<grid, block, 0, h->stream>>>((const float*)h->out, (float*)h->ostage[b], nc, h->ncp, nfields, nz);
+    KID_CUDA(cudaGetLastError());
+    h->launches++;
+    KID_CUDA(cudaEventRecord(h->ev_ready[b], h->stream));
+    KID_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_ready[b], 0));
+    KID_CUDA(cudaMemcpyAsync(out_pinned, h->ostage[b], bytes, cudaMemcpyDeviceToHost, h->copy_stream));
+    KID_CUDA(cudaEventRecord(h->ev_done[b], h->copy_stream));
+    h->ev_used[b] = true;
+    return 0;
+}
+
+void* kid_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { g_err = "cudaHostAlloc failed"; return nullptr; }
+    return p;
+}
+void kid_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int kid_output_wait(kid_handle_t* h) {
+    if (!h) return fail("null handle");
+    if (h->copy_stream) KID_CUDA(cudaStreamSynchronize(h->copy_stream));
+    return 0;
 }
 
 int kid_reduce_max(kid_handle_t* h, double t, int32_t field, double* out) {

@@ -60,13 +60,15 @@ struct KArgs {
     const FT* ps_mix;       // same shape as T; filled by profile_consts_kernel when params or profiles change
     const DevParams<FT>* prm_sets;  // per-column parameter sets (calibration ensembles), null if one set is shared
     const int* col_to_set;          // [ncp] column -> parameter set
-    FT* out;                // DIAG: dY [NV][nz][ncp] (mode 1) or one aux field [nz][ncp] (mode 2)
+    FT* out;                // DIAG: dY [NV][nz][ncp] (mode 1) or the requested aux fields [nfields][nz][ncp] (mode 2)
     int nz, nc, ncp;
     int prof_per_column;    // 0: rho_dry/T are [nz]; 1: [nz][ncp]
     int model;              // enum kid_model
     int nsteps;
     int C, NW;              // tile: columns per CTA, level chunks per column
-    int diag_mode, field;   // 0 = step, 1 = rhs only, 2 = aux field
+    int diag_mode, field;   // 0 = step, 1 = rhs only, 2 = aux fields (fields[0..nfields) -> out[f][nz][ncp])
+    int nfields;
+    int fields[KID_NAUX];
     FT dt, dz;
     double t0;
     DevSwitches sw;
@@ -481,8 +483,9 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                     } else {
                         FT v1 = FT(0), v2 = FT(0);
                         if constexpr (L::has_pr) { v1 = vt1s[kidx(k)]; v2 = vt2s[kidx(k)]; }
-                        A.out[size_t(k) * ncp + gc] = aux_field_value<FT, MOIST, PRECIP>(
-                            P, A.field, a, src, v1, v2, act_Nl, A.sw.open_system_activation != 0);
+                        for (int f = 0; f < A.nfields; ++f)  // one rhs evaluation serves every requested field
+                            A.out[size_t(f) * plane + size_t(k) * ncp + gc] = aux_field_value<FT, MOIST, PRECIP>(
+                                P, A.fields[f], a, src, v1, v2, act_Nl, A.sw.open_system_activation != 0);
                     }
                 } else {
                     // SSPRK33 as a convex combination  u_new = a·u^n + b·(y + dt·f(y)),  (a, b) = (0, 1), (3/4, 1/4),

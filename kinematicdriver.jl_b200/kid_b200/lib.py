@@ -102,6 +102,11 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         "kid_rhs": (C.c_int, [H, C.c_double, C.c_void_p]),
         "kid_get_aux": (C.c_int, [H, C.c_double, C.c_int32, C.c_void_p]),
         "kid_reduce_max": (C.c_int, [H, C.c_double, C.c_int32, C.POINTER(C.c_double)]),
+        "kid_get_aux_many": (C.c_int, [H, C.c_double, C.c_int32, C.POINTER(C.c_int32), C.c_void_p]),
+        "kid_output_enqueue": (C.c_int, [H, C.c_double, C.c_int32, C.POINTER(C.c_int32), C.c_void_p]),
+        "kid_output_wait": (C.c_int, [H]),
+        "kid_host_alloc": (C.c_void_p, [C.c_size_t]),
+        "kid_host_free": (None, [C.c_void_p]),
         "kid_obs_configure": (C.c_int, [H, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.c_int32,
                                         C.POINTER(C.c_int64)]),
         "kid_obs_accumulate": (C.c_int, [H, C.c_int32]),
@@ -126,6 +131,29 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     if path is None:
         _LIB = lib
     return lib
+
+
+class _PinnedOwner:
+    def __init__(self, lib, ptr):
+        self.lib, self.ptr = lib, ptr
+
+    def __del__(self):
+        try:
+            self.lib.kid_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype, lib: C.CDLL | None = None) -> np.ndarray:
+    """numpy array in page-locked host memory (kid_host_alloc), for the asynchronous transfers."""
+    lib = lib or load_library()
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = lib.kid_host_alloc(max(nbytes, 1))
+    if not ptr:
+        raise KidCudaError(lib.kid_last_error().decode())
+    buf = (C.c_char * max(nbytes, 1)).from_address(ptr)
+    buf._owner = _PinnedOwner(lib, ptr)  # freed when the last array view dies
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
 def _ptr(a: np.ndarray):
@@ -215,6 +243,28 @@ class Handle:
         out = np.empty((self.cfg.nc, self.cfg.nz), dtype=self.dtype)
         self._check(self.lib.kid_get_aux(self._h, float(t), fid, _ptr(out)))
         return out
+
+    @staticmethod
+    def _field_ids(fields) -> np.ndarray:
+        return np.asarray([AUX_ID[f] if isinstance(f, str) else int(f) for f in fields], dtype=np.int32)
+
+    def get_aux_many(self, t: float, fields) -> np.ndarray:
+        """[nc, nfields, nz]: all requested aux fields from ONE rhs evaluation (one kernel launch)."""
+        ids = self._field_ids(fields)
+        out = np.empty((self.cfg.nc, len(ids), self.cfg.nz), dtype=self.dtype)
+        self._check(self.lib.kid_get_aux_many(self._h, float(t), len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)), _ptr(out)))
+        return out
+
+    def output_enqueue(self, t: float, fields, out_pinned: np.ndarray):
+        """Asynchronous get_aux_many into page-locked memory (see pinned_empty); valid after output_wait()."""
+        ids = self._field_ids(fields)
+        assert out_pinned.flags["C_CONTIGUOUS"] and out_pinned.dtype == self.dtype
+        assert out_pinned.size == self.cfg.nc * len(ids) * self.cfg.nz
+        self._check(self.lib.kid_output_enqueue(self._h, float(t), len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                _ptr(out_pinned)))
+
+    def output_wait(self):
+        self._check(self.lib.kid_output_wait(self._h))
 
     def reduce_max(self, t: float, field) -> float:
         fid = AUX_ID[field] if isinstance(field, str) else int(field)

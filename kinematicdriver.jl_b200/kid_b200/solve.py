@@ -53,7 +53,12 @@ class OutputCadence:
 def simulation_output(handle, t: float, fields=None) -> dict:
     """The aux fields `CO.simulation_output(aux, t)` appends to the NetCDF file (netcdf_io.jl:144-170) plus the
     `ql_max` time series entry, read from the device at time t."""
-    out = {f: handle.get_aux(t, f) for f in (fields or AUX_FIELDS)}
+    names = list(fields or AUX_FIELDS)
+    if hasattr(handle, "get_aux_many"):
+        A = handle.get_aux_many(t, names)  # one rhs evaluation / kernel launch for all fields
+        out = {f: A[:, i, :] for i, f in enumerate(names)}
+    else:
+        out = {f: handle.get_aux(t, f) for f in names}
     out["ql_max"] = float(np.max(out["q_liq"])) if "q_liq" in out else handle.reduce_max(t, "q_liq")
     return out
 
@@ -96,6 +101,45 @@ def solve(case: M.Case, tspan=None, dt: float | None = None, saveat: float | Non
     return sol
 
 
+class OutputPipeline:
+    """The output callback of the drivers (DiscreteCallback(condition_io, affect_io!), netcdf_io.jl:176-194) without
+    stalling the integration: the aux fields of an output time are evaluated on the device and downloaded by a second
+    stream into a ring of page-locked buffers while the next steps run; `sink(t, {field: [nc, nz]})` is called when a
+    buffer has landed (one output late)."""
+
+    def __init__(self, handle, fields=None, sink=None, depth: int = 2):
+        from .lib import pinned_empty
+        self.h, self.fields = handle, list(fields or AUX_FIELDS)
+        self.sink = sink or (lambda t, out: self.results.append((t, out)))
+        self.results = []
+        shape = (handle.cfg.nc, len(self.fields), handle.cfg.nz)
+        self.ring = [pinned_empty(shape, handle.dtype, handle.lib) for _ in range(depth)]
+        self.pending = []  # (slot, t) in flight, oldest first
+        self.n = 0
+
+    def _retire(self, count: int):
+        if not count:
+            return
+        self.h.output_wait()  # the copy stream is in order: everything enqueued so far has landed
+        for slot, t in self.pending[:count]:
+            A = self.ring[slot]
+            self.sink(t, dict({f: A[:, i, :].copy() for i, f in enumerate(self.fields)},
+                              ql_max=float(A[:, self.fields.index("q_liq")].max()) if "q_liq" in self.fields else None))
+        del self.pending[:count]
+
+    def enqueue(self, t: float):
+        slot = self.n % len(self.ring)
+        if len(self.pending) == len(self.ring):  # the slot about to be reused must be consumed first
+            self._retire(1)
+        self.h.output_enqueue(t, self.fields, self.ring[slot])
+        self.pending.append((slot, t))
+        self.n += 1
+
+    def drain(self):
+        self._retire(len(self.pending))
+        return self.results
+
+
 # ------------------------------------------------------------------ drivers
 def run_KiD_simulation(FT, opts: dict | None = None, nc: int = 1, output: bool = False, backend=Handle):
     """test/experiments/KiD_driver/run_KiD_simulation.jl:13-166 (minus NetCDF/plots): returns (solution, outputs)."""
@@ -105,15 +149,21 @@ def run_KiD_simulation(FT, opts: dict | None = None, nc: int = 1, output: bool =
     case = M.k1d_case(FT, nc=nc, **opts)
     TS = case.meta["TS"]
     outputs = []
-    cb = cond = None
-    if output:
-        cond = OutputCadence(TS)
-        cb = lambda h, t: outputs.append((t, simulation_output(h, t)))  # noqa: E731
+    cb = cond = pipe = None
     h = M.make_handle(case, backend)
     if output:
-        outputs.append((0.0, simulation_output(h, 0.0)))
+        cond = OutputCadence(TS)
+        if hasattr(h, "output_enqueue"):  # asynchronous, double-buffered download of the output fields
+            pipe = OutputPipeline(h, sink=lambda t, out: outputs.append((t, out)))
+            cb = lambda hh, t: pipe.enqueue(t)  # noqa: E731
+            pipe.enqueue(0.0)
+        else:
+            cb = lambda hh, t: outputs.append((t, simulation_output(hh, t)))  # noqa: E731
+            outputs.append((0.0, simulation_output(h, 0.0)))
     o = case.meta["opts"]
     sol = solve(case, (o["t_ini"], o["t_end"]), dt=TS.dt, saveat=TS.dt_io, callback=cb, condition=cond, handle=h)
+    if pipe is not None:
+        pipe.drain()
     return sol, outputs
 
 

@@ -115,3 +115,42 @@ def test_reduce_max_on_device_matches_downloaded_field():
     h.step(0.0, 400)
     for f in ("q_liq", "N_liq", "precip_sources.q_rai", "term_vel_rai"):
         assert h.reduce_max(400.0, f) == float(np.max(h.get_aux(400.0, f)))
+
+
+def test_get_aux_many_equals_field_by_field():
+    from kid_b200.lib import AUX_FIELDS
+    case = M.k1d_ensemble_case(np.float32, nc=40, n_profiles=4, n_elem=32, moisture_choice="NonEquilibriumMoisture",
+                               precipitation_choice="Precipitation2M")
+    h = M.make_handle(case, Handle)
+    h.step(0.0, 500)
+    l0 = h.launch_count
+    A = h.get_aux_many(500.0, AUX_FIELDS)
+    assert h.launch_count - l0 == 2  # one rhs evaluation + one layout transpose for all 29 fields
+    assert A.shape == (40, len(AUX_FIELDS), 32)
+    for i, f in enumerate(AUX_FIELDS):
+        assert np.array_equal(A[:, i, :], h.get_aux(500.0, f), equal_nan=True), f
+
+
+def test_output_pipeline_matches_synchronous_output():
+    """Asynchronous double-buffered output (kid_output_enqueue) returns what simulation_output returns at the same times,
+    while the integration continues between the enqueue and the wait."""
+    from kid_b200.solve import OutputPipeline, simulation_output
+    fields = ["q_liq", "q_rai", "N_liq", "term_vel_rai", "precip_sources.q_rai", "ρ", "p"]
+    case = M.k1d_ensemble_case(np.float64, nc=9, n_profiles=3, n_elem=32, moisture_choice="NonEquilibriumMoisture",
+                               precipitation_choice="Precipitation2M")
+    times = [0.0, 100.0, 200.0, 300.0, 400.0, 500.0, 600.0]
+    ha, hb = M.make_handle(case, Handle), M.make_handle(case, Handle)
+    pipe = OutputPipeline(ha, fields)
+    sync = []
+    for i, t in enumerate(times):
+        if i:
+            ha.step(times[i - 1], 100)
+            hb.step(times[i - 1], 100)
+        pipe.enqueue(t)
+        sync.append((t, simulation_output(hb, t, fields)))
+    res = pipe.drain()
+    assert [t for t, _ in res] == times
+    for (t, a), (_, b) in zip(res, sync):
+        for f in fields:
+            assert np.array_equal(a[f], b[f]), (t, f)
+        assert a["ql_max"] == b["ql_max"]
