@@ -248,10 +248,11 @@ class Handle:
     def _field_ids(fields) -> np.ndarray:
         return np.asarray([AUX_ID[f] if isinstance(f, str) else int(f) for f in fields], dtype=np.int32)
 
-    def get_aux_many(self, t: float, fields) -> np.ndarray:
+    def get_aux_many(self, t: float, fields, out: np.ndarray | None = None) -> np.ndarray:
         """[nc, nfields, nz]: all requested aux fields from ONE rhs evaluation (one kernel launch)."""
         ids = self._field_ids(fields)
-        out = np.empty((self.cfg.nc, len(ids), self.cfg.nz), dtype=self.dtype)
+        if out is None:
+            out = np.empty((self.cfg.nc, len(ids), self.cfg.nz), dtype=self.dtype)
         self._check(self.lib.kid_get_aux_many(self._h, float(t), len(ids), ids.ctypes.data_as(C.POINTER(C.c_int32)), _ptr(out)))
         return out
 

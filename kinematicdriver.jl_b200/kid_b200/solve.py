@@ -105,13 +105,15 @@ class OutputPipeline:
     """The output callback of the drivers (DiscreteCallback(condition_io, affect_io!), netcdf_io.jl:176-194) without
     stalling the integration: the aux fields of an output time are evaluated on the device and downloaded by a second
     stream into a ring of page-locked buffers while the next steps run; `sink(t, {field: [nc, nz]})` is called when a
-    buffer has landed (one output late)."""
+    buffer has landed (one output late).  The arrays handed to a user sink are VIEWS of the page-locked ring, valid
+    during the call only (write them to disk or copy what is kept); the default sink keeps copies in `.results`."""
 
     def __init__(self, handle, fields=None, sink=None, depth: int = 2):
         from .lib import pinned_empty
         self.h, self.fields = handle, list(fields or AUX_FIELDS)
-        self.sink = sink or (lambda t, out: self.results.append((t, out)))
         self.results = []
+        self.sink = sink or (lambda t, out: self.results.append(
+            (t, {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in out.items()})))
         shape = (handle.cfg.nc, len(self.fields), handle.cfg.nz)
         self.ring = [pinned_empty(shape, handle.dtype, handle.lib) for _ in range(depth)]
         self.pending = []  # (slot, t) in flight, oldest first
@@ -123,7 +125,7 @@ class OutputPipeline:
         self.h.output_wait()  # the copy stream is in order: everything enqueued so far has landed
         for slot, t in self.pending[:count]:
             A = self.ring[slot]
-            self.sink(t, dict({f: A[:, i, :].copy() for i, f in enumerate(self.fields)},
+            self.sink(t, dict({f: A[:, i, :] for i, f in enumerate(self.fields)},
                               ql_max=float(A[:, self.fields.index("q_liq")].max()) if "q_liq" in self.fields else None))
         del self.pending[:count]
 
@@ -154,7 +156,8 @@ def run_KiD_simulation(FT, opts: dict | None = None, nc: int = 1, output: bool =
     if output:
         cond = OutputCadence(TS)
         if hasattr(h, "output_enqueue"):  # asynchronous, double-buffered download of the output fields
-            pipe = OutputPipeline(h, sink=lambda t, out: outputs.append((t, out)))
+            pipe = OutputPipeline(h)
+            outputs = pipe.results
             cb = lambda hh, t: pipe.enqueue(t)  # noqa: E731
             pipe.enqueue(0.0)
         else:
