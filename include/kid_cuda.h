@@ -111,7 +111,7 @@ typedef struct kid_config {
     int32_t local_activation;
     int32_t qtot_flux_correction;
     int32_t device;          /* CUDA device ordinal */
-    int32_t reserved[8];     /* reserved[0]: tuning override, max level chunks per column in a tile (0 = library default) */
+    int32_t reserved[8];     /* reserved[0..2]: tuning overrides (0 = library default): max level-warps per tile, columns per tile, 1 = never use the compile-time-shape kernel */
     double z_min, z_max;     /* make_function_space (K1DModel/ode_utils.jl:9-21) */
     double dt;               /* TimeStepping.dt (src/Common/ode_utils.jl:12-16) */
     double domain_width;     /* K2D aux.domain_width  */

@@ -191,6 +191,7 @@ KArgs<FT> make_args(kid_handle* h, double t0, int nsteps, int diag_mode, int fie
     a.C = h->C;
     a.NW = h->NW;
     a.diag_mode = diag_mode;
+    a.no_fixed_shape = h->cfg.reserved[2];
     a.nfields = (diag_mode == 2) ? h->diag_nfields : 0;
     for (int f = 0; f < a.nfields; ++f) a.fields[f] = h->diag_fields[f];
     a.field = field;
@@ -257,6 +258,7 @@ int choose_tile(kid_handle* h) {
     const int nz = h->cfg.nz, moist = h->cfg.moisture;
     const bool pcp = h->prm_sets != nullptr;
     int C = 32;
+    if (h->cfg.reserved[1] > 0) C = std::max(1, std::min(32, int(h->cfg.reserved[1])));  // tuning override
     while (C > 1) {
         size_t s = h->f64 ? h->lt->k1d_smem_d(moist, nz, C, pcp) : h->lt->k1d_smem_f(moist, nz, C, pcp);
         if (s <= size_t(max_smem)) break;

@@ -15,7 +15,7 @@ template <class FT, int MOIST, bool DIAG, class PRM>
 cudaError_t launch_tile_p(const KArgs<FT>& a, const DevParams<FT>& P, cudaStream_t s) {
     // the default KiD grid (128 levels, full tile) runs the instantiation with compile-time tile dimensions
     constexpr int FZ = 128;
-    const bool fixed = !DIAG && !PRM::per_column && a.nz == FZ && a.C == tile_fixed_columns<FT>() &&
+    const bool fixed = !DIAG && !PRM::per_column && !a.no_fixed_shape && a.nz == FZ && a.C == tile_fixed_columns<FT>() &&
                        a.NW == tile_max_threads<FT>() / tile_fixed_columns<FT>();
     auto kern = k1d_tile_kernel<FT, MOIST, KID_PRECIP, DIAG, PRM, 0>;
     if constexpr (!DIAG && !PRM::per_column) {

@@ -66,6 +66,7 @@ struct KArgs {
     int model;              // enum kid_model
     int nsteps;
     int C, NW;              // tile: columns per CTA, level chunks per column
+    int no_fixed_shape;     // tuning: never pick the compile-time-shape instantiation
     int diag_mode, field;   // 0 = step, 1 = rhs only, 2 = aux fields (fields[0..nfields) -> out[f][nz][ncp])
     int nfields;
     int fields[KID_NAUX];
@@ -267,6 +268,7 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
     const bool k1d = (A.model == KID_MODEL_K1D) || k2d;   // velocity, activation, condensation switched on
     const bool with_adv = (A.model == KID_MODEL_K1D || A.model == KID_MODEL_K1D_COL_SED) || k2d;
     const bool stale_Naer = (A.model == KID_MODEL_BOX || A.model == KID_MODEL_K1D_COL_SED) && A.aux_Naer != nullptr;
+    const FT* naer_p = stale_Naer ? A.aux_Naer + gc : nullptr;  // Box / col_sed: aux N_aer is a snapshot
     const FT dt = A.dt, dz = A.dz;
     const FT inv_dt = FT(1) / dt, inv_dz = FT(1) / dz;
     const int nstage_total = DIAG ? 1 : 3 * A.nsteps;
@@ -370,9 +372,14 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                 const int kc = is_bot ? 1 : (is_top ? nz - 2 : k);
                 // OLD values: this block and everything above it are still untouched; the two levels below the block
                 // were overwritten by the previous round and sit in the stash rows nz + 2·(r & 1) + {0: kb-1, 1: kb-2}
-                auto row = [&](int kk) { return (kk >= kb) ? kk : nz + 2 * (r & 1) + (kb - 1 - kk); };
-                const FT* c_p = Ys + row(kc) * C + c;      // + variable · sV
-                const FT* l_p = Ys + row(kc - 1) * C + c;
+                int row_c = k, row_l = k - 1;
+                if (j < 2 || is_top) {  // warp-uniform: the block's first warps (stash below) and the boundary cells
+                    auto row = [&](int kk) { return (kk >= kb) ? kk : nz + 2 * (r & 1) + (kb - 1 - kk); };
+                    row_c = row(kc);
+                    row_l = row(kc - 1);
+                }
+                const FT* c_p = Ys + row_c * C + c;      // + variable · sV
+                const FT* l_p = Ys + row_l * C + c;
                 const FT* u_p = Ys + (kc + 1) * C + c;
                 // face velocities (air, air - vt1, air - vt2) of faces kc (lower) and kc+1 (upper), pre-multiplied:
                 // wh = w / (2 dz) for the centred flux, aw = fcc_scale |w| / dz for the first-order correction
@@ -451,7 +458,7 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                 Point<FT> a;
                 const size_t ppi = A.prof_per_column ? size_t(k) * ncp + gc : size_t(k);
                 thermo_point<FT, MOIST, PRECIP>(P, y, rds[kidx(k)], Ts[kidx(k)], A.ps_liq[ppi], A.ps_mix[ppi], a);
-                if (stale_Naer) a.N_aer = A.aux_Naer[size_t(k) * ncp + gc];
+                if (naer_p) a.N_aer = naer_p[size_t(k) * ncp];
                 FT act_Nl = FT(0);
                 if constexpr (L::is2m) {
                     if (k1d) act_Nl = (A.sw.local_activation || k == cbk) ? acts[kidx(k)] : FT(0);

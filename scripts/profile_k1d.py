@@ -18,6 +18,8 @@ ap.add_argument("--ft", default="f32")
 ap.add_argument("--moisture", default="NonEquilibriumMoisture")
 ap.add_argument("--precip", default="Precipitation2M")
 ap.add_argument("--nw", type=int, default=0)
+ap.add_argument("--tile-c", type=int, default=0)
+ap.add_argument("--no-fixed", type=int, default=0)
 ap.add_argument("--order", default="hash", choices=["hash", "sorted", "uniform"])
 a = ap.parse_args()
 FT = np.float32 if a.ft == "f32" else np.float64
@@ -27,6 +29,8 @@ else:
     cs = M.k1d_ensemble_case(FT, nc=a.columns, n_profiles=16, n_elem=a.nz, moisture_choice=a.moisture, precipitation_choice=a.precip,
                              order=a.order)
 if a.nw: cs.cfg.reserved[0] = a.nw
+if a.tile_c: cs.cfg.reserved[1] = a.tile_c
+if a.no_fixed: cs.cfg.reserved[2] = 1
 h = M.make_handle(cs, Handle)
 h.step(0.0, a.t_start); h.synchronize()
 t = float(a.t_start)
