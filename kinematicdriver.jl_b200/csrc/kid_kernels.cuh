@@ -364,6 +364,21 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
             FT adv[NADV];
 #pragma unroll
             for (int i = 0; i < NADV; ++i) adv[i] = FT(0);
+            // u^n of the stage combine and the grid-point constants come from global memory / L2: issue the loads now,
+            // the whole READ phase and the barrier hide their latency
+            FT un[DIAG ? 1 : NV], ps_l = FT(0), ps_m = FT(0);
+            if (valid) {
+                if constexpr (!DIAG) {
+                    if (stage != 0) {
+                        const FT* gU = A.Y + size_t(k) * ncp + gc;
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) un[v] = gU[v * plane];
+                    }
+                }
+                const size_t ppi = A.prof_per_column ? size_t(k) * ncp + gc : size_t(k);
+                ps_l = A.ps_liq[ppi];
+                ps_m = A.ps_mix[ppi];
+            }
             if (valid && with_adv) {
                 // The boundary cells take the stencil of their inner neighbour (Extrapolate: the tendency of cell 0 is
                 // that of cell 1, of cell nz-1 that of cell nz-2; the flux correction always extrapolates), so every
@@ -456,8 +471,7 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
 #pragma unroll
                 for (int v = 0; v < NV; ++v) y[v] = Ys[sidx(v, k)];
                 Point<FT> a;
-                const size_t ppi = A.prof_per_column ? size_t(k) * ncp + gc : size_t(k);
-                thermo_point<FT, MOIST, PRECIP>(P, y, rds[kidx(k)], Ts[kidx(k)], A.ps_liq[ppi], A.ps_mix[ppi], a);
+                thermo_point<FT, MOIST, PRECIP>(P, y, rds[kidx(k)], Ts[kidx(k)], ps_l, ps_m, a);
                 if (naer_p) a.N_aer = naer_p[size_t(k) * ncp];
                 FT act_Nl = FT(0);
                 if constexpr (L::is2m) {
@@ -500,7 +514,7 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                     FT* gY = A.Y + size_t(k) * ncp + gc;
 #pragma unroll
                     for (int v = 0; v < NV; ++v) {
-                        const FT u = (stage == 0) ? y[v] : gY[v * plane];
+                        const FT u = (stage == 0) ? y[v] : un[v];
                         const FT yn = rk_a * u + (rk_b * y[v] + rk_c * tend[v]);
                         Ys[sidx(v, k)] = yn;
                         if (stage == 2) gY[v * plane] = yn;
