@@ -13,3 +13,4 @@ import json;d=json.load(open('gpurun_out/$f.json'));print('$f', d.get('value'), 
 timeout 600 python bench.py --steps 20 --warmup 3 --cpu-seconds 0 > gpurun_out/bench_short.json 2>> gpurun_out/bench.err && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 20 --warmup 3 --cpu-seconds 0 > gpurun_out/ncu_launches.log 2>&1
 tail -1 gpurun_out/ncu_launches.log | cut -c1-300
+timeout 900 python scripts/bench_configs.py > gpurun_out/configs.json 2> gpurun_out/configs.err; echo rc=$?; tail -2 gpurun_out/configs.err; head -c 1500 gpurun_out/configs.json
