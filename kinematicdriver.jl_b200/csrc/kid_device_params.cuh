@@ -36,7 +36,10 @@ constexpr int KID_GSER_TERMS = 26;
     X(sb_sc_pref)      /* kcc(ν+2)/(ν+1)                                          */ \
     X(arg_lns) X(arg_f) X(arg_gg) X(arg_Sm_pref) /* ARG2000 mode constants        */ \
     X(rain_r0_pow) X(snow_r0_pow) X(ice_r0_pow) /* r0^(me+Δm)                     */ \
-    X(rain_li_exp) X(snow_li_exp) X(ice_li_exp) /* 1/(me+Δm+1)                    */
+    X(rain_li_exp) X(snow_li_exp) X(ice_li_exp) /* 1/(me+Δm+1)                    */ \
+    /* reciprocals of parameters that only ever divide (one FMUL instead of rcp + mul per grid point) */ \
+    X(inv_tau_relax_liq) X(inv_tau_relax_ice) X(inv_sb_x_star) X(inv_sb_numadj_tau)    \
+    X(inv_sb_xc_max) X(inv_sb_xc_min) X(inv_sb_xr_max) X(inv_sb_xr_min)
 
 template <class FT>
 struct DevParamsBody {
@@ -102,6 +105,14 @@ inline void fill_dev_params(DevParams<FT>& P, const double* table) {
     P.rain_li_exp = FT(1) / (P.rain_me + P.rain_dm + FT(1));
     P.snow_li_exp = FT(1) / (P.snow_me + P.snow_dm + FT(1));
     P.ice_li_exp = FT(1) / (P.ice_me + P.ice_dm + FT(1));
+    P.inv_tau_relax_liq = FT(1) / P.ne_tau_relax_liq;
+    P.inv_tau_relax_ice = FT(1) / P.ne_tau_relax_ice;
+    P.inv_sb_x_star = FT(1) / P.sb_x_star;
+    P.inv_sb_numadj_tau = FT(1) / P.sb_numadj_tau;
+    P.inv_sb_xc_max = FT(1) / P.sb_xc_max;
+    P.inv_sb_xc_min = FT(1) / P.sb_xc_min;
+    P.inv_sb_xr_max = FT(1) / P.sb_xr_max;
+    P.inv_sb_xr_min = FT(1) / P.sb_xr_min;
     {
         double sgam = double(FT(-0.5) + FT(1.5) * P.sb_beta + FT(1)), d = 1.0;
         for (int n = 0; n < KID_GSER_TERMS; ++n) { d /= (sgam + n); P.sb_gser[n] = FT(d); }
