@@ -69,6 +69,7 @@ struct kid_handle {
     int C = 32, NW = 1;
     // K2D
     void *U = nullptr, *S = nullptr, *prev_aux = nullptr, *xc = nullptr, *out2 = nullptr;
+    double* zsin = nullptr;
     void *send_left = nullptr, *send_right = nullptr, *recv_left = nullptr, *recv_right = nullptr;
     int Nq = 0, nfields = 0;
     K2DField fields[KID_MAX_DSS];
@@ -200,6 +201,7 @@ KArgs<FT> make_args(kid_handle* h, double t0, int nsteps, int diag_mode, int fie
     a.t0 = t0;
     a.sw = h->sw;
     a.xc = (const FT*)h->xc;
+    a.zsin = h->zsin;
     a.prev_aux = (FT*)h->prev_aux;
     a.outS = (FT*)h->S;
     a.update_prev = 0;
@@ -368,6 +370,12 @@ int k2d_setup(kid_handle* h) {
         std::vector<float> xf(x.begin(), x.end());
         KID_CUDA(cudaMemcpyAsync(h->xc, xf.data(), size_t(h->ncp) * 4, cudaMemcpyHostToDevice, h->stream));
     }
+    // vertical factor of the stream function at the faces (src/K2DModel/tendency.jl:4-9): sin(π z_f / H)
+    std::vector<double> zs(c.nz + 1);
+    const double dz = (c.z_max - c.z_min) / c.nz;
+    for (int k = 0; k <= c.nz; ++k) zs[k] = std::sin(M_PI / c.domain_height * (c.z_min + double(h->f64 ? dz : double(float(dz))) * k));
+    KID_CUDA(cudaMalloc(&h->zsin, zs.size() * sizeof(double)));
+    KID_CUDA(cudaMemcpyAsync(h->zsin, zs.data(), zs.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     KID_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -473,6 +481,7 @@ void kid_destroy(kid_handle_t* h) {
     if (h) {
         if (h->obsG) cudaFree(h->obsG);
         if (h->red) cudaFree(h->red);
+        if (h->zsin) cudaFree(h->zsin);
         if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
         for (int b = 0; b < 2; ++b) {
             if (h->ostage[b]) cudaFree(h->ostage[b]);

@@ -77,6 +77,7 @@ struct KArgs {
     // activation reads before precompute_aux_precip! refreshes them, separate output of the precipitation
     // advection fields S1/S2 (they are DSS'd on their own before being added to ρq_tot)
     const FT* xc;           // [ncp]
+    const double* zsin;     // [nz + 1] sin(π z_face / H): the vertical factor of the stream function per face
     FT* prev_aux;           // [3][nz][ncp]
     FT* outS;               // [2][nz][ncp]
     int update_prev;
@@ -291,21 +292,46 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                                       : 0.0;
         auto rwf = [&](int kface) -> FT {  // ρw at face kface (between cells kface-1 and kface)
             if (!k2d) return rw;
-            return FT(wxd * sin(M_PI / A.height * (A.z_min + double(dz) * kface)));
+            return FT(wxd * A.zsin[kface]);
         };
 
         // ---- pass 1 (pointwise): terminal velocities and activation rate of this thread's levels
         if constexpr (L::has_pr) {
             if (active) {
                 int first = INT_MAX;
+                // Single-evaluation (DIAG) launches — every K2D stage is one — are bound by the latency of the global
+                // loads in this loop, not by issue slots: they request the NEXT level's values before evaluating this
+                // one.  (The fused step kernel is issue-bound; there the extra registers cost more than they hide.)
+                FT nx_ps_l = FT(0), nx_ps_m = FT(0), nx_prev[3] = {FT(0), FT(0), FT(0)};
+                auto fetch = [&](int kk) {
+                    const size_t ppi = A.prof_per_column ? size_t(kk) * ncp + gc : size_t(kk);
+                    nx_ps_l = A.ps_liq[ppi];
+                    nx_ps_m = A.ps_mix[ppi];
+                    if constexpr (L::is2m) {
+                        if (k2d) {
+                            const size_t pi = size_t(kk) * ncp + gc;
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) nx_prev[q] = A.prev_aux[q * plane + pi];
+                        }
+                    }
+                };
+                if constexpr (DIAG) { if (j < nz) fetch(j); }
 #pragma unroll 1
                 for (int k = j; k < nz; k += NW) {
                     FT y[NV];
 #pragma unroll
                     for (int v = 0; v < NV; ++v) y[v] = Ys[sidx(v, k)];
                     Point<FT> a;
-                    const size_t ppi = A.prof_per_column ? size_t(k) * ncp + gc : size_t(k);
-                    thermo_point<FT, MOIST, PRECIP>(P, y, rds[kidx(k)], Ts[kidx(k)], A.ps_liq[ppi], A.ps_mix[ppi], a);
+                    FT prev0 = FT(0), prev1 = FT(0), prev2 = FT(0);
+                    if constexpr (DIAG) {
+                        const FT ps_l = nx_ps_l, ps_m = nx_ps_m;
+                        prev0 = nx_prev[0]; prev1 = nx_prev[1]; prev2 = nx_prev[2];
+                        if (k + NW < nz) fetch(k + NW);
+                        thermo_point<FT, MOIST, PRECIP>(P, y, rds[kidx(k)], Ts[kidx(k)], ps_l, ps_m, a);
+                    } else {
+                        const size_t ppi = A.prof_per_column ? size_t(k) * ncp + gc : size_t(k);
+                        thermo_point<FT, MOIST, PRECIP>(P, y, rds[kidx(k)], Ts[kidx(k)], A.ps_liq[ppi], A.ps_mix[ppi], a);
+                    }
                     FT v1, v2;
                     terminal_velocities<FT, PRECIP>(P, A.sw, a, v1, v2);
                     vt1s[kidx(k)] = v1;
@@ -317,9 +343,9 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                             // K2D calls activation BEFORE precompute_aux_precip! (K2DModel/ode_utils.jl:43-44): it
                             // sees the q_rai, N_liq, N_rai the previous rhs! call left in aux
                             const size_t pi = size_t(k) * ncp + gc;
-                            q_rai_act = A.prev_aux[pi];
-                            N_liq_act = A.prev_aux[plane + pi];
-                            N_rai_act = A.prev_aux[2 * plane + pi];
+                            q_rai_act = prev0;
+                            N_liq_act = prev1;
+                            N_rai_act = prev2;
                             if (A.update_prev) {
                                 A.prev_aux[pi] = a.q_rai;
                                 A.prev_aux[plane + pi] = a.N_liq;
