@@ -69,7 +69,7 @@ struct kid_handle {
     int C = 32, NW = 1;
     // K2D
     void *U = nullptr, *S = nullptr, *prev_aux = nullptr, *xc = nullptr, *out2 = nullptr;
-    double* zsin = nullptr;
+    double *zsin = nullptr, *cosx = nullptr, *cosz = nullptr;
     void *send_left = nullptr, *send_right = nullptr, *recv_left = nullptr, *recv_right = nullptr;
     int Nq = 0, nfields = 0;
     K2DField fields[KID_MAX_DSS];
@@ -225,6 +225,8 @@ K2DArgs<FT> make_k2d_args(kid_handle* h, double t_stage, int stage, int use_recv
     a.i_tot = h->i_tot; a.i_rai = h->i_rai; a.i_sno = h->i_sno; a.precip = h->cfg.precip;
     a.stage = stage; a.use_recv = use_recv; a.rhs_only = rhs_only;
     a.dt = FT(h->cfg.dt); a.t = FT(t_stage); a.t1 = FT(h->params[KID_P_kid_t1]);
+    a.cosx = h->cosx; a.cosz = h->cosz;
+    a.ts = (a.t < a.t1) ? std::sin(M_PI * double(a.t) / double(a.t1)) : 0.0;
     a.z_min = FT(h->cfg.z_min); a.dz = FT((h->cfg.z_max - h->cfg.z_min) / h->cfg.nz);
     a.width = h->cfg.domain_width; a.height = h->cfg.domain_height;
     a.dxe = h->cfg.domain_width / h->cfg.helem_global;
@@ -374,6 +376,16 @@ int k2d_setup(kid_handle* h) {
     std::vector<double> zs(c.nz + 1);
     const double dz = (c.z_max - c.z_min) / c.nz;
     for (int k = 0; k <= c.nz; ++k) zs[k] = std::sin(M_PI / c.domain_height * (c.z_min + double(h->f64 ? dz : double(float(dz))) * k));
+    // factors of ρu at the cell centres / nodes: cos(π z_c / H), cos(2π x_c / W) with x_c as the kernels see it (FT)
+    std::vector<double> cz(c.nz), cx(h->ncp, 0.0);
+    const double dzf = h->f64 ? dz : double(float(dz));
+    const double zmin_f = h->f64 ? c.z_min : double(float(c.z_min));
+    for (int k = 0; k < c.nz; ++k) cz[k] = std::cos(M_PI / c.domain_height * (zmin_f + (k + 0.5) * dzf));
+    for (int i = 0; i < h->ncp; ++i) cx[i] = std::cos(2.0 * M_PI / c.domain_width * (h->f64 ? x[i] : double(float(x[i]))));
+    KID_CUDA(cudaMalloc(&h->cosz, cz.size() * sizeof(double)));
+    KID_CUDA(cudaMalloc(&h->cosx, cx.size() * sizeof(double)));
+    KID_CUDA(cudaMemcpyAsync(h->cosz, cz.data(), cz.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    KID_CUDA(cudaMemcpyAsync(h->cosx, cx.data(), cx.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     KID_CUDA(cudaMalloc(&h->zsin, zs.size() * sizeof(double)));
     KID_CUDA(cudaMemcpyAsync(h->zsin, zs.data(), zs.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     KID_CUDA(cudaStreamSynchronize(h->stream));
@@ -482,6 +494,8 @@ void kid_destroy(kid_handle_t* h) {
         if (h->obsG) cudaFree(h->obsG);
         if (h->red) cudaFree(h->red);
         if (h->zsin) cudaFree(h->zsin);
+        if (h->cosx) cudaFree(h->cosx);
+        if (h->cosz) cudaFree(h->cosz);
         if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
         for (int b = 0; b < 2; ++b) {
             if (h->ostage[b]) cudaFree(h->ostage[b]);

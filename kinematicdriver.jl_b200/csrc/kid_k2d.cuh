@@ -33,6 +33,9 @@ struct K2DArgs {
     const FT* rho_dry;
     const FT* w1;   // [ncp]
     const FT* xc;   // [ncp]
+    const double* cosx;  // [ncp]    cos(2π x_c / W)      horizontal factor of ρu (src/K2DModel/tendency.jl:4-9)
+    const double* cosz;  // [nz]     cos(π z_center / H)  vertical factor of ρu
+    double ts;           // sin(π t / t1) for t < t1, else 0
     FT* send_left; FT* send_right;              // [nfields][nz]
     const FT* recv_left; const FT* recv_right;  // [nfields][nz]
     int nz, nc, ncp, nv, helem, Nq, prof_per_column;
@@ -46,8 +49,10 @@ struct K2DArgs {
     FT w[KID_MAX_NQ];               // GLL weights
 };
 
-// one thread per (element, level): weak divergence of every horizontally advected field, then pack the
-// rank-edge nodes for the neighbour exchange
+// one thread per (element, level): weak divergence of every horizontally advected field at the element's Nq nodes,
+// then pack the rank-edge nodes for the neighbour exchange.  ρu = ½ w1 (W/H) cos(πz/H) cos(2πx/W) ts is evaluated in
+// double from host-built factor tables and rounded like the reference's map.  (A thread-per-node variant with warp
+// shuffles was measured slower: 45 vs 34 µs — the element-local loop keeps the fluxes in registers.)
 template <class FT>
 __global__ void k2d_hdiv_kernel(const K2DArgs<FT> A) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -56,25 +61,25 @@ __global__ void k2d_hdiv_kernel(const K2DArgs<FT> A) {
     const int Nq = A.Nq;
     const size_t plane = size_t(A.nz) * A.ncp;
     const size_t row = size_t(k) * A.ncp;
-    FT rho[KID_MAX_NQ], rho_u[KID_MAX_NQ];
-    const double zc = double(A.z_min) + (k + 0.5) * double(A.dz);
+    FT u_over_rho[KID_MAX_NQ];
+    const double czk = A.cosz[k];
     for (int j = 0; j < Nq; ++j) {
         const int c = e * Nq + j;
         const FT rd = A.rho_dry[A.prof_per_column ? row + c : size_t(k)];
-        rho[j] = rd + A.Y[size_t(A.i_tot) * plane + row + c];
-        const double ts = (A.t < A.t1) ? sin(M_PI * double(A.t) / double(A.t1)) : 0.0;
-        rho_u[j] = FT(0.5 * double(A.w1[c]) * A.width / A.height * cos(M_PI / A.height * zc) *
-                      cos(2.0 * M_PI / A.width * double(A.xc[c])) * ts);
+        const FT rho = rd + A.Y[size_t(A.i_tot) * plane + row + c];
+        const FT rho_u = FT(0.5 * double(A.w1[c]) * A.width / A.height * czk * A.cosx[c] * A.ts);
+        u_over_rho[j] = rho_u / rho;
     }
+    const FT scale = FT(2) / FT(A.dxe);
     for (int f = 0; f < A.nfields; ++f) {
         const K2DField fd = A.fields[f];
-        FT flux[KID_MAX_NQ];
-        for (int j = 0; j < Nq; ++j) flux[j] = rho_u[j] / rho[j] * A.Y[size_t(fd.adv_var) * plane + row + e * Nq + j];
+        FT wflux[KID_MAX_NQ];
+        for (int j = 0; j < Nq; ++j) wflux[j] = A.w[j] * (u_over_rho[j] * A.Y[size_t(fd.adv_var) * plane + row + e * Nq + j]);
         FT* tgt = (fd.is_S ? A.S : A.dY) + size_t(fd.plane) * plane + row;
         for (int i = 0; i < Nq; ++i) {
             FT acc = FT(0);
-            for (int j = 0; j < Nq; ++j) acc += A.D[j * Nq + i] * (A.w[j] * flux[j]);
-            const FT hd = -acc / A.w[i] * (FT(2) / FT(A.dxe));
+            for (int j = 0; j < Nq; ++j) acc += A.D[j * Nq + i] * wflux[j];
+            const FT hd = -acc / A.w[i] * scale;
             tgt[e * Nq + i] += -hd;
         }
         if (e == 0) A.send_left[size_t(f) * A.nz + k] = tgt[0];
@@ -91,34 +96,68 @@ __global__ void k2d_dss_update_kernel(const K2DArgs<FT> A) {
     const int Nq = A.Nq, e = c / Nq, i = c % Nq;
     const size_t plane = size_t(A.nz) * A.ncp;
     const size_t row = size_t(k) * A.ncp;
-    FT Sval[2] = {FT(0), FT(0)};
-    FT dss_dY[KID_MAX_DSS];
-    for (int f = 0; f < A.nfields; ++f) {
-        const K2DField fd = A.fields[f];
-        const FT* src = (fd.is_S ? A.S : A.dY) + size_t(fd.plane) * plane + row;
-        FT v = src[c];
-        if (i == 0 || i == Nq - 1) {
-            // weighted_dss!: the duplicated node of two neighbouring elements gets the average of both copies
-            // (uniform mesh: equal weights).  Periodic in x; across a rank boundary the partner value was received.
-            FT partner;
-            if (i == 0) {
-                if (e > 0) partner = src[(e - 1) * Nq + Nq - 1];
-                else partner = A.use_recv ? A.recv_left[size_t(f) * A.nz + k] : src[(A.helem - 1) * Nq + Nq - 1];
-                v = (partner + v) / FT(2);
-            } else {
-                if (e < A.helem - 1) partner = src[(e + 1) * Nq];
-                else partner = A.use_recv ? A.recv_right[size_t(f) * A.nz + k] : src[0];
-                v = (v + partner) / FT(2);
+    constexpr int MAXV = 8;  // largest state (NonEq + 2M)
+    // ---- all global loads first: they are independent, so their latencies overlap
+    // weighted_dss!: the duplicated node of two neighbouring elements gets the average of both copies (uniform mesh:
+    // equal weights).  Periodic in x; across a rank boundary the partner value was received.
+    const bool left_edge = (i == 0), right_edge = (i == Nq - 1);
+    int partner_col = -1;  // column of the duplicate node inside this rank, or -1: none / received
+    bool from_recv = false;
+    if (left_edge) {
+        if (e > 0) partner_col = (e - 1) * Nq + Nq - 1;
+        else if (A.use_recv) from_recv = true;
+        else partner_col = (A.helem - 1) * Nq + Nq - 1;
+    } else if (right_edge) {
+        if (e < A.helem - 1) partner_col = (e + 1) * Nq;
+        else if (A.use_recv) from_recv = true;
+        else partner_col = 0;
+    }
+    FT own[KID_MAX_DSS], par[KID_MAX_DSS];
+#pragma unroll
+    for (int f = 0; f < KID_MAX_DSS; ++f) {
+        own[f] = par[f] = FT(0);
+        if (f < A.nfields) {
+            const K2DField fd = A.fields[f];
+            const FT* src = (fd.is_S ? A.S : A.dY) + size_t(fd.plane) * plane + row;
+            own[f] = src[c];
+            if (partner_col >= 0) par[f] = src[partner_col];
+            else if (from_recv) par[f] = (left_edge ? A.recv_left : A.recv_right)[size_t(f) * A.nz + k];
+        }
+    }
+    FT dy[MAXV], yv[MAXV], uv[MAXV];
+#pragma unroll
+    for (int var = 0; var < MAXV; ++var) {
+        dy[var] = yv[var] = uv[var] = FT(0);
+        if (var < A.nv) {
+            const size_t gi = size_t(var) * plane + row + c;
+            dy[var] = A.dY[gi];
+            if (!A.rhs_only) {
+                yv[var] = A.Y[gi];
+                if (A.stage != 0) uv[var] = A.U[gi];
             }
         }
-        if (fd.is_S) Sval[fd.plane] = v;
-        dss_dY[f] = v;
     }
-    for (int var = 0; var < A.nv; ++var) {
+    // ---- DSS
+    FT Sval[2] = {FT(0), FT(0)};
+#pragma unroll
+    for (int f = 0; f < KID_MAX_DSS; ++f) {
+        if (f < A.nfields) {
+            FT v = own[f];
+            if (left_edge && (partner_col >= 0 || from_recv)) v = (par[f] + v) / FT(2);
+            else if (right_edge && (partner_col >= 0 || from_recv)) v = (v + par[f]) / FT(2);
+            own[f] = v;
+            if (A.fields[f].is_S) { if (A.fields[f].plane == 0) Sval[0] = v; else Sval[1] = v; }
+        }
+    }
+    // ---- assemble the tendencies in the reference's order, SSPRK33 stage combine
+#pragma unroll
+    for (int var = 0; var < MAXV; ++var) {
+        if (var >= A.nv) break;
         const size_t gi = size_t(var) * plane + row + c;
-        FT tend = A.dY[gi];
-        for (int f = 0; f < A.nfields; ++f)
-            if (!A.fields[f].is_S && A.fields[f].plane == var) tend = dss_dY[f];
+        FT tend = dy[var];
+#pragma unroll
+        for (int f = 0; f < KID_MAX_DSS; ++f)
+            if (f < A.nfields && !A.fields[f].is_S && A.fields[f].plane == var) tend = own[f];
         if (A.precip == KID_PRECIP_1M) {
             if (var == A.i_tot) tend += Sval[0] + Sval[1];
             if (var == A.i_rai) tend += Sval[0];
@@ -128,8 +167,8 @@ __global__ void k2d_dss_update_kernel(const K2DArgs<FT> A) {
             if (var == A.i_rai) tend += Sval[0];
         }
         if (A.rhs_only) { A.out[gi] = tend; continue; }
-        const FT y = A.Y[gi];
-        FT u = (A.stage == 0) ? y : A.U[gi];
+        const FT y = yv[var];
+        const FT u = (A.stage == 0) ? y : uv[var];
         if (A.stage == 0) A.U[gi] = y;
         FT yn;
         if (A.stage == 0) yn = y + A.dt * tend;
