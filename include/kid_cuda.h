@@ -158,6 +158,17 @@ int kid_get_state(kid_handle_t* h, void* Y);
 int kid_set_state_async(kid_handle_t* h, const void* Y_pinned);
 int kid_get_state_async(kid_handle_t* h, void* Y_pinned);
 
+/* replaces: ρ_ivp + initial_condition_1d + initialise_state and the ρ_dry, T, q_surf fields of initialise_aux
+ * (src/Common/initial_condition.jl:50-231, src/Common/ode_utils.jl:23-54, src/K1DModel/ode_utils.jl:80-117) for the
+ * ShipwayHill2012 sounding: the hydrostatic profile and the initial state of every column are built ON the device from
+ * sounding = {z_0, z_1, z_2, rv_0, rv_1, rv_2, tht_0, tht_1, tht_2} and one surface pressure per column
+ * (p0: nc FLOAT_TYPE values, NULL = the drivers' default 100000 Pa), so each ensemble member can have its own p0 without a host ODE
+ * solve.  Needs kid_set_params (and kid_set_column_scalar(PRESCRIBED_ND) if members differ in Nd) first; afterwards
+ * the handle is ready to step (profiles, q_surf and state are set).  K1DModel handles only. */
+int kid_init_shipway_hill(kid_handle_t* h, const double* sounding, const void* p0, int32_t dry);
+/* download the time-invariant profiles (the layout kid_set_profiles takes: nc x nz, or nz if one profile is shared) */
+int kid_get_profiles(kid_handle_t* h, void* rho_dry, void* T);
+
 /* replaces: ODE.solve!(integrator) between two save/callback times: advances
  * the device-resident state by nsteps SSPRK33 steps of size dt starting at
  * time t0 (3 rhs evaluations per step).  Asynchronous w.r.t. the host. */

@@ -10,6 +10,7 @@
 
 #include "kid_k2d.cuh"
 #include "kid_launch.h"
+#include "kid_init.cuh"
 
 using namespace kid;
 
@@ -763,6 +764,75 @@ int kid_output_enqueue(kid_handle_t* h, double t, int32_t nfields, const int32_t
     KID_CUDA(cudaMemcpyAsync(out_pinned, h->ostage[b], bytes, cudaMemcpyDeviceToHost, h->copy_stream));
     KID_CUDA(cudaEventRecord(h->ev_done[b], h->copy_stream));
     h->ev_used[b] = true;
+    return 0;
+}
+
+int kid_init_shipway_hill(kid_handle_t* h, const double* sounding, const void* p0, int32_t dry) {
+    if (!h || !sounding) return fail("null argument");
+    if (!h->params_set) return fail("kid_set_params must be called before kid_init_shipway_hill");
+    if (h->cfg.model != KID_MODEL_K1D && h->cfg.model != KID_MODEL_K1D_COL_SED)
+        return fail("kid_init_shipway_hill: K1DModel handles only");
+    const int nz = h->cfg.nz, nc = h->cfg.nc;
+    const size_t n = size_t(nz) * h->ncp;
+    for (void** p : {&h->rho_dry, &h->T, &h->ps_liq, &h->ps_mix}) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+        KID_CUDA(cudaMalloc(p, n * h->fsz));
+        KID_CUDA(cudaMemsetAsync(*p, 0, n * h->fsz, h->stream));
+    }
+    h->prof_per_column = 1;
+    h->consts_dirty = true;
+    void* p0_dev = nullptr;
+    KID_CUDA(cudaMalloc(&p0_dev, size_t(h->ncp) * h->fsz));
+    if (upload_columns(h, p0_dev, p0, 100000.0)) { cudaFree(p0_dev); return 1; }
+    KID_CUDA(cudaMemsetAsync(h->Y, 0, state_elems(h) * h->fsz, h->stream));
+    auto fill = [&](auto& a) {
+        a.z_0 = sounding[0]; a.z_1 = sounding[1]; a.z_2 = sounding[2];
+        a.rv_0 = sounding[3]; a.rv_1 = sounding[4]; a.rv_2 = sounding[5];
+        a.th_0 = sounding[6]; a.th_1 = sounding[7]; a.th_2 = sounding[8];
+        a.R_d = h->params[KID_P_td_R_d]; a.R_v = h->params[KID_P_td_R_v]; a.cp_d = h->params[KID_P_td_cp_d];
+        a.cp_v = h->params[KID_P_td_cp_v]; a.grav = h->params[KID_P_td_grav]; a.MSLP = h->params[KID_P_td_MSLP];
+        a.z_min = h->cfg.z_min; a.dz = (h->cfg.z_max - h->cfg.z_min) / nz;
+        a.nz = nz; a.nc = nc; a.ncp = h->ncp; a.nv = h->nv; a.nsub = 4; a.dry = dry;
+        a.i_tot = 0; a.i_Na = na_index(h->cfg.moisture, h->cfg.precip);
+    };
+    if (!(sounding[2] >= h->cfg.z_max)) { cudaFree(p0_dev); return fail("z_max cannot be higher than z_2"); }
+    if (h->f64) {
+        ICArgs<double> a{}; fill(a);
+        a.p0 = (const double*)p0_dev; a.Nd = (const double*)h->Nd; a.rho_dry = (double*)h->rho_dry; a.T = (double*)h->T;
+        a.Y = (double*)h->Y; a.q_surf = (double*)h->q_surf;
+        init_shipway_hill_kernel<double><<<(nc + 63) / 64, 64, 0, h->stream>>>(a);
+    } else {
+        ICArgs<float> a{}; fill(a);
+        a.p0 = (const float*)p0_dev; a.Nd = (const float*)h->Nd; a.rho_dry = (float*)h->rho_dry; a.T = (float*)h->T;
+        a.Y = (float*)h->Y; a.q_surf = (float*)h->q_surf;
+        init_shipway_hill_kernel<float><<<(nc + 63) / 64, 64, 0, h->stream>>>(a);
+    }
+    KID_CUDA(cudaGetLastError());
+    h->launches++;
+    const int na = na_index(h->cfg.moisture, h->cfg.precip);
+    if (na >= 0 && h->cfg.model == KID_MODEL_K1D_COL_SED) {  // aux N_aer snapshot, as in kid_set_state
+        const size_t plane = n * h->fsz;
+        if (!h->aux_Naer) KID_CUDA(cudaMalloc(&h->aux_Naer, plane));
+        KID_CUDA(cudaMemcpyAsync(h->aux_Naer, (const char*)h->Y + size_t(na) * plane, plane, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    KID_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(p0_dev);
+    h->profiles_set = true;
+    h->state_set = true;
+    return 0;
+}
+
+int kid_get_profiles(kid_handle_t* h, void* rho_dry, void* T) {
+    if (!h || !rho_dry || !T) return fail("null argument");
+    if (!h->profiles_set) return fail("no profiles on the device yet");
+    if (h->prof_per_column) {
+        if (to_host_layout(h, h->rho_dry, rho_dry, 1)) return 1;
+        return to_host_layout(h, h->T, T, 1);
+    }
+    KID_CUDA(cudaMemcpyAsync(rho_dry, h->rho_dry, size_t(h->cfg.nz) * h->fsz, cudaMemcpyDeviceToHost, h->stream));
+    KID_CUDA(cudaMemcpyAsync(T, h->T, size_t(h->cfg.nz) * h->fsz, cudaMemcpyDeviceToHost, h->stream));
+    KID_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

@@ -1,0 +1,126 @@
+// Initial condition on the device (sm_100a): the ShipwayHill2012 sounding, the hydrostatic density profile and the
+// per-level initial state of the 1-D rainshaft, one thread per column, so that every ensemble member / calibration case
+// can carry its own surface pressure p0 without a host ODE solve per member.
+//
+// Replaces (reference): init_profile (src/Common/initial_condition.jl:50-84), dρ_dz + ρ_ivp (:100-149, a Tsit5 solve whose
+// dense output is sampled at the cell centres), initial_condition_1d (:155-231), the PySDM helpers
+// (src/Common/pysdm_functions.jl:8-63) and initialise_state / the ρ_dry, T, q_surf fields of initialise_aux
+// (src/Common/ode_utils.jl:23-54, src/K1DModel/ode_utils.jl:80-117).
+// The IVP is integrated in double with classical RK4 from z_0 straight to the cell centres (`nsub` substeps per level,
+// steps split at the sounding's kink z_1); at Δz/4 ≈ 4 m the result agrees with the adaptive solve to ~1e-11.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace kid {
+
+template <class FT>
+struct ICArgs {
+    // sounding (kid_params z_0..2, rv_0..2, tht_0..2) and thermodynamic constants
+    double z_0, z_1, z_2, rv_0, rv_1, rv_2, th_0, th_1, th_2;
+    double R_d, R_v, cp_d, cp_v, grav, MSLP;
+    double z_min, dz;
+    int nz, nc, ncp, nv, nsub, dry;
+    int i_tot, i_Na;      // state indices (i_Na < 0: no N_aer)
+    const FT* p0;         // [ncp] surface pressure per column
+    const FT* Nd;         // [ncp] prescribed_Nd per column
+    FT* rho_dry;          // [nz][ncp]
+    FT* T;                // [nz][ncp]
+    FT* Y;                // [nv][nz][ncp] (zero-filled by the caller)
+    FT* q_surf;           // [ncp]
+};
+
+template <class FT>
+struct ICProfile {
+    const ICArgs<FT>& A;
+    __device__ explicit ICProfile(const ICArgs<FT>& a) : A(a) {}
+    __device__ void sounding(double z, double& qv, double& th) const {
+        const double rv0 = A.dry ? 0.0 : A.rv_0, rv1 = A.dry ? 0.0 : A.rv_1, rv2 = A.dry ? 0.0 : A.rv_2;
+        const double rv = z < A.z_1 ? rv0 + (rv1 - rv0) / (A.z_1 - A.z_0) * (z - A.z_0) : rv1 + (rv2 - rv1) / (A.z_2 - A.z_1) * (z - A.z_1);
+        qv = rv / (1.0 + rv);
+        th = z < A.z_1 ? A.th_0 : A.th_1 + (A.th_2 - A.th_1) / (A.z_2 - A.z_1) * (z - A.z_1);
+    }
+    __device__ double theta_dry(double th, double qv) const {  // SDM_θ_dry
+        const double r = qv / (1.0 - qv);
+        return th * pow(1.0 + r * (A.R_v / A.R_d), A.R_d / A.cp_d);
+    }
+    __device__ double T_of(double th_dry, double rho_dry) const {  // SDM_T
+        const double kap = A.R_d / A.cp_d;
+        return th_dry * pow(rho_dry * th_dry / A.MSLP * A.R_d, kap / (1.0 - kap));
+    }
+    __device__ double rho_surface(double p0) const {  // ρ_0 of init_profile: SDM_ρ_dry at the surface, then SDM_ρ_of_ρ_dry
+        double qv0, th0;
+        sounding(A.z_0, qv0, th0);  // θ_0 = tht_0 (z_0 < z_1)
+        const double kap = A.R_d / A.cp_d;
+        double rho_dry0;
+        if (qv0 > 0.0) {
+            const double r = qv0 / (1.0 - qv0);
+            rho_dry0 = p0 * (1.0 - 1.0 / (1.0 + 1.0 / (A.R_v / A.R_d) / r)) / (pow(p0 / A.MSLP, kap) * A.R_d * A.th_0);
+            return rho_dry0 * (1.0 + r);
+        }
+        return p0 / (pow(p0 / A.MSLP, kap) * A.R_d * A.th_0);
+    }
+    __device__ double drho_dz(double z, double rho) const {  // initial_condition.jl:100-130
+        double qv, th;
+        sounding(z, qv, th);
+        const double thd = theta_dry(th, qv);
+        const double r = qv / (1.0 - qv);
+        const double rho_dry = rho / (1.0 + r);
+        const double T = T_of(thd, rho_dry);
+        double R_m = A.R_d, cp_m = A.cp_d, p = rho_dry * A.R_d * T;
+        if (qv > 0.0) {
+            R_m = A.R_v / (1.0 / r + 1.0) + A.R_d / (1.0 + r);
+            cp_m = A.cp_v / (1.0 / r + 1.0) + A.cp_d / (1.0 + r);
+            p = rho_dry * (1.0 + r) * R_m * T;  // SDM_p
+        }
+        const double rho_sdm = p / R_m / T;
+        return A.grav / T * rho_sdm * (R_m / cp_m - 1.0) / R_m;
+    }
+    __device__ double rk4(double z, double rho, double h) const {
+        const double k1 = drho_dz(z, rho);
+        const double k2 = drho_dz(z + 0.5 * h, rho + 0.5 * h * k1);
+        const double k3 = drho_dz(z + 0.5 * h, rho + 0.5 * h * k2);
+        const double k4 = drho_dz(z + h, rho + h * k3);
+        return rho + h / 6.0 * (k1 + 2.0 * k2 + 2.0 * k3 + k4);
+    }
+    // integrate from za to zb (zb > za), splitting at the kink of the sounding
+    __device__ double advance(double za, double zb, double rho, int nsub) const {
+        if (za < A.z_1 && A.z_1 < zb) {
+            rho = advance(za, A.z_1, rho, nsub);
+            return advance(A.z_1, zb, rho, nsub);
+        }
+        const double h = (zb - za) / nsub;
+        for (int s = 0; s < nsub; ++s) rho = rk4(za + s * h, rho, h);
+        return rho;
+    }
+};
+
+template <class FT>
+__global__ void init_shipway_hill_kernel(const ICArgs<FT> A) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= A.nc) return;
+    ICProfile<FT> pr(A);
+    const size_t plane = size_t(A.nz) * A.ncp;
+    double z = A.z_0, rho = pr.rho_surface(double(A.p0[c]));
+    double qv_s, th_s;
+    pr.sounding(0.0, qv_s, th_s);  // aux.q_surf = init_profile(z = 0).qv (K1DModel/ode_utils.jl:96)
+    A.q_surf[c] = FT(qv_s);
+    const double Nd = double(A.Nd[c]);
+    for (int k = 0; k < A.nz; ++k) {
+        const double zc = A.z_min + (k + 0.5) * A.dz;
+        if (zc > z) { rho = pr.advance(z, zc, rho, k == 0 ? A.nsub * 2 : A.nsub); z = zc; }
+        double qv, th;
+        pr.sounding(zc, qv, th);
+        // initial_condition_1d: ρ = FT(ρ_profile(z)), everything after in FT
+        const FT rho_ft = FT(rho), qv_ft = FT(qv);
+        const FT rho_dry = FT(double(rho_ft) / (1.0 + double(qv_ft) / (1.0 - double(qv_ft))));
+        const FT thd = FT(pr.theta_dry(double(FT(th)), double(qv_ft)));
+        const FT T = FT(pr.T_of(double(thd), double(rho_dry)));
+        const size_t pi = size_t(k) * A.ncp + c;
+        A.rho_dry[pi] = rho_dry;
+        A.T[pi] = T;
+        A.Y[size_t(A.i_tot) * plane + pi] = qv_ft * rho_ft;
+        if (A.i_Na >= 0) A.Y[size_t(A.i_Na) * plane + pi] = FT(Nd) * rho_dry / FT(1.225);
+    }
+}
+
+}  // namespace kid

@@ -97,6 +97,8 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         "kid_get_state": (C.c_int, [H, C.c_void_p]),
         "kid_set_state_async": (C.c_int, [H, C.c_void_p]),
         "kid_get_state_async": (C.c_int, [H, C.c_void_p]),
+        "kid_init_shipway_hill": (C.c_int, [H, C.POINTER(C.c_double), C.c_void_p, C.c_int32]),
+        "kid_get_profiles": (C.c_int, [H, C.c_void_p, C.c_void_p]),
         "kid_step": (C.c_int, [H, C.c_double, C.c_int32]),
         "kid_set_steps_per_launch": (C.c_int, [H, C.c_int32]),
         "kid_rhs": (C.c_int, [H, C.c_double, C.c_void_p]),
@@ -211,6 +213,24 @@ class Handle:
             return
         v = np.ascontiguousarray(np.broadcast_to(np.asarray(values, dtype=self.dtype), (self.cfg.nc,)))
         self._check(self.lib.kid_set_column_scalar(self._h, which, _ptr(v)))
+
+    def init_shipway_hill(self, sounding, p0: np.ndarray | None = None, dry: bool = False):
+        """Profiles, q_surf and initial state built on the device (ρ_ivp + initial_condition_1d per column).
+        sounding: (z_0, z_1, z_2, rv_0, rv_1, rv_2, tht_0, tht_1, tht_2); p0: one surface pressure per column."""
+        snd = np.ascontiguousarray(sounding, dtype=np.float64)
+        assert snd.size == 9
+        p = None
+        if p0 is not None:
+            p = np.ascontiguousarray(np.broadcast_to(np.asarray(p0, dtype=self.dtype), (self.cfg.nc,)))
+        self._check(self.lib.kid_init_shipway_hill(self._h, snd.ctypes.data_as(C.POINTER(C.c_double)),
+                                                   None if p is None else _ptr(p), int(dry)))
+
+    def get_profiles(self):
+        """(ρ_dry, T) as uploaded / built on the device: [nc, nz] each (or [nz] for one shared profile)."""
+        shape = (self.cfg.nc, self.cfg.nz)
+        r, t = np.empty(shape, dtype=self.dtype), np.empty(shape, dtype=self.dtype)
+        self._check(self.lib.kid_get_profiles(self._h, _ptr(r), _ptr(t)))
+        return r, t
 
     def set_state(self, Y: np.ndarray):
         y = np.ascontiguousarray(Y, dtype=self.dtype)

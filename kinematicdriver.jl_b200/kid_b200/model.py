@@ -40,6 +40,9 @@ class Case:
     column_to_set: np.ndarray | None = None
     z_centers: np.ndarray | None = None
     meta: dict = field(default_factory=dict)
+    # initial condition built on the device (kid_init_shipway_hill): {"sounding": 9 values, "p0": [nc], "dry": bool};
+    # ρ_dry, T, Y0 and q_surf are then None until `materialise` downloads them
+    device_ic: dict | None = None
 
     @property
     def dtype(self):
@@ -186,6 +189,13 @@ def box_case(FT=np.float64, nc: int = 1, device: int = 0, precipitation_choice="
 def apply_case(handle, case: Case):
     """Upload a Case into a backend handle (order matters: params and profiles before the state)."""
     handle.set_params(case.params, case.column_to_set)
+    if case.device_ic is not None and case.Y0 is None:
+        if not hasattr(handle, "init_shipway_hill"):
+            raise RuntimeError("this case builds its initial condition on the device: materialise(case) it first")
+        for which, values in case.col_scalars.items():
+            handle.set_column_scalar(which, values)
+        handle.init_shipway_hill(case.device_ic["sounding"], case.device_ic["p0"], case.device_ic.get("dry", False))
+        return handle
     handle.set_profiles(case.ρ_dry, case.T)
     for which, values in case.col_scalars.items():
         handle.set_column_scalar(which, values)
@@ -195,6 +205,37 @@ def apply_case(handle, case: Case):
 
 def make_handle(case: Case, backend=Handle):
     return apply_case(backend(case.cfg), case)
+
+
+def materialise(case: Case, handle=None) -> Case:
+    """Host copy of a device-built initial condition: downloads ρ_dry, T, the initial state and q_surf so that the case
+    can be handed to another backend (the test oracle) or sliced on the host."""
+    if case.Y0 is not None:
+        return case
+    import copy
+    h = handle or make_handle(case)
+    out = copy.copy(case)
+    out.ρ_dry, out.T = h.get_profiles()
+    out.Y0 = h.get_state()
+    out.col_scalars = dict(case.col_scalars)
+    out.col_scalars[COL_Q_SURF] = np.full(case.cfg.nc, case.device_ic["q_surf"], dtype=case.dtype)
+    return out
+
+
+def morton_order(*keys: np.ndarray, bits: int = 10) -> np.ndarray:
+    """Permutation that sorts members along a Z-order curve through the unit cube of their (normalised) keys:
+    neighbouring members are close in EVERY key, not only in the first one of a lexicographic sort."""
+    code = np.zeros(keys[0].shape, dtype=np.uint64)
+    q = []
+    for k in keys:
+        k = np.asarray(k, dtype=np.float64)
+        span = k.max() - k.min()
+        q.append(np.minimum(((k - k.min()) / (span if span > 0 else 1.0) * (1 << bits)).astype(np.uint64), (1 << bits) - 1))
+    n = len(keys)
+    for b in range(bits):
+        for d, qd in enumerate(q):
+            code |= ((qd >> np.uint64(b)) & np.uint64(1)) << np.uint64(b * n + (n - 1 - d))
+    return np.argsort(code, kind="stable")
 
 
 # ------------------------------------------------------------------ ensembles
@@ -214,11 +255,19 @@ def uniform01(seed: int, c: np.ndarray, k: int) -> np.ndarray:
 
 
 def k1d_ensemble_case(FT=np.float32, nc: int = 1024, seed: int = 20240601, n_profiles: int = 16,
-                      column_offset: int = 0, device: int = 0, order: str = "hash", **options) -> Case:
+                      column_offset: int = 0, device: int = 0, order: str = "hash", ic: str = "host", **options) -> Case:
     """Synthetic calibration-style ensemble of SURVEY §8(d): member c perturbs w1, prescribed Nd and the
-    surface pressure p0 (quantised to n_profiles distinct soundings so the host-side IVP stays cheap)."""
+    surface pressure p0.  ic="host": p0 is quantised to n_profiles distinct soundings so the host-side IVP stays cheap;
+    ic="device": every member has its own p0 = 1e5·(0.98 + 0.04·u_2) exactly as §8(d) defines it, and the hydrostatic
+    profile + initial state of each column are built on the device (kid_init_shipway_hill).
+    order: "hash" (member index order), "sorted" (lexicographic by sounding, w1, Nd) or "morton" (Z-order through
+    (w1, Nd, p0): neighbouring columns are similar in all three)."""
     FT = np.dtype(FT).type
     c = np.arange(column_offset, column_offset + nc)
+    if ic == "device":
+        return _k1d_ensemble_case_device_ic(FT, c, seed, device, order, options)
+    if ic != "host":
+        raise ValueError("ic must be 'host' or 'device'")
     # SURVEY §8(d) proposes w1 in [1, 3]; the reference formulation itself (closed lid: top SetValue(0) flux for
     # N_liq/N_rai/ρq_rai under an updraft) grows without bound at the domain top for w1 >~ 2.5 and overflows
     # Float32, so the synthetic ensemble keeps w1 in [1, 2.2]
@@ -251,6 +300,29 @@ def k1d_ensemble_case(FT=np.float32, nc: int = 1024, seed: int = 20240601, n_pro
                 col_scalars={COL_Q_SURF: bank_q[pidx].astype(FT), COL_W1: w1.astype(FT),
                              COL_PRESCRIBED_ND: Nd.astype(FT)},
                 z_centers=base.z_centers, meta=dict(base.meta, seed=seed, n_profiles=n_profiles, order=order))
+
+
+def _k1d_ensemble_case_device_ic(FT, c, seed, device, order, options) -> Case:
+    nc = c.size
+    w1 = 2.0 * (0.5 + 0.6 * uniform01(seed, c, 0))
+    Nd = 10.0 ** (7.0 + 1.5 * uniform01(seed, c, 1))
+    p0 = 1e5 * (0.98 + 0.04 * uniform01(seed, c, 2))
+    if order in ("sorted", "morton"):
+        perm = morton_order(w1, np.log10(Nd), p0)
+        w1, Nd, p0 = w1[perm], Nd[perm], p0[perm]
+    elif order != "hash":
+        raise ValueError("order must be 'hash', 'sorted' or 'morton'")
+    base = k1d_case(FT, nc=1, device=device, **options)  # parameters, grid, q_surf (p0-independent)
+    o = base.meta["opts"]
+    import copy
+    cfg = copy.copy(base.cfg)
+    cfg.nc = nc
+    sounding = [o[k] for k in ("z_0", "z_1", "z_2", "rv_0", "rv_1", "rv_2", "tht_0", "tht_1", "tht_2")]
+    return Case(cfg=cfg, params=base.params, ρ_dry=None, T=None, Y0=None, var_names=base.var_names,
+                col_scalars={COL_W1: w1.astype(FT), COL_PRESCRIBED_ND: Nd.astype(FT)}, z_centers=base.z_centers,
+                meta=dict(base.meta, seed=seed, order=order, p0=p0),
+                device_ic=dict(sounding=sounding, p0=p0.astype(FT), dry=False,
+                               q_surf=float(base.col_scalars[COL_Q_SURF][0])))
 
 
 def box_ensemble_case(FT=np.float64, nc: int = 1024, seed: int = 20240601, n_ic: int = 64, column_offset: int = 0,

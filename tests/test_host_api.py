@@ -132,3 +132,20 @@ def test_product_never_imports_the_oracle():
     for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.h")):
         txt = f.read_text()
         assert "oracle" not in txt.lower() or f.name == "model.py" and "CPU oracle" in txt, f
+
+
+def test_morton_order_keeps_neighbours_close_in_every_key():
+    from kid_b200 import model as M
+    rng = np.random.default_rng(3)
+    a, b, c = rng.uniform(1, 2.2, 32768), rng.uniform(7, 8.5, 32768), rng.uniform(0.98e5, 1.02e5, 32768)
+    perm = M.morton_order(a, b, c)
+    assert sorted(perm.tolist()) == list(range(32768))
+    def spread(x):  # mean range of a key inside a warp of 32 neighbouring members, relative to the key's full range
+        g = x[perm].reshape(-1, 32)
+        return float(np.mean(g.max(1) - g.min(1)) / (x.max() - x.min()))
+    lex = np.lexsort((c, b, a))
+    def spread_lex(x):
+        g = x[lex].reshape(-1, 32)
+        return float(np.mean(g.max(1) - g.min(1)) / (x.max() - x.min()))
+    assert max(spread(a), spread(b), spread(c)) < 0.25      # close in all three keys
+    assert max(spread_lex(b), spread_lex(c)) > 0.8          # a lexicographic sort only helps the first key
