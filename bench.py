@@ -37,6 +37,7 @@ NZ = 128
 BYTES_PER_GP_STEP = 2 * 8 * 4 + 2 * 4  # NonEq+2M f32: read+write 8 prognostics, read per-column ρ_dry, T
 METRIC = "grid-point-steps/s"
 ORDER = "sorted"
+IC = "device"
 PREROLL_SPL = 60  # the untimed pre-roll runs in launches of 60 fused steps
 
 
@@ -84,12 +85,19 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def build_case(nc: int, column_offset: int, device: int):
+def build_case(nc: int, column_offset: int, device: int, host_ic: bool = False):
+    """SURVEY §8(d) ensemble: member c has w1, Nd, p0 from the counter hash.  --ic device (default): every member its own
+    p0, hydrostatic profile and initial state built on the device (kid_init_shipway_hill); --ic host: p0 quantised to 16
+    soundings solved on the host.  Member order: "sorted" stores the members along a Z-order curve through
+    (w1, log Nd, p0) (--ic host: lexicographically by sounding, w1, Nd), so that neighbouring columns — the 32 lanes of a
+    warp — follow the same microphysics branches; --order hash keeps the hash order of §8(d)."""
     from kid_b200 import model as M
-    # member order: the ensemble is stored sorted by (sounding, w1, Nd) so that neighbouring columns (the 32 lanes of a
-    # warp) follow the same microphysics branches; the hash order of SURVEY §8(d) is available with --order hash
-    return M.k1d_ensemble_case(np.float32, nc=nc, n_profiles=16, column_offset=column_offset, device=device, n_elem=NZ,
-                               order=ORDER, moisture_choice="NonEquilibriumMoisture", precipitation_choice="Precipitation2M")
+    kw = dict(column_offset=column_offset, device=device, n_elem=NZ, order=ORDER,
+              moisture_choice="NonEquilibriumMoisture", precipitation_choice="Precipitation2M")
+    if IC == "device" and not host_ic:
+        return M.k1d_ensemble_case(np.float32, nc=nc, ic="device", **kw)
+    # host IC; the CPU arm of a device-IC run keeps the exact per-member p0 (one host IVP per member of its small sample)
+    return M.k1d_ensemble_case(np.float32, nc=nc, n_profiles=None if IC == "device" else 16, **kw)
 
 
 def cpu_reference_throughput(case, Y_dev_sample, t_start: float, target_s: float = 15.0):
@@ -99,11 +107,9 @@ def cpu_reference_throughput(case, Y_dev_sample, t_start: float, target_s: float
     from oracle.oracle import OracleHandle
     cores = os.cpu_count() or 1
     ncpu = Y_dev_sample.shape[0]
-    sub = M.Case(cfg=case.cfg, params=case.params, ρ_dry=case.ρ_dry[:ncpu], T=case.T[:ncpu], Y0=Y_dev_sample,
-                 var_names=case.var_names, col_scalars={k: v[:ncpu] for k, v in case.col_scalars.items()})
     import copy
-    sub.cfg = copy.copy(case.cfg)
-    sub.cfg.nc = ncpu
+    sub = copy.copy(M.materialise(M.slice_columns(case, 0, ncpu)))  # device-built profiles of the sample -> host
+    sub.Y0 = Y_dev_sample
     o = M.make_handle(sub, OracleHandle)
     t0 = time.perf_counter()
     o.step(t_start, 4)
@@ -128,7 +134,7 @@ def run_reference(args):
     from oracle.oracle import OracleHandle
     cores = os.cpu_count() or 1
     ncpu = 32 * cores
-    case = build_case(ncpu, 0, 0)
+    case = build_case(ncpu, 0, 0, host_ic=True)
     o = M.make_handle(case, OracleHandle)
     t_start = float(args.t_start)
     # bring the sample to the same developed state the device arm times (untimed)
@@ -233,13 +239,14 @@ def run_ours(args):
     # H2D upload, the K steps and the D2H download of different chunks overlap (kid_set_state_async / kid_step /
     # kid_get_state_async).  Everything — copies included — is inside the timed region.
     from kid_b200.solve import PipelinedEnsemble
-    Yh = torch.empty(case.Y0.shape, dtype=torch.float32).pin_memory()
+    state_shape = (nc, len(case.var_names), NZ)
+    Yh = torch.empty(state_shape, dtype=torch.float32).pin_memory()
     Yn = Yh.numpy()
     h.get_state(Yn)  # developed state as the "user's" host input
     pipe = PipelinedEnsemble(case, nchunks=args.e2e_chunks)
     pipe.set_steps_per_launch(spl)
     e2e_steps = args.steps
-    Yw = torch.empty(case.Y0.shape, dtype=torch.float32).pin_memory().numpy()
+    Yw = torch.empty(state_shape, dtype=torch.float32).pin_memory().numpy()
     Yw[...] = Yn
     pipe.solve(Yw, t, spl)  # warm the chunk handles (first launch of each, pinned-page first touch)
     del Yw
@@ -280,7 +287,11 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "KiD 1D NonEq+Precipitation2M(SB2006) ensemble, 128 levels, Float32 (BASELINE configs[3])",
                        "columns_per_gpu": nc, "levels": NZ, "steps_per_launch": spl, "t_start_s": t_timed0,
-                       "member_order": ORDER + (" by (sounding, w1, Nd)" if ORDER == "sorted" else " (SURVEY 8d counter hash)"),
+                       "member_order": ("hash (SURVEY 8d counter hash)" if ORDER == "hash" else
+                                        "sorted along a Z-order curve through (w1, log Nd, p0)" if IC == "device" else
+                                        "sorted by (sounding, w1, Nd)"),
+                       "initial_condition": ("built on the device, every member its own p0 (SURVEY 8d)" if IC == "device" else
+                                             "host, p0 quantised to 16 soundings"),
                        "l2": "state per GPU (%.2f GiB) is far larger than the 126 MB L2; no flush needed" % (state_bytes / 2**30),
                        "parallelism": f"columns sharded x{world}, no collective", "state_finite": finite},
             "clocks": clocks,
@@ -314,10 +325,12 @@ def main():
     ap.add_argument("--t-start", type=int, default=480, help="model time [s] at which the timed window starts")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample length (0 = skip)")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="column chunks (handles/streams) of the end-to-end pipelined call")
+    ap.add_argument("--ic", default="device", choices=["device", "host"], help="where the initial condition is built")
     ap.add_argument("--order", default="sorted", choices=["sorted", "hash"], help="storage order of the ensemble members")
     args = ap.parse_args()
-    global ORDER
+    global ORDER, IC
     ORDER = args.order
+    IC = args.ic
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     return run_reference(args) if args.impl == "reference" else run_ours(args)

@@ -207,6 +207,23 @@ def make_handle(case: Case, backend=Handle):
     return apply_case(backend(case.cfg), case)
 
 
+def slice_columns(case: Case, a: int, b: int) -> Case:
+    """Columns [a, b) of an ensemble case as a case of their own (host arrays are views)."""
+    import copy
+    cfg = copy.copy(case.cfg)
+    cfg.nc = b - a
+    scal = {k: np.asarray(v)[a:b] for k, v in case.col_scalars.items()}
+    c2s = None if case.column_to_set is None else case.column_to_set[a:b]
+    if case.device_ic is not None and case.Y0 is None:
+        return Case(cfg=cfg, params=case.params, ρ_dry=None, T=None, Y0=None, var_names=case.var_names, col_scalars=scal,
+                    column_to_set=c2s, z_centers=case.z_centers, meta=case.meta,
+                    device_ic=dict(case.device_ic, p0=np.asarray(case.device_ic["p0"])[a:b]))
+    pc = np.ndim(case.ρ_dry) == 2
+    return Case(cfg=cfg, params=case.params, ρ_dry=case.ρ_dry[a:b] if pc else case.ρ_dry, T=case.T[a:b] if pc else case.T,
+                Y0=case.Y0[a:b], var_names=case.var_names, col_scalars=scal, column_to_set=c2s, z_centers=case.z_centers,
+                meta=case.meta, device_ic=case.device_ic)
+
+
 def materialise(case: Case, handle=None) -> Case:
     """Host copy of a device-built initial condition: downloads ρ_dry, T, the initial state and q_surf so that the case
     can be handed to another backend (the test oracle) or sliced on the host."""
@@ -273,15 +290,25 @@ def k1d_ensemble_case(FT=np.float32, nc: int = 1024, seed: int = 20240601, n_pro
     # Float32, so the synthetic ensemble keeps w1 in [1, 2.2]
     w1 = 2.0 * (0.5 + 0.6 * uniform01(seed, c, 0))
     Nd = 10.0 ** (7.0 + 1.5 * uniform01(seed, c, 1))
-    pidx = np.minimum((uniform01(seed, c, 2) * n_profiles).astype(np.int64), n_profiles - 1)
+    u2 = uniform01(seed, c, 2)
+    if n_profiles is None:  # every member its own p0 (one host IVP per member: small ensembles only)
+        p0_exact = 1e5 * (0.98 + 0.04 * u2)
+        if order in ("sorted", "morton"):
+            perm = morton_order(w1, np.log10(Nd), p0_exact)
+            w1, Nd, p0_exact = w1[perm], Nd[perm], p0_exact[perm]
+        elif order != "hash":
+            raise ValueError("order must be 'hash', 'sorted' or 'morton'")
+        p0_levels, pidx, n_profiles, order = p0_exact, np.arange(nc), nc, "done"
+    else:
+        pidx = np.minimum((u2 * n_profiles).astype(np.int64), n_profiles - 1)
+        p0_levels = 1e5 * (0.98 + 0.04 * (np.arange(n_profiles) + 0.5) / n_profiles)
     if order == "sorted":
         # the order of ensemble members is arbitrary: placing similar members (same sounding, similar updraft) in
         # neighbouring columns keeps the 32 lanes of a warp on the same microphysics branches
         perm = np.lexsort((Nd, w1, pidx))
         w1, Nd, pidx = w1[perm], Nd[perm], pidx[perm]
-    elif order != "hash":
+    elif order not in ("hash", "done"):
         raise ValueError("order must be 'hash' or 'sorted'")
-    p0_levels = 1e5 * (0.98 + 0.04 * (np.arange(n_profiles) + 0.5) / n_profiles)
     base = None
     bank_ρ, bank_T, bank_Y, bank_q = [], [], [], []
     for p0 in p0_levels:

@@ -202,21 +202,8 @@ class PipelinedEnsemble:
         edges[-1] = nc
         self.ranges = [(int(a), int(b)) for a, b in zip(edges[:-1], edges[1:]) if b > a]
         self.handles = []
-        pc = np.ndim(case.ρ_dry) == 2
         for a, b in self.ranges:
-            cfg = copy.copy(case.cfg)
-            cfg.nc = b - a
-            scal = {k: np.asarray(v)[a:b] for k, v in case.col_scalars.items()}
-            c2s = None if case.column_to_set is None else case.column_to_set[a:b]
-            if case.device_ic is not None and case.Y0 is None:  # initial condition built on the device, per chunk
-                sub = M.Case(cfg=cfg, params=case.params, ρ_dry=None, T=None, Y0=None, var_names=case.var_names,
-                             col_scalars=scal, column_to_set=c2s,
-                             device_ic=dict(case.device_ic, p0=np.asarray(case.device_ic["p0"])[a:b]))
-            else:
-                sub = M.Case(cfg=cfg, params=case.params, ρ_dry=case.ρ_dry[a:b] if pc else case.ρ_dry,
-                             T=case.T[a:b] if pc else case.T, Y0=case.Y0[a:b], var_names=case.var_names,
-                             col_scalars=scal, column_to_set=c2s)
-            self.handles.append(M.make_handle(sub, backend))
+            self.handles.append(M.make_handle(M.slice_columns(case, a, b), backend))
 
     def set_steps_per_launch(self, n: int):
         for h in self.handles:

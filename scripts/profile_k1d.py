@@ -20,14 +20,15 @@ ap.add_argument("--precip", default="Precipitation2M")
 ap.add_argument("--nw", type=int, default=0)
 ap.add_argument("--tile-c", type=int, default=0)
 ap.add_argument("--no-fixed", type=int, default=0)
-ap.add_argument("--order", default="hash", choices=["hash", "sorted", "uniform"])
+ap.add_argument("--order", default="hash", choices=["hash", "sorted", "uniform", "morton"])
+ap.add_argument("--ic", default="host", choices=["host", "device"])
 a = ap.parse_args()
 FT = np.float32 if a.ft == "f32" else np.float64
 if a.order == "uniform":
     cs = M.k1d_case(FT, nc=a.columns, n_elem=a.nz, moisture_choice=a.moisture, precipitation_choice=a.precip)
 else:
     cs = M.k1d_ensemble_case(FT, nc=a.columns, n_profiles=16, n_elem=a.nz, moisture_choice=a.moisture, precipitation_choice=a.precip,
-                             order=a.order)
+                             order=a.order, ic=a.ic)
 if a.nw: cs.cfg.reserved[0] = a.nw
 if a.tile_c: cs.cfg.reserved[1] = a.tile_c
 if a.no_fixed: cs.cfg.reserved[2] = 1
