@@ -183,6 +183,18 @@ function solve(moisture, precip, Y, aux, tspan; model::Symbol, dt, saveat, nz, z
     end
 end
 
+# ------------------------------------------------------------------ initial condition on the device
+"""
+    init_shipway_hill!(h, kid_params, p0::Vector{FT})
+
+Replaces `ρ_ivp` + `initial_condition_1d` + `initialise_state` (src/Common/initial_condition.jl:50-231) for an ensemble
+whose members differ in the surface pressure: one hydrostatic profile and initial state per column, built on the device.
+"""
+function init_shipway_hill!(h::Ptr{Cvoid}, kp, p0::Vector{FT}; dry = false) where {FT}
+    snd = Float64[kp.z_0, kp.z_1, kp.z_2, kp.rv_0, kp.rv_1, kp.rv_2, kp.tht_0, kp.tht_1, kp.tht_2]
+    check(ccall((:kid_init_shipway_hill, libkid), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Cvoid}, Int32), h, snd, p0, dry ? 1 : 0))
+end
+
 # ------------------------------------------------------------------ calibration observables on the device
 const OBS_NAMES = ["qt", "ql", "qr", "qv", "qlr", "rt", "rl", "rr", "rv", "rlr", "Nl", "Nr", "Na", "rho",
                    "rain averaged terminal velocity", "rainrate"]   # enum kid_obs_var
