@@ -18,6 +18,9 @@
 #include <string>
 #include <vector>
 
+#ifdef KID_OPCOUNT
+#include "opcount.hpp"  // operation-counting scalar: libkid_oracle_opcount.so (oracle/Makefile), measurement only
+#endif
 #include "kid_physics.hpp"
 
 namespace kidoracle {
@@ -91,21 +94,21 @@ struct Model {
 
     // K1D: src/K1DModel/tendency.jl:208-210, 240-248
     void precompute_aux_prescribed_velocity_k1d(ColAux<FT>& a, FT t) {
-        FT rw = FT((t < P.kid_t1) ? double(a.w1) * std::sin(M_PI * double(t) / double(P.kid_t1)) : 0.0);
+        FT rw = FT((t < P.kid_t1) ? double(a.w1) * kidm::sin(M_PI * double(t) / double(P.kid_t1)) : 0.0);
         std::fill(a.rho_w.begin(), a.rho_w.end(), rw);
         a.rho_w0 = rw;
     }
     // K2D: src/K2DModel/tendency.jl:4-46
     void precompute_aux_prescribed_velocity_k2d(ColAux<FT>& a, FT x, FT t) {
         double W = cfg.domain_width, H = cfg.domain_height;
-        double ts = (t < P.kid_t1) ? std::sin(M_PI * double(t) / double(P.kid_t1)) : 0.0;
+        double ts = (t < P.kid_t1) ? kidm::sin(M_PI * double(t) / double(P.kid_t1)) : 0.0;
         for (int k = 0; k < nz; ++k) {
             double z = double(zc[k]);
-            a.rho_u[k] = FT(0.5 * double(a.w1) * W / H * std::cos(M_PI / H * z) * std::cos(2 * M_PI / W * double(x)) * ts);
+            a.rho_u[k] = FT(0.5 * double(a.w1) * W / H * kidm::cos(M_PI / H * z) * kidm::cos(2 * M_PI / W * double(x)) * ts);
         }
         for (int k = 0; k <= nz; ++k) {
             double z = cfg.z_min + double(dz) * k;
-            a.rho_w[k] = FT(double(a.w1) * std::sin(M_PI / H * z) * std::sin(2 * M_PI / W * double(x)) * ts);
+            a.rho_w[k] = FT(double(a.w1) * kidm::sin(M_PI / H * z) * kidm::sin(2 * M_PI / W * double(x)) * ts);
         }
         a.rho_w0 = FT(0);
     }
@@ -160,8 +163,8 @@ struct Model {
             SB2006<FT> sb(P, sw.rain_formation != KID_RF_SB2006NL);
             for (int k = 0; k < nz; ++k) a.q_rai[k] = q_(var(Yc, L.rai)[k], a.rho[k]);
             for (int k = 0; k < nz; ++k) a.q_sno[k] = q_(var(Yc, L.sno)[k], a.rho[k]);
-            for (int k = 0; k < nz; ++k) a.N_rai[k] = std::max(FT(0), var(Yc, L.Nr)[k]);
-            for (int k = 0; k < nz; ++k) a.N_liq[k] = std::max(FT(0), var(Yc, L.Nl)[k]);
+            for (int k = 0; k < nz; ++k) a.N_rai[k] = kidm::max(FT(0), var(Yc, L.Nr)[k]);
+            for (int k = 0; k < nz; ++k) a.N_liq[k] = kidm::max(FT(0), var(Yc, L.Nl)[k]);
             for (int k = 0; k < nz; ++k)
                 sb.rain_terminal_velocity(a.q_rai[k], a.rho[k], a.N_rai[k], a.vt_N_rai[k], a.vt_rai[k]);
         }
@@ -181,7 +184,7 @@ struct Model {
         FT S_max = arg.max_supersaturation(P.kid_r_dry, P.kid_std_dry, budget, P.kid_kappa, T, p, w, q_tot, q_liq,
                                            q_ice, preexisting);
         FT N_act = arg.total_N_activated(S_max, P.kid_r_dry, P.kid_std_dry, budget, P.kid_kappa, T);
-        bool zero = std::isnan(N_act) || (sw.local_activation && (S_max < S || N_act < N_liq));
+        bool zero = kidm::isnan(N_act) || (sw.local_activation && (S_max < S || N_act < N_liq));
         return zero ? FT(0) : (N_act - N_liq) / dt;
     }
     // src/K1DModel/tendency.jl:133-177 (+ find_cloud_base! :21-32)
@@ -426,7 +429,7 @@ struct Model {
     void add_fcc(const std::vector<FT>& wf, const FT* x, FT* out) {
         std::vector<FT> C(nz, FT(0));
         for (int k = 1; k < nz - 1; ++k)
-            C[k] = P.num_fcc_scale * (std::fabs(wf[k + 1]) * (x[k + 1] - x[k]) - std::fabs(wf[k]) * (x[k] - x[k - 1])) / dz;
+            C[k] = P.num_fcc_scale * (kidm::fabs(wf[k + 1]) * (x[k + 1] - x[k]) - kidm::fabs(wf[k]) * (x[k] - x[k - 1])) / dz;
         C[0] = C[1];
         C[nz - 1] = C[nz - 2];
         for (int k = 0; k < nz; ++k) out[k] += C[k];
@@ -641,7 +644,7 @@ static void gll_setup(int Nq, std::vector<double>& x, std::vector<double>& w, st
         PN = p1; PNm1 = p0;
     };
     for (int i = 0; i < Nq; ++i) {
-        double xi = -std::cos(M_PI * i / N);
+        double xi = -kidm::cos(M_PI * i / N);
         for (int it = 0; it < 100; ++it) {
             double PN, PNm1;
             legendre(xi, PN, PNm1);
@@ -650,7 +653,7 @@ static void gll_setup(int Nq, std::vector<double>& x, std::vector<double>& w, st
             double dx = f / fp;
             if (i == 0 || i == N) break;
             xi -= dx;
-            if (std::fabs(dx) < 1e-16) break;
+            if (kidm::fabs(dx) < 1e-16) break;
         }
         if (i == 0) xi = -1;
         if (i == N) xi = 1;
@@ -832,10 +835,26 @@ extern "C" {
 void* kidoracle_create(const kid_config_t* cfg) {
     Layout L;
     if (!make_layout(cfg->moisture, cfg->precip, L)) return nullptr;
+#ifndef KID_OPCOUNT
     if (cfg->float_type == KID_F32) return new Oracle<float>(*cfg);
+#endif
+#ifdef KID_OPCOUNT
+    // the counting build runs everything in its counting scalar (a wrapped double): host arrays are Float64
+    if (cfg->float_type == KID_F64) return new Oracle<kidm::Cnt>(*cfg);
+    return nullptr;
+#else
     if (cfg->float_type == KID_F64) return new Oracle<double>(*cfg);
     return nullptr;
+#endif
 }
+#ifdef KID_OPCOUNT
+// counters since the last reset: {add, mul, div, sqrt, exp/log/pow/cbrt/sin/cos, erf/Γ, comparisons+min/max/abs}
+void kidoracle_opcount_reset(void) { kidm::counters() = kidm::OpCounters(); }
+void kidoracle_opcount_get(double* out) {
+    const kidm::OpCounters& c = kidm::counters();
+    out[0] = c.add; out[1] = c.mul; out[2] = c.div; out[3] = c.sqrt; out[4] = c.transc; out[5] = c.special; out[6] = c.cmp;
+}
+#endif
 void kidoracle_destroy(void* h) { delete static_cast<OracleBase*>(h); }
 int kidoracle_nvars(void* h) { return static_cast<OracleBase*>(h)->nvars(); }
 int kidoracle_set_params(void* h, const double* table, int nparams) {

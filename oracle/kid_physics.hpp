@@ -21,6 +21,13 @@
 
 #include "../include/kid_cuda.h"
 
+// math shims: <cmath> for float/double; oracle/opcount.hpp adds overloads for its operation-counting scalar (it must be
+// included BEFORE this header so that the templates below see them)
+namespace kidm {
+using std::pow; using std::max; using std::sqrt; using std::exp; using std::cbrt; using std::fabs; using std::min;
+using std::log; using std::sin; using std::cos; using std::tgamma; using std::erf; using std::isnan;
+}  // namespace kidm
+
 namespace kidoracle {
 
 // ---------------------------------------------------------------- parameters
@@ -53,9 +60,9 @@ inline double expint_E1(double x) {
             term *= -x / k;
             double add = -term / k;
             sum += add;
-            if (std::fabs(add) < 1e-17 * std::fabs(sum)) break;
+            if (kidm::fabs(add) < 1e-17 * kidm::fabs(sum)) break;
         }
-        return -euler - std::log(x) + sum;
+        return -euler - kidm::log(x) + sum;
     }
     // modified Lentz continued fraction
     double b = x + 1.0, c = 1e300, d = 1.0 / b, h = d;
@@ -66,9 +73,9 @@ inline double expint_E1(double x) {
         c = b + an / c;
         double del = c * d;
         h *= del;
-        if (std::fabs(del - 1.0) < 1e-16) break;
+        if (kidm::fabs(del - 1.0) < 1e-16) break;
     }
-    return h * std::exp(-x);
+    return h * kidm::exp(-x);
 }
 inline double gamma_upper_pos(double a, double x) {  // a > 0
     if (x < a + 1.0) {
@@ -77,38 +84,38 @@ inline double gamma_upper_pos(double a, double x) {  // a > 0
             ap += 1.0;
             del *= x / ap;
             sum += del;
-            if (std::fabs(del) < std::fabs(sum) * 1e-17) break;
+            if (kidm::fabs(del) < kidm::fabs(sum) * 1e-17) break;
         }
-        double lower = sum * std::exp(-x + a * std::log(x));
-        return std::tgamma(a) - lower;
+        double lower = sum * kidm::exp(-x + a * kidm::log(x));
+        return kidm::tgamma(a) - lower;
     }
     double b = x + 1.0 - a, c = 1e300, d = 1.0 / b, h = d;
     for (int i = 1; i < 1000; ++i) {
         double an = -i * (i - a);
         b += 2.0;
         d = an * d + b;
-        if (std::fabs(d) < 1e-300) d = 1e-300;
+        if (kidm::fabs(d) < 1e-300) d = 1e-300;
         c = b + an / c;
-        if (std::fabs(c) < 1e-300) c = 1e-300;
+        if (kidm::fabs(c) < 1e-300) c = 1e-300;
         d = 1.0 / d;
         double del = d * c;
         h *= del;
-        if (std::fabs(del - 1.0) < 1e-16) break;
+        if (kidm::fabs(del - 1.0) < 1e-16) break;
     }
-    return std::exp(-x + a * std::log(x)) * h;
+    return kidm::exp(-x + a * kidm::log(x)) * h;
 }
 inline double gamma_upper(double a, double x) {
     if (a > 0.0) return gamma_upper_pos(a, x);
     if (a == 0.0) return expint_E1(x);
     // Γ(a,x) = (Γ(a+1,x) − x^a e^{−x}) / a
-    return (gamma_upper(a + 1.0, x) - std::pow(x, a) * std::exp(-x)) / a;
+    return (gamma_upper(a + 1.0, x) - kidm::pow(x, a) * kidm::exp(-x)) / a;
 }
 template <class FT>
-inline FT sf_gamma(FT a) { return FT(std::tgamma(double(a))); }
+inline FT sf_gamma(FT a) { return FT(kidm::tgamma(double(a))); }
 template <class FT>
 inline FT sf_gamma_inc_upper(FT a, FT x) { return FT(gamma_upper(double(a), double(x))); }
 template <class FT>
-inline FT sf_erf(FT x) { return FT(std::erf(double(x))); }
+inline FT sf_erf(FT x) { return FT(kidm::erf(double(x))); }
 
 // ------------------------------------------------------------ Thermodynamics
 template <class FT>
@@ -137,8 +144,8 @@ struct Thermo {
     }
     // Clausius-Clapeyron with constant Δcp (TD.saturation_vapor_pressure)
     FT psat_generic(FT T, FT LH_0, FT dcp) const {
-        return P.td_p_triple * std::pow(T / P.td_T_triple, dcp / P.td_R_v) *
-               std::exp((LH_0 - dcp * P.td_T_0) / P.td_R_v * (FT(1) / P.td_T_triple - FT(1) / T));
+        return P.td_p_triple * kidm::pow(T / P.td_T_triple, dcp / P.td_R_v) *
+               kidm::exp((LH_0 - dcp * P.td_T_0) / P.td_R_v * (FT(1) / P.td_T_triple - FT(1) / T));
     }
     FT psat_liquid(FT T) const { return psat_generic(T, P.td_LH_v0, P.td_cp_v - P.td_cp_l); }
     FT psat_ice(FT T) const { return psat_generic(T, P.td_LH_s0, P.td_cp_v - P.td_cp_i); }
@@ -146,7 +153,7 @@ struct Thermo {
     FT liquid_fraction_T(FT T) const {
         if (T > P.td_T_freeze) return FT(1);
         if (T > P.td_T_icenuc)
-            return std::pow((T - P.td_T_icenuc) / (P.td_T_freeze - P.td_T_icenuc), P.td_pow_icenuc);
+            return kidm::pow((T - P.td_T_icenuc) / (P.td_T_freeze - P.td_T_icenuc), P.td_pow_icenuc);
         return FT(0);
     }
     FT psat_mixed(FT T) const {
@@ -160,7 +167,7 @@ struct Thermo {
     // TD.condensate_partition(thermo_params, T, ρ, q_tot) -> (q_liq, q_ice)
     // (Common/tendency.jl:44-45,64-65,329,334,359,371)
     void condensate_partition(FT T, FT rho, FT q_tot, FT& q_liq, FT& q_ice) const {
-        FT q_c = std::max(FT(0), q_tot - q_vap_saturation(T, rho));
+        FT q_c = kidm::max(FT(0), q_tot - q_vap_saturation(T, rho));
         FT lam = liquid_fraction_T(T);
         q_liq = lam * q_c;
         q_ice = (FT(1) - lam) * q_c;
@@ -173,14 +180,14 @@ struct Thermo {
     // TD.potential_temperature(thermo_params, T, ρ_dry) (Common/tendency.jl:47)
     FT potential_temperature_dry(FT T, FT rho_dry) const {
         FT p = P.td_R_d * rho_dry * T;
-        return T / std::pow(p / P.td_MSLP, P.td_R_d / P.td_cp_d);
+        return T / kidm::pow(p / P.td_MSLP, P.td_R_d / P.td_cp_d);
     }
     // TD.liquid_ice_pottemp(thermo_params, T, ρ, q_tot, q_liq, q_ice) (Common/tendency.jl:48)
     FT liquid_ice_pottemp(FT T, FT rho, FT q_tot, FT q_liq, FT q_ice) const {
         FT R_m = gas_constant_air(q_tot, q_liq, q_ice);
         FT cpm = cp_m(q_tot, q_liq, q_ice);
         FT p = R_m * rho * T;
-        FT theta = T / std::pow(p / P.td_MSLP, R_m / cpm);
+        FT theta = T / kidm::pow(p / P.td_MSLP, R_m / cpm);
         return theta * (FT(1) - (P.td_LH_v0 * q_liq + P.td_LH_s0 * q_ice) / (cpm * T));
     }
     // CM.ThermodynamicsInterface.supersaturation_over_liquid/ice (K1DModel/tendency.jl:55)
@@ -209,38 +216,38 @@ struct Thermo {
 // src/Common/helper_functions.jl:222-224
 template <class FT>
 inline FT triangle_inequality_limiter(FT force, FT limit) {
-    return force + limit - std::sqrt(force * force + limit * limit);
+    return force + limit - kidm::sqrt(force * force + limit * limit);
 }
 // src/Common/tendency.jl:11-14
 template <class FT>
-inline FT limit(FT q, FT dt, int n = 1) { return std::max(FT(0), q) / dt / FT(n); }
+inline FT limit(FT q, FT dt, int n = 1) { return kidm::max(FT(0), q) / dt / FT(n); }
 // src/Common/tendency.jl:17-19
 template <class FT>
-inline FT q_(FT rhoq, FT rho) { return std::max(FT(0), rhoq / rho); }
+inline FT q_(FT rhoq, FT rho) { return kidm::max(FT(0), rhoq / rho); }
 
 // ------------------------------------------------- CloudMicrophysics: common
 template <class FT>
 inline FT logistic_function(FT x, FT x0, FT k) {
     const FT eps = std::numeric_limits<FT>::epsilon();
-    x = std::max(FT(0), x);
-    if (std::fabs(x) < eps) return FT(0);
-    return FT(1) / (FT(1) + std::exp(-k * (x / x0 - x0 / x)));
+    x = kidm::max(FT(0), x);
+    if (kidm::fabs(x) < eps) return FT(0);
+    return FT(1) / (FT(1) + kidm::exp(-k * (x / x0 - x0 / x)));
 }
 template <class FT>
 inline FT logistic_function_integral(FT x, FT x0, FT k) {
     const FT eps = std::numeric_limits<FT>::epsilon();
-    x = std::max(FT(0), x);
-    if (std::fabs(x) < eps) return FT(0);
-    FT trnslt = -std::log(FT(1) - std::exp(-k)) / k;
+    x = kidm::max(FT(0), x);
+    if (kidm::fabs(x) < eps) return FT(0);
+    FT trnslt = -kidm::log(FT(1) - kidm::exp(-k)) / k;
     FT kt = k * (x / x0 - FT(1) + trnslt);
-    return (kt > FT(40)) ? x - x0 : (std::log(FT(1) + std::exp(kt)) / k - trnslt) * x0;
+    return (kt > FT(40)) ? x - x0 : (kidm::log(FT(1) + kidm::exp(kt)) / k - trnslt) * x0;
 }
 
 // ------------------------------------------------- CloudMicrophysics: 0M, NonEq
 // CM0.remove_precipitation(params, q_liq, q_ice, q_vap_sat) (Common/tendency.jl:396)
 template <class FT>
 inline FT cm0_remove_precipitation(const Prm<FT>& P, FT q_liq, FT q_ice, FT q_vap_sat) {
-    return -std::max(FT(0), q_liq + q_ice - P.p0m_S_0 * q_vap_sat) / P.p0m_tau_precip;
+    return -kidm::max(FT(0), q_liq + q_ice - P.p0m_S_0 * q_vap_sat) / P.p0m_tau_precip;
 }
 // CMNe.conv_q_vap_to_q_lcl_icl (Common/tendency.jl:327,332,357,369)
 template <class FT>
@@ -268,17 +275,17 @@ struct CM1 {
     // Marshall-Palmer intercept: rain/ice constant, snow n0 = μ (ρ q / ρ0)^ν with ρ0 = 1 kg/m3
     FT n0_rain() const { return P.rain_n0; }
     FT n0_ice() const { return P.ice_n0; }
-    FT n0_snow(FT q_sno, FT rho) const { return P.snow_mu * std::pow(rho * std::max(FT(0), q_sno), P.snow_nu); }
+    FT n0_snow(FT q_sno, FT rho) const { return P.snow_mu * kidm::pow(rho * kidm::max(FT(0), q_sno), P.snow_nu); }
     FT n0(const Species1M<FT>& s, FT q, FT rho) const { return s.is_snow ? n0_snow(q, rho) : n0_rain(); }
     // terminal-velocity prefactor: rain from drag balance, snow a parameter
     FT v0(const Species1M<FT>& s, FT rho) const {
         if (s.is_snow) return P.snow_v0;
-        return std::sqrt(FT(8) / FT(3) / P.rain_C_drag * (P.rain_rho_w / rho - FT(1)) * P.td_grav * P.rain_r0);
+        return kidm::sqrt(FT(8) / FT(3) / P.rain_C_drag * (P.rain_rho_w / rho - FT(1)) * P.td_grav * P.rain_r0);
     }
     // CM1.lambda_inverse(pdf, mass, q, ρ)
     FT lambda_inverse(FT n0v, FT r0, FT m0, FT me, FT dm, FT chim, FT q, FT rho) const {
         if (q > FT(0) && rho > FT(0)) {
-            return std::pow(rho * q * std::pow(r0, me + dm) / (chim * m0 * n0v * sf_gamma(me + dm + FT(1))),
+            return kidm::pow(rho * q * kidm::pow(r0, me + dm) / (chim * m0 * n0v * sf_gamma(me + dm + FT(1))),
                             FT(1) / (me + dm + FT(1)));
         }
         return FT(0);
@@ -293,7 +300,7 @@ struct CM1 {
     FT terminal_velocity(const Species1M<FT>& s, FT rho, FT q) const {
         if (q > FT(0)) {
             FT li = lambda_inverse(s, q, rho);
-            return s.chiv * v0(s, rho) * std::pow(li / s.r0, s.ve + s.dv) *
+            return s.chiv * v0(s, rho) * kidm::pow(li / s.r0, s.ve + s.dv) *
                    sf_gamma(s.me + s.ve + s.dm + s.dv + FT(1)) / sf_gamma(s.me + s.dm + FT(1));
         }
         return FT(0);
@@ -310,7 +317,7 @@ struct CM1 {
             FT G = td.G_func_ice(T);
             FT li = lambda_inverse_ice(q_ice, rho);
             FT r_is = P.ice_r_ice_snow;
-            rate = FT(4) * FT(M_PI) * S * G * n0_ice() / rho * std::exp(-r_is / li) *
+            rate = FT(4) * FT(M_PI) * S * G * n0_ice() / rho * kidm::exp(-r_is / li) *
                    (r_is * r_is / (P.ice_me + P.ice_dm) + (r_is * li + li * li));
         }
         return rate;
@@ -322,7 +329,7 @@ struct CM1 {
             FT li = lambda_inverse(s, q_pre, rho);
             FT ex = s.ae + s.ve + s.da + s.dv;
             rate = q_clo * E * n0(s, q_pre, rho) * s.a0 * v0(s, rho) * s.chia * s.chiv * li *
-                   sf_gamma(ex + FT(1)) / std::pow(s.r0 / li, ex);
+                   sf_gamma(ex + FT(1)) / kidm::pow(s.r0 / li, ex);
         }
         return rate;
     }
@@ -335,7 +342,7 @@ struct CM1 {
             FT li = lambda_inverse(r, q_rai, rho);
             FT ex = r.me + r.ae + r.ve + r.dm + r.da + r.dv;
             rate = P.ce_ice_rai / rho * n0_rain() * n0_ice() * r.m0 * r.a0 * v0(r, rho) * r.chim * r.chia * r.chiv *
-                   li_ice * li * sf_gamma(ex + FT(1)) / std::pow(r.r0 / li, ex);
+                   li_ice * li * sf_gamma(ex + FT(1)) / kidm::pow(r.r0 / li, ex);
         }
         return rate;
     }
@@ -347,18 +354,18 @@ struct CM1 {
             FT li_i = lambda_inverse(si, q_i, rho), li_j = lambda_inverse(sj, q_j, rho);
             FT v_ti = terminal_velocity(si, rho, q_i), v_tj = terminal_velocity(sj, rho, q_j);
             FT mj = sj.me + sj.dm;
-            rate = FT(M_PI) / rho * n0_i * n0_j * sj.m0 * sj.chim * P.ce_rai_sno * std::fabs(v_ti - v_tj) /
-                   std::pow(sj.r0, mj) *
-                   (FT(2) * sf_gamma(mj + FT(1)) * std::pow(li_i, FT(3)) * std::pow(li_j, mj + FT(1)) +
-                    FT(2) * sf_gamma(mj + FT(2)) * std::pow(li_i, FT(2)) * std::pow(li_j, mj + FT(2)) +
-                    sf_gamma(mj + FT(3)) * li_i * std::pow(li_j, mj + FT(3)));
+            rate = FT(M_PI) / rho * n0_i * n0_j * sj.m0 * sj.chim * P.ce_rai_sno * kidm::fabs(v_ti - v_tj) /
+                   kidm::pow(sj.r0, mj) *
+                   (FT(2) * sf_gamma(mj + FT(1)) * kidm::pow(li_i, FT(3)) * kidm::pow(li_j, mj + FT(1)) +
+                    FT(2) * sf_gamma(mj + FT(2)) * kidm::pow(li_i, FT(2)) * kidm::pow(li_j, mj + FT(2)) +
+                    sf_gamma(mj + FT(3)) * li_i * kidm::pow(li_j, mj + FT(3)));
         }
         return rate;
     }
     FT ventilation(const Species1M<FT>& s, FT li, FT rho) const {
-        return s.a_vent + s.b_vent * std::cbrt(P.air_nu_air / P.air_D_vapor) /
-                              std::pow(s.r0 / li, (s.ve + s.dv) / FT(2)) *
-                              std::sqrt(FT(2) * v0(s, rho) * s.chiv / P.air_nu_air * li) *
+        return s.a_vent + s.b_vent * kidm::cbrt(P.air_nu_air / P.air_D_vapor) /
+                              kidm::pow(s.r0 / li, (s.ve + s.dv) / FT(2)) *
+                              kidm::sqrt(FT(2) * v0(s, rho) * s.chiv / P.air_nu_air * li) *
                               sf_gamma((s.ve + s.dv + FT(5)) / FT(2));
     }
     // CM1.evaporation_sublimation(rain, vel, aps, tps, q_tot, q_liq, q_ice, q_rai, q_sno, ρ, T) (Common/tendency.jl:540)
@@ -371,7 +378,7 @@ struct CM1 {
             FT li = lambda_inverse(r, q_rai, rho);
             rate = FT(4) * FT(M_PI) * n0_rain() / rho * S * G * li * li * ventilation(r, li, rho);
         }
-        return std::min(FT(0), rate);
+        return kidm::min(FT(0), rate);
     }
     // ... same method for snow (Common/tendency.jl:563): deposition or sublimation
     FT sublimation_snow(FT q_tot, FT q_liq, FT q_ice, FT q_rai, FT q_sno, FT rho, FT T) const {
@@ -406,34 +413,34 @@ inline FT cm2_conv_q_lcl_to_q_rai(const Prm<FT>& P, int rf, FT q_liq, FT rho, FT
     const FT eps = std::numeric_limits<FT>::epsilon();
     switch (rf) {
         case KID_RF_KK2000: {
-            q_liq = std::max(FT(0), q_liq);
-            return P.rf_acnv0 * std::pow(q_liq, P.rf_acnv1) * std::pow(N_d, P.rf_acnv2) * std::pow(rho, P.rf_acnv3);
+            q_liq = kidm::max(FT(0), q_liq);
+            return P.rf_acnv0 * kidm::pow(q_liq, P.rf_acnv1) * kidm::pow(N_d, P.rf_acnv2) * kidm::pow(rho, P.rf_acnv3);
         }
         case KID_RF_B1994: {
-            q_liq = std::max(FT(0), q_liq);
+            q_liq = kidm::max(FT(0), q_liq);
             FT d = (N_d >= P.rf_acnv4) ? P.rf_acnv5 : P.rf_acnv6;
-            return P.rf_acnv0 * std::pow(d, P.rf_acnv1) * std::pow(q_liq * rho, P.rf_acnv2) *
-                   std::pow(N_d, P.rf_acnv3) / rho;
+            return P.rf_acnv0 * kidm::pow(d, P.rf_acnv1) * kidm::pow(q_liq * rho, P.rf_acnv2) *
+                   kidm::pow(N_d, P.rf_acnv3) / rho;
         }
         case KID_RF_TC1980: {
-            q_liq = std::max(FT(0), q_liq);
-            FT q_thr = P.rf_acnv5 * N_d / rho * std::pow(P.rf_acnv3, P.rf_acnv4);
+            q_liq = kidm::max(FT(0), q_liq);
+            FT q_thr = P.rf_acnv5 * N_d / rho * kidm::pow(P.rf_acnv3, P.rf_acnv4);
             FT heav = (q_liq - q_thr > FT(0)) ? FT(1) : FT(0);
-            return P.rf_acnv2 * std::pow(q_liq, P.rf_acnv0) * std::pow(N_d, P.rf_acnv1) * heav;
+            return P.rf_acnv2 * kidm::pow(q_liq, P.rf_acnv0) * kidm::pow(N_d, P.rf_acnv1) * heav;
         }
         case KID_RF_LD2004: {
             if (q_liq <= eps) return FT(0);
             FT L = q_liq * rho;
-            FT r_vol = std::cbrt(FT(3) * L / FT(4) / FT(M_PI) / P.rf_acnv2 / N_d) * FT(1e6);
-            FT beta_6 = std::cbrt((r_vol + FT(3)) / r_vol);
-            FT E = P.rf_acnv1 * std::pow(beta_6, FT(6));
+            FT r_vol = kidm::cbrt(FT(3) * L / FT(4) / FT(M_PI) / P.rf_acnv2 / N_d) * FT(1e6);
+            FT beta_6 = kidm::cbrt((r_vol + FT(3)) / r_vol);
+            FT E = P.rf_acnv1 * kidm::pow(beta_6, FT(6));
             FT R_6 = beta_6 * r_vol;
-            FT R_6C = P.rf_acnv0 / std::pow(L, FT(1) / FT(6)) / std::sqrt(R_6);
+            FT R_6C = P.rf_acnv0 / kidm::pow(L, FT(1) / FT(6)) / kidm::sqrt(R_6);
             FT heav = (R_6 - R_6C > FT(0)) ? FT(1) : FT(0);
             return E * L * L * L / N_d / rho * heav;
         }
         case KID_RF_VARTIMESCALE: {
-            return std::max(FT(0), q_liq) / (P.rf_acnv0 * std::pow(N_d / FT(1e8), P.rf_acnv1));
+            return kidm::max(FT(0), q_liq) / (P.rf_acnv0 * kidm::pow(N_d / FT(1e8), P.rf_acnv1));
         }
     }
     return FT(0);
@@ -441,10 +448,10 @@ inline FT cm2_conv_q_lcl_to_q_rai(const Prm<FT>& P, int rf, FT q_liq, FT rho, FT
 // CM2.accretion(scheme, q_liq, q_rai[, ρ]) (Common/tendency.jl:463,465)
 template <class FT>
 inline FT cm2_accretion_1m(const Prm<FT>& P, int rf, FT q_liq, FT q_rai, FT rho) {
-    q_liq = std::max(FT(0), q_liq);
-    q_rai = std::max(FT(0), q_rai);
+    q_liq = kidm::max(FT(0), q_liq);
+    q_rai = kidm::max(FT(0), q_rai);
     switch (rf) {
-        case KID_RF_KK2000: return P.rf_accr0 * std::pow(q_liq * q_rai, P.rf_accr1) * std::pow(rho, P.rf_accr2);
+        case KID_RF_KK2000: return P.rf_accr0 * kidm::pow(q_liq * q_rai, P.rf_accr1) * kidm::pow(rho, P.rf_accr2);
         case KID_RF_B1994: return P.rf_accr0 * q_liq * rho * q_rai;
         case KID_RF_TC1980: return P.rf_accr0 * q_liq * q_rai;
     }
@@ -466,14 +473,14 @@ struct SB2006 {
         FT L = rho * q_rai;
         RainPdf o;
         if (limited) {
-            FT xr_hat = std::max(P.sb_xr_min, std::min(P.sb_xr_max, L / N_rai));
-            FT N0 = std::max(P.sb_N0_min, std::min(P.sb_N0_max, N_rai * std::cbrt(FT(M_PI) * P.sb_rho_w / xr_hat)));
-            o.lam_r = std::max(P.sb_lam_min,
-                               std::min(P.sb_lam_max, std::sqrt(std::sqrt(FT(M_PI) * P.sb_rho_w * N0 / L))));
-            o.x_r = std::max(P.sb_xr_min, std::min(P.sb_xr_max, L * o.lam_r / N0));
+            FT xr_hat = kidm::max(P.sb_xr_min, kidm::min(P.sb_xr_max, L / N_rai));
+            FT N0 = kidm::max(P.sb_N0_min, kidm::min(P.sb_N0_max, N_rai * kidm::cbrt(FT(M_PI) * P.sb_rho_w / xr_hat)));
+            o.lam_r = kidm::max(P.sb_lam_min,
+                               kidm::min(P.sb_lam_max, kidm::sqrt(kidm::sqrt(FT(M_PI) * P.sb_rho_w * N0 / L))));
+            o.x_r = kidm::max(P.sb_xr_min, kidm::min(P.sb_xr_max, L * o.lam_r / N0));
         } else {
-            o.x_r = std::max(P.sb_xr_min, std::min(P.sb_xr_max, L / N_rai));
-            o.lam_r = std::cbrt(FT(M_PI) * P.sb_rho_w / o.x_r);
+            o.x_r = kidm::max(P.sb_xr_min, kidm::min(P.sb_xr_max, L / N_rai));
+            o.lam_r = kidm::cbrt(FT(M_PI) * P.sb_rho_w / o.x_r);
         }
         return o;
     }
@@ -481,25 +488,25 @@ struct SB2006 {
     void rain_terminal_velocity(FT q_rai, FT rho, FT N_rai, FT& vt0, FT& vt1) const {
         FT lam = pdf_rain(q_rai, rho, N_rai).lam_r;
         FT aR = P.sb_aR, bR = P.sb_bR, cR = P.sb_cR;
-        FT rc = -FT(1) / (FT(2) * cR) * std::log(aR / bR);
-        auto G1 = [](FT t) { return std::exp(-t); };
-        auto G4 = [](FT t) { return (t * t * t + FT(3) * t * t + FT(6) * t + FT(6)) * std::exp(-t); };
+        FT rc = -FT(1) / (FT(2) * cR) * kidm::log(aR / bR);
+        auto G1 = [](FT t) { return kidm::exp(-t); };
+        auto G4 = [](FT t) { return (t * t * t + FT(3) * t * t + FT(6) * t + FT(6)) * kidm::exp(-t); };
         FT pa0 = G1(FT(2) * rc * lam), pb0 = G1(FT(2) * rc * (lam + cR));
         FT pa1 = G4(FT(2) * rc * lam) / FT(6), pb1 = G4(FT(2) * rc * (lam + cR)) / FT(6);
-        FT sr = std::sqrt(P.sb_vel_rho0 / rho);
+        FT sr = kidm::sqrt(P.sb_vel_rho0 / rho);
         FT r1 = FT(1) + cR / lam;
-        vt0 = (N_rai < eps()) ? FT(0) : std::max(FT(0), sr * (aR * pa0 - bR * pb0 / r1));
-        vt1 = (q_rai < eps()) ? FT(0) : std::max(FT(0), sr * (aR * pa1 - bR * pb1 / (r1 * r1 * r1 * r1)));
+        vt0 = (N_rai < eps()) ? FT(0) : kidm::max(FT(0), sr * (aR * pa0 - bR * pb0 / r1));
+        vt1 = (q_rai < eps()) ? FT(0) : kidm::max(FT(0), sr * (aR * pa1 - bR * pb1 / (r1 * r1 * r1 * r1)));
     }
     // CM2.autoconversion(acnv, pdf_c, q_liq, q_rai, ρ, N_liq) (Common/tendency.jl:600,605)
     void autoconversion(FT q_liq, FT q_rai, FT rho, FT N_liq, FT& dq_rai_dt, FT& dN_rai_dt) const {
         dq_rai_dt = dN_rai_dt = FT(0);
         if (q_liq < eps() || N_liq < eps()) return;
         FT L_liq = rho * q_liq;
-        FT x_liq = std::min(P.sb_x_star, L_liq / N_liq);
-        q_rai = std::max(FT(0), q_rai);
+        FT x_liq = kidm::min(P.sb_x_star, L_liq / N_liq);
+        q_rai = kidm::max(FT(0), q_rai);
         FT tau = FT(1) - q_liq / (q_liq + q_rai);
-        FT phi_au = P.sb_A * std::pow(tau, P.sb_a) * std::pow(FT(1) - std::pow(tau, P.sb_a), P.sb_b);
+        FT phi_au = P.sb_A * kidm::pow(tau, P.sb_a) * kidm::pow(FT(1) - kidm::pow(tau, P.sb_a), P.sb_b);
         FT nu = P.sb_nu_c;
         FT dL = P.sb_kcc / FT(20) / P.sb_x_star * (nu + FT(2)) * (nu + FT(4)) / ((nu + FT(1)) * (nu + FT(1))) *
                 (L_liq * L_liq) * (x_liq * x_liq) * (FT(1) + phi_au / ((FT(1) - tau) * (FT(1) - tau))) * P.sb_rho0 / rho;
@@ -513,8 +520,8 @@ struct SB2006 {
         FT L_liq = rho * q_liq, L_rai = rho * q_rai;
         FT x_liq = L_liq / N_liq;
         FT tau = FT(1) - q_liq / (q_liq + q_rai);
-        FT phi_ac = std::pow(tau / (tau + P.sb_tau0), P.sb_c);
-        FT dL = P.sb_kcr * L_liq * L_rai * phi_ac * std::sqrt(P.sb_rho0 / rho);
+        FT phi_ac = kidm::pow(tau / (tau + P.sb_tau0), P.sb_c);
+        FT dL = P.sb_kcr * L_liq * L_rai * phi_ac * kidm::sqrt(P.sb_rho0 / rho);
         dN_liq_dt = -dL / x_liq;
         dq_rai_dt = dL / rho;
     }
@@ -529,24 +536,24 @@ struct SB2006 {
         if (q_rai < eps() || N_rai < eps()) return FT(0);
         FT L = rho * q_rai;
         // λr converted from diameter space [1/m] to mass space [kg^(-1/3)]
-        FT lam_x = pdf_rain(q_rai, rho, N_rai).lam_r * std::cbrt(FT(6) / FT(M_PI) / P.sb_rho_w);
-        return -P.sb_krr * N_rai * L * std::sqrt(P.sb_rho0 / rho) * std::pow(FT(1) + P.sb_kappa_rr / lam_x, P.sb_d);
+        FT lam_x = pdf_rain(q_rai, rho, N_rai).lam_r * kidm::cbrt(FT(6) / FT(M_PI) / P.sb_rho_w);
+        return -P.sb_krr * N_rai * L * kidm::sqrt(P.sb_rho0 / rho) * kidm::pow(FT(1) + P.sb_kappa_rr / lam_x, P.sb_d);
     }
     // CM2.rain_breakup(pdf_r, brek, q_rai, ρ, N_rai, dN_rai_dt_sc) (Common/tendency.jl:617)
     FT rain_breakup(FT q_rai, FT rho, FT N_rai, FT dN_rai_dt_sc) const {
         if (q_rai < eps() || N_rai < eps()) return FT(0);
         FT xr = pdf_rain(q_rai, rho, N_rai).x_r;
-        FT Dr = std::cbrt(xr * FT(6) / FT(M_PI) / P.sb_rho_w);
+        FT Dr = kidm::cbrt(xr * FT(6) / FT(M_PI) / P.sb_rho_w);
         FT dD = Dr - P.sb_Deq;
-        FT phi_br = (Dr < P.sb_Dr_th) ? FT(-1) : ((dD <= FT(0)) ? P.sb_kbr * dD : FT(2) * (std::exp(P.sb_kappa_br * dD) - FT(1)));
+        FT phi_br = (Dr < P.sb_Dr_th) ? FT(-1) : ((dD <= FT(0)) ? P.sb_kbr * dD : FT(2) * (kidm::exp(P.sb_kappa_br * dD) - FT(1)));
         return -(phi_br + FT(1)) * dN_rai_dt_sc;
     }
     // CM2.number_increase/decrease_for_mass_limit(numadj, x, q, ρ, N) (Common/tendency.jl:628-635)
     FT number_increase_for_mass_limit(FT x_max, FT q, FT rho, FT N) const {
-        return std::max(FT(0), rho * q / x_max - N) / P.sb_numadj_tau;
+        return kidm::max(FT(0), rho * q / x_max - N) / P.sb_numadj_tau;
     }
     FT number_decrease_for_mass_limit(FT x_min, FT q, FT rho, FT N) const {
-        return std::min(FT(0), rho * q / x_min - N) / P.sb_numadj_tau;
+        return kidm::min(FT(0), rho * q / x_min - N) / P.sb_numadj_tau;
     }
     // CM2.rain_evaporation(sb2006, aps, tps, q_tot, q_liq, q_ice, q_rai, q_sno, ρ, N_rai, T)
     // (Common/tendency.jl:642-644)
@@ -558,20 +565,20 @@ struct SB2006 {
             FT x_star = P.sb_xr_min;
             FT G = td.G_func_liquid(T);
             FT xr = pdf_rain(q_rai, rho, N_rai).x_r;
-            FT Dr = std::cbrt(FT(6) / FT(M_PI) / P.sb_rho_w) * std::cbrt(xr);
-            FT t_star = std::cbrt(FT(6) * x_star / xr);
+            FT Dr = kidm::cbrt(FT(6) / FT(M_PI) / P.sb_rho_w) * kidm::cbrt(xr);
+            FT t_star = kidm::cbrt(FT(6) * x_star / xr);
             FT beta = P.sb_beta;
-            FT a_vent_0 = P.sb_av * sf_gamma_inc_upper(FT(-1), t_star) / std::pow(FT(6), FT(-2) / FT(3));
+            FT a_vent_0 = P.sb_av * sf_gamma_inc_upper(FT(-1), t_star) / kidm::pow(FT(6), FT(-2) / FT(3));
             FT b_vent_0 = P.sb_bv * sf_gamma_inc_upper(FT(-0.5) + FT(1.5) * beta, t_star) /
-                          std::pow(FT(6), beta / FT(2) - FT(0.5));
-            FT a_vent_1 = P.sb_av * sf_gamma(FT(2)) / std::cbrt(FT(6));
-            FT b_vent_1 = P.sb_bv * sf_gamma(FT(2.5) + FT(1.5) * beta) / std::pow(FT(6), beta / FT(2) + FT(0.5));
-            FT N_Re = P.sb_alpha * std::pow(xr, beta) * std::sqrt(P.sb_rho0 / rho) * Dr / P.air_nu_air;
-            FT sc3 = std::cbrt(P.air_nu_air / P.air_D_vapor);
-            FT Fv0 = a_vent_0 + b_vent_0 * sc3 * std::sqrt(N_Re);
-            FT Fv1 = a_vent_1 + b_vent_1 * sc3 * std::sqrt(N_Re);
-            evap0 = std::min(FT(0), FT(2) * FT(M_PI) * G * S * N_rai * Dr * Fv0 / xr);
-            evap1 = std::min(FT(0), FT(2) * FT(M_PI) * G * S * N_rai * Dr * Fv1 / rho);
+                          kidm::pow(FT(6), beta / FT(2) - FT(0.5));
+            FT a_vent_1 = P.sb_av * sf_gamma(FT(2)) / kidm::cbrt(FT(6));
+            FT b_vent_1 = P.sb_bv * sf_gamma(FT(2.5) + FT(1.5) * beta) / kidm::pow(FT(6), beta / FT(2) + FT(0.5));
+            FT N_Re = P.sb_alpha * kidm::pow(xr, beta) * kidm::sqrt(P.sb_rho0 / rho) * Dr / P.air_nu_air;
+            FT sc3 = kidm::cbrt(P.air_nu_air / P.air_D_vapor);
+            FT Fv0 = a_vent_0 + b_vent_0 * sc3 * kidm::sqrt(N_Re);
+            FT Fv1 = a_vent_1 + b_vent_1 * sc3 * kidm::sqrt(N_Re);
+            evap0 = kidm::min(FT(0), FT(2) * FT(M_PI) * G * S * N_rai * Dr * Fv0 / xr);
+            evap1 = kidm::min(FT(0), FT(2) * FT(M_PI) * G * S * N_rai * Dr * Fv1 / rho);
             evap0 = (N_rai < eps()) ? FT(0) : evap0;
             evap1 = (q_rai < eps()) ? FT(0) : evap1;
         }
@@ -589,7 +596,7 @@ struct ARG {
     FT coeff_of_curvature(FT T) const { return FT(2) * P.arg_sigma * P.arg_M_w / P.arg_rho_w / P.arg_R / T; }
     FT critical_supersaturation(FT T, FT r_dry, FT kappa) const {
         FT A = coeff_of_curvature(T);
-        return FT(2) / std::sqrt(kappa) * std::pow(A / FT(3) / r_dry, FT(3) / FT(2));
+        return FT(2) / kidm::sqrt(kappa) * kidm::pow(A / FT(3) / r_dry, FT(3) / FT(2));
     }
     FT max_supersaturation(FT r_dry, FT stdev, FT N_mode, FT kappa, FT T, FT p, FT w, FT q_tot, FT q_liq, FT q_ice,
                            FT N_liq) const {
@@ -603,26 +610,26 @@ struct ARG {
         FT alpha = L * g * eps_m / R_m / cpm / (T * T) - g / R_m / T;
         FT gamma = R_m * T / eps_m / p_vs + eps_m * L * L / cpm / T / p;
         FT A = coeff_of_curvature(T);
-        FT zeta = FT(2) * A / FT(3) * std::sqrt(alpha * w / G);
+        FT zeta = FT(2) * A / FT(3) * kidm::sqrt(alpha * w / G);
         FT Sm = critical_supersaturation(T, r_dry, kappa);
-        FT lns = std::log(stdev);
-        FT f = P.arg_f1 * std::exp(P.arg_f2 * lns * lns);
+        FT lns = kidm::log(stdev);
+        FT f = P.arg_f1 * kidm::exp(P.arg_f2 * lns * lns);
         FT gg = P.arg_g1 + P.arg_g2 * lns;
-        FT eta = std::pow(alpha * w / G, FT(3) / FT(2)) / (FT(2) * FT(M_PI) * P.arg_rho_w * gamma * N_mode);
+        FT eta = kidm::pow(alpha * w / G, FT(3) / FT(2)) / (FT(2) * FT(M_PI) * P.arg_rho_w * gamma * N_mode);
         FT tmp = FT(1) / (Sm * Sm) *
-                 (f * std::pow(zeta / eta, P.arg_p1) + gg * std::pow(Sm * Sm / (eta + FT(3) * zeta), P.arg_p2));
-        FT S_max_ARG = FT(1) / std::sqrt(tmp);
+                 (f * kidm::pow(zeta / eta, P.arg_p1) + gg * kidm::pow(Sm * Sm / (eta + FT(3) * zeta), P.arg_p2));
+        FT S_max_ARG = FT(1) / kidm::sqrt(tmp);
         // pre-existing liquid droplets (N_ice = 0 ⇒ the ice terms vanish)
         FT rho_air = p / (R_m * T);
         FT r_liq = (N_liq > std::numeric_limits<FT>::epsilon())
-                       ? std::cbrt(rho_air * q_liq / N_liq / P.arg_rho_w / (FT(4) / FT(3) * FT(M_PI)))
+                       ? kidm::cbrt(rho_air * q_liq / N_liq / P.arg_rho_w / (FT(4) / FT(3) * FT(M_PI)))
                        : FT(0);
         FT K_l = FT(4) * FT(M_PI) * P.arg_rho_w * N_liq * r_liq * G * gamma;
         return S_max_ARG * (alpha * w) / (alpha * w + K_l * S_max_ARG);
     }
     FT total_N_activated(FT S_max, FT r_dry, FT stdev, FT N_mode, FT kappa, FT T) const {
         FT Sm = critical_supersaturation(T, r_dry, kappa);
-        FT u = FT(2) * std::log(Sm / S_max) / FT(3) / std::sqrt(FT(2)) / std::log(stdev);
+        FT u = FT(2) * kidm::log(Sm / S_max) / FT(3) / kidm::sqrt(FT(2)) / kidm::log(stdev);
         return N_mode * (FT(1) / FT(2)) * (FT(1) - sf_erf(u));
     }
 };
