@@ -175,7 +175,12 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dist = None
+    numa = {}
     if world > 1:
+        # several ranks share the host: keep each rank and its pinned staging buffers on its GPU's NUMA node
+        from kid_b200.lib import bind_to_gpu_numa_node
+        pr = torch.cuda.get_device_properties(local)
+        numa = bind_to_gpu_numa_node(f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0")
         import torch.distributed as dist
         # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -293,7 +298,8 @@ def run_ours(args):
                        "initial_condition": ("built on the device, every member its own p0 (SURVEY 8d)" if IC == "device" else
                                              "host, p0 quantised to 16 soundings"),
                        "l2": "state per GPU (%.2f GiB) is far larger than the 126 MB L2; no flush needed" % (state_bytes / 2**30),
-                       "parallelism": f"columns sharded x{world}, no collective", "state_finite": finite},
+                       "parallelism": f"columns sharded x{world}, no collective", "state_finite": finite,
+                       **({"host_numa_binding": numa} if numa else {})},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": state_bytes / e2e_steps,
                     "d2h_bytes_per_step": state_bytes / e2e_steps,

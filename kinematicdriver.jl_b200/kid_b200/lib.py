@@ -158,6 +158,30 @@ def pinned_empty(shape, dtype, lib: C.CDLL | None = None) -> np.ndarray:
     return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
+def bind_to_gpu_numa_node(pci_bus_id: str) -> dict:
+    """One process per GPU: run this process (and first-touch its page-locked staging buffers) on the CPUs of the NUMA node
+    the GPU hangs off, so that host<->device copies of several ranks do not cross the socket interconnect.
+    Returns what was done ({} if the topology is not exposed in sysfs)."""
+    try:
+        dom_bus = pci_bus_id.lower()
+        if len(dom_bus.split(":")[0]) == 8:  # CUDA prints 8 hex digits for the PCI domain, sysfs uses 4
+            dom_bus = dom_bus[4:]
+        node = int(Path(f"/sys/bus/pci/devices/{dom_bus}/numa_node").read_text())
+        if node < 0:
+            return {}
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except (OSError, ValueError):
+        return {}
+
+
 def _ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
