@@ -263,6 +263,9 @@ int choose_tile(kid_handle* h) {
     const int nz = h->cfg.nz, moist = h->cfg.moisture;
     const bool pcp = h->prm_sets != nullptr;
     int C = 32;
+    // few columns (the drivers' single-column runs): a narrower tile puts more level-warps on each column, so a stage
+    // needs fewer rounds (barriers) — one column x 128 levels is one round of 128 threads
+    while (C / 2 >= h->cfg.nc && C > 1) C /= 2;
     if (h->cfg.reserved[1] > 0) C = std::max(1, std::min(32, int(h->cfg.reserved[1])));  // tuning override
     while (C > 1) {
         size_t s = h->f64 ? h->lt->k1d_smem_d(moist, nz, C, pcp) : h->lt->k1d_smem_f(moist, nz, C, pcp);
