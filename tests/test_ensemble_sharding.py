@@ -1,0 +1,61 @@
+"""Ensemble sharding across ranks (bench.py --gpus N: contiguous column ranges, no collective): the shards of the
+hash-ordered ensemble are exactly the global ensemble, and a world_size-2 gloo job stepping its shards on the CPU oracle
+reproduces the single-process run (the only cross-rank traffic is the max-reduction of the timing)."""
+import os
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from kid_b200 import model as M
+from kid_b200.lib import COL_PRESCRIBED_ND, COL_W1
+
+KW = dict(n_elem=16, moisture_choice="NonEquilibriumMoisture", precipitation_choice="Precipitation2M")
+
+
+def test_shards_tile_the_global_ensemble():
+    full = M.k1d_ensemble_case(np.float32, nc=96, n_profiles=4, order="hash", **KW)
+    parts = [M.k1d_ensemble_case(np.float32, nc=32, n_profiles=4, order="hash", column_offset=32 * r, **KW) for r in range(3)]
+    for r, p in enumerate(parts):
+        sl = slice(32 * r, 32 * r + 32)
+        assert np.array_equal(p.Y0, full.Y0[sl]) and np.array_equal(p.ρ_dry, full.ρ_dry[sl])
+        for k in (COL_W1, COL_PRESCRIBED_ND):
+            assert np.array_equal(p.col_scalars[k], full.col_scalars[k][sl])
+    # device-built initial condition: the per-member surface pressures shard the same way
+    fd = M.k1d_ensemble_case(np.float32, nc=96, ic="device", order="hash", **KW)
+    pd = M.k1d_ensemble_case(np.float32, nc=32, ic="device", order="hash", column_offset=64, **KW)
+    assert np.array_equal(pd.device_ic["p0"], fd.device_ic["p0"][64:]) and len(np.unique(fd.device_ic["p0"])) == 96
+    # slice_columns is the same operation on an existing case
+    s = M.slice_columns(full, 32, 64)
+    assert np.array_equal(s.Y0, parts[1].Y0) and s.cfg.nc == 32
+
+
+def _rank(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.oracle import OracleHandle
+    import torch
+    nc = 8
+    case = M.k1d_ensemble_case(np.float64, nc=nc, n_profiles=2, order="hash", column_offset=rank * nc, **KW)
+    h = M.make_handle(case, OracleHandle)
+    dist.barrier()
+    h.step(0.0, 40)
+    t = torch.tensor([float(rank + 1)], dtype=torch.float64)  # stands for the per-rank elapsed time
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    assert t.item() == world
+    np.save(out + f".{rank}.npy", h.get_state())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_job_reproduces_the_single_process_ensemble(tmp_path):
+    from oracle.oracle import OracleHandle
+    out = str(tmp_path / "Y")
+    mp.spawn(_rank, args=(2, 29641, out), nprocs=2, join=True)
+    full = M.k1d_ensemble_case(np.float64, nc=16, n_profiles=2, order="hash", **KW)
+    h = M.make_handle(full, OracleHandle)
+    h.step(0.0, 40)
+    Y = h.get_state()
+    got = np.concatenate([np.load(out + f".{r}.npy") for r in range(2)])
+    assert np.array_equal(got, Y)
