@@ -330,7 +330,7 @@ def main():
     ap.add_argument("--steps-per-launch", type=int, default=10)
     ap.add_argument("--t-start", type=int, default=480, help="model time [s] at which the timed window starts")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample length (0 = skip)")
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="column chunks (handles/streams) of the end-to-end pipelined call")
+    ap.add_argument("--e2e-chunks", type=int, default=32, help="column chunks (handles/streams) of the end-to-end pipelined call")
     ap.add_argument("--ic", default="device", choices=["device", "host"], help="where the initial condition is built")
     ap.add_argument("--order", default="sorted", choices=["sorted", "hash"], help="storage order of the ensemble members")
     args = ap.parse_args()

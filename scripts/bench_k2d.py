@@ -11,7 +11,7 @@ from kid_b200 import k2d, model as M
 from kid_b200.lib import Handle
 
 ap = argparse.ArgumentParser(); ap.add_argument("--steps", type=int, default=200); ap.add_argument("--weak", action="store_true")
-ap.add_argument("--ft", default="f32")
+ap.add_argument("--ft", default="f32"); ap.add_argument("--tile-c", type=int, default=0); ap.add_argument("--nw", type=int, default=0)
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -23,7 +23,10 @@ FT = np.float32 if a.ft == "f32" else np.float64
 nx = 1024 * (world if a.weak else 1)
 kw = dict(nx=nx, nz=256, npoly=3, moisture_choice="NonEquilibriumMoisture", precipitation_choice="Precipitation2M",
           domain_width=48000.0 * (world if a.weak else 1), domain_height=3000.0)
-h = M.make_handle(k2d.k2d_case(FT, rank=rank, world=world, device=local, **kw), Handle)
+cs = k2d.k2d_case(FT, rank=rank, world=world, device=local, **kw)
+if a.tile_c: cs.cfg.reserved[1] = a.tile_c
+if a.nw: cs.cfg.reserved[0] = a.nw
+h = M.make_handle(cs, Handle)
 ring = k2d.DistributedRing(h, dist, rank, world) if world > 1 else None
 def step(t0, n):
     if ring: ring.step(t0, n)
