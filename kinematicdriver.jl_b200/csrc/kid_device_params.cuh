@@ -3,8 +3,8 @@
 // DevParams<FT> = the flat table of include/kid_params.h converted to FLOAT_TYPE, plus
 // parameter-only derived constants (Γ-function values, reciprocal exponents) that the
 // reference recomputes inside every broadcast (CloudMicrophysics evaluates SF.gamma(...) of
-// parameter sums per grid point).  One instance lives in __constant__ memory when all
-// columns share a parameter set (operands come straight from the constant bank); for
+// parameter sums per grid point).  When all columns share a parameter set the instance travels
+// as a __grid_constant__ kernel argument (operands come straight from the constant bank); for
 // per-column sets the tile kernel stages one instance per column in shared memory.
 #pragma once
 #include <cmath>

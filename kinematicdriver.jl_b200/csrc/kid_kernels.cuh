@@ -7,21 +7,23 @@
 //
 // k1d_tile_kernel: one CTA owns a TILE of C columns x all nz levels and keeps the tile's
 // state in shared memory for the whole launch (all SSPRK33 stages of `nsteps` steps), so
-// HBM sees one read and one write of the state per STEP while the rhs — thermodynamics,
+// HBM sees one read and one write of the state per LAUNCH while the rhs — thermodynamics,
 // terminal velocities, ARG activation + cloud-base search, condensation, 0M/1M/2M process
-// rates, the upwind-corrected advection/sedimentation stencil and the SSPRK33 stage combine
-// — is evaluated from shared memory/registers.  Thread (c, j) owns column c and the j-th
-// contiguous chunk of levels; a warp is 32 columns at the SAME levels, so the branches of
-// the microphysics (cloud / no cloud / rain) are warp-coherent across ensemble members.
-// The vertical stencil is a sliding window in registers (face flux carried upward); only the
-// chunk-edge values come from neighbouring threads through shared memory.
+// rates, the flux-corrected advection/sedimentation stencil and the SSPRK33 stage combine
+// — is evaluated from shared memory/registers.  Thread (c, j) serves column c; in round r it
+// works on level r·NW + j, so a warp is 32 columns at the SAME level (the microphysics
+// branches are warp-coherent across ensemble members) and every warp gets levels from all
+// parts of the column (balanced load, no serial sweep).  Per stage: pass 1 (terminal
+// velocities, activation, cloud base) -> barrier -> per round: READ phase (old neighbours ->
+// advective tendencies) -> barrier -> WRITE phase (sources + stage combine, in place).
+// DESIGN.md §3.1 has the full description.
 //
 // Replaces (reference): rhs! closures src/K1DModel/ode_utils.jl:29-73,
 // src/BoxModel/ode_utils.jl:10-22, the SSPRK33 loop of ODE.solve
 // (test/experiments/KiD_driver/run_KiD_simulation.jl:159-166).
 #pragma once
 #include <climits>
-// threads per tile CTA: Float32 fits the sweep in 64 registers (1024 threads = 32 warps per SM);
+// threads per tile CTA: the Float32 kernel fits in 64 registers (1024 threads = 32 warps per SM);
 // Float64 needs the full 128 (512 threads)
 #ifndef KID_TILE_MAXT_F32
 #define KID_TILE_MAXT_F32 1024

@@ -1,6 +1,6 @@
 // Host-side launch interface between the C ABI (kid_capi.cu) and the per-precipitation-style
 // kernel translation units (kid_inst.cu compiled once per KID_PRECIP value, so the four
-// heavy instantiation sets build in parallel and each owns its __constant__ parameter block).
+// heavy instantiation sets build in parallel).
 #pragma once
 #include <cuda_runtime.h>
 
