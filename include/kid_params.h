@@ -22,7 +22,7 @@
 #ifndef KID_PARAMS_H
 #define KID_PARAMS_H
 
-#define KID_PARAMS_VERSION 1
+#define KID_PARAMS_VERSION 2
 
 #define KID_PARAM_LIST(X)                                                      \
     /* Thermodynamics.Parameters.ThermodynamicsParameters */                   \
@@ -76,6 +76,10 @@
     X(sb_lam_min) X(sb_lam_max) X(sb_rho_w)                                    \
     /* CMP.SB2006VelType */                                                    \
     X(sb_aR) X(sb_bR) X(sb_cR) X(sb_vel_rho0)                                  \
+    /* CMP.Chen2022VelTypeRain (Chen et al. 2022, Table B1): q = exp(rho0·ρ),  \
+       a_i, a3·ρ^a3_pow, b_i - b_rho·ρ, c_i */                                 \
+    X(ch_rho0) X(ch_a1) X(ch_a2) X(ch_a3) X(ch_a3_pow)                         \
+    X(ch_b1) X(ch_b2) X(ch_b3) X(ch_b_rho) X(ch_c1) X(ch_c2) X(ch_c3)          \
     /* numerical knobs restating un-vendored ClimaCore operators */            \
     X(num_fcc_scale)
 

@@ -456,7 +456,8 @@ int kid_create(const kid_config_t* cfg, kid_handle_t** out) {
     if ((cfg->model == KID_MODEL_K1D || cfg->model == KID_MODEL_K1D_COL_SED || cfg->model == KID_MODEL_K2D) && cfg->nz < 3)
         return fail("K1DModel needs at least 3 levels (Extrapolate boundary stencils)");
     if (!(cfg->dt > 0)) return fail("dt must be positive");
-    if (cfg->sedimentation == KID_SED_CHEN2022) return fail("sedimentation Chen2022 is not implemented on the device path");
+    if (cfg->sedimentation == KID_SED_CHEN2022 && cfg->precip != KID_PRECIP_2M)
+        return fail("sedimentation Chen2022 is implemented for Precipitation2M (rain) only: the Chen2022 snow velocity of Precipitation1M is not on the device path");
     if (cfg->precip == KID_PRECIP_1M && (cfg->rain_formation < KID_RF_CLIMA_1M || cfg->rain_formation > KID_RF_VARTIMESCALE))
         return fail("invalid rain_formation for Precipitation1M");
     if (cfg->precip == KID_PRECIP_2M && cfg->rain_formation != KID_RF_SB2006 && cfg->rain_formation != KID_RF_SB2006NL)
@@ -472,6 +473,7 @@ int kid_create(const kid_config_t* cfg, kid_handle_t** out) {
     h->fsz = h->f64 ? 8 : 4;
     h->lt = table_of(cfg->precip);
     h->sw.rain_formation = cfg->rain_formation;
+    h->sw.sedimentation = cfg->sedimentation;
     h->sw.sb_limited = cfg->rain_formation != KID_RF_SB2006NL;
     h->sw.precip_sources = cfg->precip_sources;
     h->sw.precip_sinks = cfg->precip_sinks;

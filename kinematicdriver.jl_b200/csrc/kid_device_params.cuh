@@ -123,6 +123,7 @@ inline void fill_dev_params(DevParams<FT>& P, const double* table) {
 // run-time switches shared by every kernel (uniform across the grid)
 struct DevSwitches {
     int rain_formation;
+    int sedimentation;  // enum kid_sedimentation
     int sb_limited;  // CMP.SB2006(toml) vs CMP.SB2006(toml, false)
     int precip_sources, precip_sinks, open_system_activation, local_activation, qtot_flux_correction;
 };

@@ -127,9 +127,17 @@ function param_table(aux, moisture, precip; fcc_scale = 1.0)::Vector{Float64}
                            sb.pdf_c.νc, sb.pdf_c.xc_min, sb.pdf_c.xc_max, sb.pdf_r.xr_min, sb.pdf_r.xr_max,
                            limited ? sb.pdf_r.N0_min : 0, limited ? sb.pdf_r.N0_max : 0,
                            limited ? sb.pdf_r.λ_min : 0, limited ? sb.pdf_r.λ_max : 0, sb.pdf_r.ρw,
-                           vel.aR, vel.bR, vel.cR, vel.ρ0])
+                           ])
+        if vel isa CMP.Chen2022VelTypeRain   # sedimentation_choice = "Chen2022" (helper_functions.jl:69-70)
+            append!(v, z(4))
+            append!(v, Float64[vel.ρ0, vel.a[1], vel.a[2], vel.a[3], vel.a3_pow, vel.b[1], vel.b[2], vel.b[3], vel.b_ρ,
+                               vel.c[1], vel.c[2], vel.c[3]])
+        else
+            append!(v, Float64[vel.aR, vel.bR, vel.cR, vel.ρ0])
+            append!(v, z(12))
+        end
     else
-        append!(v, z(35))
+        append!(v, z(35 + 12))
     end
     push!(v, Float64(fcc_scale))  # num_fcc_scale
     return v

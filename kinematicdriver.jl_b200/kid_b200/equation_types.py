@@ -109,7 +109,8 @@ def get_precipitation_type(precipitation_choice: str, toml_dict=None, *, rain_fo
         if sedimentation_choice in ("CliMA_1M", None):
             st = "CliMA_1M"
         elif sedimentation_choice == "Chen2022":
-            raise NotImplementedError("sedimentation_choice=Chen2022 is not implemented on the device path yet")
+            raise NotImplementedError("sedimentation_choice=Chen2022 with Precipitation1M (Chen2022 snow velocity) is not "
+                                      "implemented on the device path; it is available with Precipitation2M")
         else:
             raise ValueError(f"Invalid sedimentation choice: {sedimentation_choice}")
         rf = "CliMA_1M" if rain_formation_choice is None else rain_formation_choice
@@ -120,7 +121,7 @@ def get_precipitation_type(precipitation_choice: str, toml_dict=None, *, rain_fo
         if sedimentation_choice in ("SB2006", None):
             st = "SB2006"
         elif sedimentation_choice == "Chen2022":
-            raise NotImplementedError("sedimentation_choice=Chen2022 is not implemented on the device path yet")
+            st = "Chen2022"  # CMP.Chen2022VelTypeRain (helper_functions.jl:69-70)
         else:
             raise ValueError(f"Invalid sedimentation choice: {sedimentation_choice}")
         rf = "SB2006" if rain_formation_choice is None else rain_formation_choice

@@ -12,7 +12,7 @@ from pathlib import Path
 import numpy as np
 
 KID_ABI_VERSION = 1
-KID_PARAMS_VERSION = 1
+KID_PARAMS_VERSION = 2
 
 # enum kid_model
 MODEL_BOX, MODEL_K1D, MODEL_K1D_COL_SED, MODEL_K2D = 0, 1, 2, 3

@@ -172,6 +172,19 @@ DEFAULTS: dict[str, float] = {
     "SB2006_raindrops_terminal_velocity_coeff_aR": 9.65,
     "SB2006_raindrops_terminal_velocity_coeff_bR": 10.3,
     "SB2006_raindrops_terminal_velocity_coeff_cR": 600.0,
+    # CMP.Chen2022VelTypeRain: Chen et al. (2022) Table B1
+    "Chen2022_table_B1_q_coeff": 0.115231,
+    "Chen2022_table_B1_a1_coeff": 0.044612,
+    "Chen2022_table_B1_a2_coeff": -0.263166,
+    "Chen2022_table_B1_a3_coeff": 4.7178,
+    "Chen2022_table_B1_a3_pow_coeff": -0.47335,
+    "Chen2022_table_B1_b1_coeff": 2.2955,
+    "Chen2022_table_B1_b2_coeff": 2.2955,
+    "Chen2022_table_B1_b3_coeff": 1.1451,
+    "Chen2022_table_B1_b_rho_coeff": 0.038465,
+    "Chen2022_table_B1_c1_coeff": 0.0,
+    "Chen2022_table_B1_c2_coeff": 0.184325,
+    "Chen2022_table_B1_c3_coeff": 0.184325,
     # KinematicDriver / Common (no defaults in ClimaParams: set by override_toml_dict)
     "prescribed_flow_w1": 2.0,
     "prescribed_flow_t1": 600.0,
@@ -485,7 +498,13 @@ def flatten_params(td: dict, rain_formation: str | int | None = None) -> np.ndar
              sb_aR=g("SB2006_raindrops_terminal_velocity_coeff_aR"),
              sb_bR=g("SB2006_raindrops_terminal_velocity_coeff_bR"),
              sb_cR=g("SB2006_raindrops_terminal_velocity_coeff_cR"),
-             sb_vel_rho0=g("SB2006_reference_air_density"))
+             sb_vel_rho0=g("SB2006_reference_air_density"),
+             ch_rho0=g("Chen2022_table_B1_q_coeff"), ch_a1=g("Chen2022_table_B1_a1_coeff"),
+             ch_a2=g("Chen2022_table_B1_a2_coeff"), ch_a3=g("Chen2022_table_B1_a3_coeff"),
+             ch_a3_pow=g("Chen2022_table_B1_a3_pow_coeff"), ch_b1=g("Chen2022_table_B1_b1_coeff"),
+             ch_b2=g("Chen2022_table_B1_b2_coeff"), ch_b3=g("Chen2022_table_B1_b3_coeff"),
+             ch_b_rho=g("Chen2022_table_B1_b_rho_coeff"), ch_c1=g("Chen2022_table_B1_c1_coeff"),
+             ch_c2=g("Chen2022_table_B1_c2_coeff"), ch_c3=g("Chen2022_table_B1_c3_coeff"))
     v["num_fcc_scale"] = g("flux_correction_scale")
     names = param_names()
     missing = [n for n in names if n not in v]

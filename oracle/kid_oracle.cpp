@@ -166,7 +166,10 @@ struct Model {
             for (int k = 0; k < nz; ++k) a.N_rai[k] = kidm::max(FT(0), var(Yc, L.Nr)[k]);
             for (int k = 0; k < nz; ++k) a.N_liq[k] = kidm::max(FT(0), var(Yc, L.Nl)[k]);
             for (int k = 0; k < nz; ++k)
-                sb.rain_terminal_velocity(a.q_rai[k], a.rho[k], a.N_rai[k], a.vt_N_rai[k], a.vt_rai[k]);
+                if (sw.sedimentation == KID_SED_CHEN2022)
+                    sb.rain_terminal_velocity_chen2022(a.q_rai[k], a.rho[k], a.N_rai[k], a.vt_N_rai[k], a.vt_rai[k]);
+                else
+                    sb.rain_terminal_velocity(a.q_rai[k], a.rho[k], a.N_rai[k], a.vt_N_rai[k], a.vt_rai[k]);
         }
     }
 

@@ -498,6 +498,29 @@ struct SB2006 {
         vt0 = (N_rai < eps()) ? FT(0) : kidm::max(FT(0), sr * (aR * pa0 - bR * pb0 / r1));
         vt1 = (q_rai < eps()) ? FT(0) : kidm::max(FT(0), sr * (aR * pa1 - bR * pb1 / (r1 * r1 * r1 * r1)));
     }
+    // CM2.rain_terminal_velocity(sb2006, vel::Chen2022VelTypeRain, q_rai, ρ, N_rai) -> (vt_N, vt_q)
+    // (sedimentation_choice = "Chen2022", helper_functions.jl:69-70).  Chen et al. (2022) eq. 20 with the Table B1
+    // coefficients: v_k = Σ_i a_i λ^δ Γ(b_i+δ) / (λ+c_i)^(b_i+δ) / Γ(δ), δ = k+1, k = 0 (number) and 3 (mass);
+    // a_i = a_i0·exp(ρ0 ρ) (a_3 also ·ρ^a3_pow), b_i = b_i0 - b_ρ ρ, converted from mm to m (a·1000^b, c·1000).
+    void rain_terminal_velocity_chen2022(FT q_rai, FT rho, FT N_rai, FT& vt0, FT& vt3) const {
+        FT lam = pdf_rain(q_rai, rho, N_rai).lam_r;
+        FT q = kidm::exp(P.ch_rho0 * rho);
+        FT ai[3] = {P.ch_a1 * q, P.ch_a2 * q, P.ch_a3 * q * kidm::pow(rho, P.ch_a3_pow)};
+        FT bi[3] = {P.ch_b1 - P.ch_b_rho * rho, P.ch_b2 - P.ch_b_rho * rho, P.ch_b3 - P.ch_b_rho * rho};
+        FT ci[3] = {P.ch_c1 * FT(1000), P.ch_c2 * FT(1000), P.ch_c3 * FT(1000)};
+        auto add = [&](FT a, FT b, FT c, int k) {
+            FT d = FT(k + 1);
+            return a * kidm::pow(lam, d) * FT(std::tgamma(double(b + d))) / kidm::pow(lam + c, b + d) / FT(std::tgamma(double(d)));
+        };
+        FT s0 = FT(0), s3 = FT(0);
+        for (int i = 0; i < 3; ++i) {
+            FT aiu = ai[i] * kidm::pow(FT(1000), bi[i]);
+            s0 = s0 + add(aiu, bi[i], ci[i], 0);
+            s3 = s3 + add(aiu, bi[i], ci[i], 3);
+        }
+        vt0 = (N_rai < eps()) ? FT(0) : kidm::max(FT(0), s0);
+        vt3 = (q_rai < eps()) ? FT(0) : kidm::max(FT(0), s3);
+    }
     // CM2.autoconversion(acnv, pdf_c, q_liq, q_rai, ρ, N_liq) (Common/tendency.jl:600,605)
     void autoconversion(FT q_liq, FT q_rai, FT rho, FT N_liq, FT& dq_rai_dt, FT& dN_rai_dt) const {
         dq_rai_dt = dN_rai_dt = FT(0);

@@ -462,3 +462,26 @@ def test_pipelined_ensemble_matches_single_handle():
     pipe = PipelinedEnsemble(cs, nchunks=3)
     pipe.solve(Yp, 0.0, 120)
     assert np.array_equal(Yp, ref)
+
+
+@pytest.mark.parametrize("FT", [np.float64, np.float32])
+def test_chen2022_rain_sedimentation_parity(FT):
+    """sedimentation_choice = "Chen2022" with Precipitation2M: terminal velocities, rhs and stepped state vs the oracle,
+    and a different answer than the SB2006 velocities."""
+    kw = dict(nc=8, n_profiles=2, n_elem=32, moisture_choice="NonEquilibriumMoisture", precipitation_choice="Precipitation2M")
+    cs = M.k1d_ensemble_case(FT, sedimentation_scheme_choice="Chen2022", **kw)
+    g, o = M.make_handle(cs, Handle), M.make_handle(cs, OracleHandle)
+    g.step(0.0, 900)
+    o.set_state(g.get_state())
+    for f in ("term_vel_rai", "term_vel_N_rai"):
+        a, b = g.get_aux(900.0, f), o.get_aux(900.0, f)
+        assert b.max() > 0.5 and np.abs(a - b).max() <= (1e-9 if FT is np.float64 else 2e-4) * b.max(), f
+    sb = M.make_handle(M.k1d_ensemble_case(FT, **kw), Handle)
+    sb.set_state(g.get_state())
+    assert np.abs(sb.get_aux(900.0, "term_vel_rai") - g.get_aux(900.0, "term_vel_rai")).max() > 0.05
+    g2, o2 = M.make_handle(cs, Handle), M.make_handle(cs, OracleHandle)
+    g2.step(0.0, 300)
+    o2.step(0.0, 300)
+    e = errors(g2.get_state(), o2.get_state(), cs.var_names)
+    tol = 1e-6 if FT is np.float64 else 5e-2
+    assert max(e.values()) < tol, e

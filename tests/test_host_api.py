@@ -149,3 +149,10 @@ def test_morton_order_keeps_neighbours_close_in_every_key():
         return float(np.mean(g.max(1) - g.min(1)) / (x.max() - x.min()))
     assert max(spread(a), spread(b), spread(c)) < 0.25      # close in all three keys
     assert max(spread_lex(b), spread_lex(c)) > 0.8          # a lexicographic sort only helps the first key
+
+
+def test_chen2022_is_a_2m_sedimentation_choice_only():
+    p = ET.get_precipitation_type("Precipitation2M", PR.override_toml_dict(), sedimentation_choice="Chen2022")
+    assert p.sedimentation == 2 and p.sedimentation_name == "Chen2022"
+    with pytest.raises(NotImplementedError):
+        ET.get_precipitation_type("Precipitation1M", PR.override_toml_dict(), sedimentation_choice="Chen2022")

@@ -186,3 +186,23 @@ def test_water_budget_closed_box():
         tot1 = Y1[:, n.index("ρq_liq")] + Y1[:, n.index("ρq_rai")]
         np.testing.assert_allclose(tot1, tot0, rtol=1e-12)
         assert np.all(Y1[:, n.index("ρq_rai")] > Y0[:, n.index("ρq_rai")])  # rain forms
+
+
+def test_chen2022_rain_velocity_is_a_plausible_fall_speed():
+    """No golden value exists for CM2.rain_terminal_velocity(sb2006, Chen2022VelTypeRain, ...): the restated Chen et al.
+    (2022) Table B1 fit must at least give fall speeds of the magnitude of the SB2006 ones it replaces (unit slips in the
+    mm -> m conversion of its coefficients would show as factors of 10^3b)."""
+    import numpy as np
+    from kid_b200 import model as M
+    from oracle.oracle import OracleHandle
+    kw = dict(nc=1, n_elem=48, moisture_choice="NonEquilibriumMoisture", precipitation_choice="Precipitation2M")
+    sb = M.make_handle(M.k1d_case(np.float64, **kw), OracleHandle)
+    ch = M.make_handle(M.k1d_case(np.float64, sedimentation_scheme_choice="Chen2022", **kw), OracleHandle)
+    sb.step(0.0, 1500)
+    ch.set_state(sb.get_state())
+    for f, lo, hi in (("term_vel_rai", 0.7, 1.5), ("term_vel_N_rai", 0.5, 3.0)):
+        x, y = sb.get_aux(1500.0, f)[0], ch.get_aux(1500.0, f)[0]
+        m = x > 0.1
+        assert m.any() and np.all(y >= 0) and np.all(y < 12.0)
+        r = y[m] / x[m]
+        assert lo < r.min() and r.max() < hi, (f, r.min(), r.max())
