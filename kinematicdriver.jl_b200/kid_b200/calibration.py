@@ -119,6 +119,44 @@ def kid_calibration_case(FT, model_settings: dict, cases: list[dict], u: np.ndar
     return M.with_parameter_sets(ens, overrides, column_to_set=col_member)
 
 
+def box_calibration_case(FT, model_settings: dict, cases: list[dict], u: np.ndarray, u_names: list[str]) -> M.Case:
+    """run_box_multiple_cases (calibration/KiDUtils.jl:238-261) + run_box (:263-322) for a whole ensemble: column =
+    member * n_cases + case.  A case is (qt, Nd, k); k is also the cloud gamma-distribution parameter ν of SB2006
+    (`toml_dict["SB2006_cloud_gamma_distribution_coeff_nu"] = k`, KiDUtils.jl:267), so every (member, case) pair has its
+    own parameter set."""
+    u = np.atleast_2d(np.asarray(u, dtype=np.float64))
+    if u.shape[0] != len(u_names):
+        raise ValueError("u must be [n_params, n_ensemble]")
+    ms = dict(model_settings)
+    n_ens, n_cases = u.shape[1], len(cases)
+    nc = n_ens * n_cases
+    col_case, col_member = np.arange(nc) % n_cases, np.arange(nc) // n_cases
+    kw = dict(precipitation_choice=ms.get("precipitation_choice", "Precipitation2M"),
+              rain_formation_choice=ms.get("rain_formation_choice", "SB2006"), rhod=ms.get("rhod", 1.22),
+              dt=ms.get("dt", 1.0), t_end=ms.get("t_end", 3600.0), precip_sinks=int(ms.get("precip_sinks", 0)),
+              microphys_params=dict(ms.get("toml_overrides") or {}))
+    per_case = [M.box_case(FT, nc=1, qt=c["qt"], Nd=c["Nd"], k=c["k"], **kw) for c in cases]
+    base = per_case[0]
+    import copy
+    cfg = copy.copy(base.cfg)
+    cfg.nc = nc
+    FTt = np.dtype(FT).type
+    ens = M.Case(cfg=cfg, params=base.params, ρ_dry=np.concatenate([per_case[i].ρ_dry for i in col_case]).astype(FTt),
+                 T=np.concatenate([per_case[i].T for i in col_case]).astype(FTt),
+                 Y0=np.concatenate([per_case[i].Y0 for i in col_case]).astype(FTt), var_names=base.var_names,
+                 col_scalars={COL_PRESCRIBED_ND: np.array([cases[i]["Nd"] for i in col_case], dtype=FTt)},
+                 z_centers=base.z_centers, meta=dict(base.meta, cases=cases, col_case=col_case, col_member=col_member))
+    deps = ms.get("param_dependencies") or []  # apply_param_dependency! (KiDUtils.jl:384-391)
+    overrides = []
+    for col in range(nc):
+        ov = {name: float(u[p, col_member[col]]) for p, name in enumerate(u_names)}
+        for dep in deps:
+            ov[dep["dependant"]] = ov.get(dep["base"], base.meta["toml"][dep["base"]]) * dep["ratio"]
+        ov["SB2006_cloud_gamma_distribution_parameter"] = float(cases[col_case[col]]["k"])
+        overrides.append(ov)
+    return M.with_parameter_sets(ens, overrides, column_to_set=np.arange(nc))
+
+
 def run_ensembles(u, u_names, config: dict, n_ensemble: int | None = None, FT=np.float64, backend=Handle) -> list:
     """calibration/OptimizationUtils.jl:197-211 without the ReferenceStatistics transform (a host-side linear map):
     returns [G(u[:, i]) for i in 1:n_ensemble], each the concatenation over the cases (KiDUtils.jl:45-81)."""
@@ -134,7 +172,10 @@ def run_ensembles(u, u_names, config: dict, n_ensemble: int | None = None, FT=np
     filt = make_filter_props(fcfg["nz_unfiltered"], t_calib, apply=fcfg["apply"],
                              nz_per_filtered_cell=fcfg.get("nz_per_filtered_cell"),
                              nt_per_filtered_cell=fcfg.get("nt_per_filtered_cell", 1))
-    case = kid_calibration_case(FT, ms, cases, u[:, :n_ensemble], list(u_names))
+    if ms.get("model", "KiD") == "Box":
+        case = box_calibration_case(FT, ms, cases, u[:, :n_ensemble], list(u_names))
+    else:
+        case = kid_calibration_case(FT, ms, cases, u[:, :n_ensemble], list(u_names))
     G = solve_gvector(case, variables, t_calib, filt, t_ini=float(ms.get("t_ini", 0.0)), backend=backend)
     n_cases = len(cases)
     return [G[m * n_cases:(m + 1) * n_cases].reshape(-1) for m in range(n_ensemble)]

@@ -57,3 +57,29 @@ def test_run_ensembles_on_the_oracle_backend():
     # member 0 / case 0 is the plain single-column run
     single = CAL.run_dyn_model(u[:, 0], u_names, config, backend=OracleEnsembleHandle)
     assert np.array_equal(single, G[0])
+
+
+BOX_CONFIG = {
+    "model": dict(model="Box", precipitation_choice="Precipitation2M", rain_formation_choice="SB2006", rhod=1.22, dt=1.0,
+                  t_end=1200.0, t_calib=[0.0, 600.0, 1200.0], filter=dict(apply=False, nz_unfiltered=[1, 1, 1, 1])),
+    "observations": dict(data_names=["ql", "qr", "Nl", "Nr"],
+                         cases=[dict(qt=1e-3, Nd=1e8, k=2.0), dict(qt=1.5e-3, Nd=3e8, k=4.0)]),
+}
+BOX_NAMES = ["SB2006_collection_kernel_coeff_kcc", "SB2006_collection_kernel_coeff_kcr"]
+
+
+def test_box_calibration_ensemble_on_the_oracle_backend():
+    u = np.array([[4.44e9, 6e9], [5.25, 4.0]])
+    G = CAL.run_ensembles(u, BOX_NAMES, BOX_CONFIG, 2, backend=OracleEnsembleHandle)
+    assert len(G) == 2 and G[0].shape == (2 * 3 * 4,) and np.isfinite(np.stack(G)).all()
+    case = CAL.box_calibration_case(np.float64, BOX_CONFIG["model"], BOX_CONFIG["observations"]["cases"], u, BOX_NAMES)
+    # every (member, case) pair has its own parameter set: the case's k is SB2006's cloud ν
+    assert case.params.shape[0] == 4 and list(case.column_to_set) == [0, 1, 2, 3]
+    from kid_b200.parameters import param_names
+    nu = case.params[:, param_names().index("sb_nu_c")]
+    assert list(nu) == [2.0, 4.0, 2.0, 4.0]
+    single = CAL.run_dyn_model(u[:, 1], BOX_NAMES, BOX_CONFIG, backend=OracleEnsembleHandle)
+    assert np.array_equal(single, G[1])
+    # rain forms from cloud water: ql decreases, qr increases over the run in every member/case
+    g = G[0].reshape(2, 3, 4)   # [case][time][variable]
+    assert np.all(g[:, -1, 0] < g[:, 0, 0]) and np.all(g[:, -1, 1] > g[:, 0, 1])

@@ -154,3 +154,14 @@ def test_output_pipeline_matches_synchronous_output():
         for f in fields:
             assert np.array_equal(a[f], b[f]), (t, f)
         assert a["ql_max"] == b["ql_max"]
+
+
+def test_box_calibration_ensemble_matches_the_oracle_backend():
+    from oracle.oracle import OracleEnsembleHandle
+    from test_calibration_host import BOX_CONFIG, BOX_NAMES
+    u = np.array([[4.44e9, 6e9, 3e9], [5.25, 4.0, 6.5]])
+    Gd = np.stack(CAL.run_ensembles(u, BOX_NAMES, BOX_CONFIG, 3, FT=np.float64))
+    Go = np.stack(CAL.run_ensembles(u, BOX_NAMES, BOX_CONFIG, 3, FT=np.float64, backend=OracleEnsembleHandle))
+    g, o = Gd.reshape(3, 2, 3, 4), Go.reshape(3, 2, 3, 4)  # [member][case][time][variable]
+    for v in range(4):
+        assert np.abs(g[..., v] - o[..., v]).max() <= 1e-7 * np.abs(o[..., v]).max(), v
