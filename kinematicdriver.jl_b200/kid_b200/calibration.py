@@ -87,7 +87,7 @@ def kid_calibration_case(FT, model_settings: dict, cases: list[dict], u: np.ndar
         raise ValueError("u must be [n_params, n_ensemble]")
     n_ens, n_cases = u.shape[1], len(cases)
     ms = dict(model_settings)
-    model = {"KiD": M.MODEL_K1D, "KiD_col_sed": M.MODEL_K1D_COL_SED}[ms.get("model", "KiD")]
+    model = {"KiD": M.MODEL_K1D}[ms.get("model", "KiD")]
     kw = {k: ms[k] for k in ("moisture_choice", "precipitation_choice", "rain_formation_scheme_choice",
                              "sedimentation_scheme_choice", "z_min", "z_max", "n_elem", "dt", "t_end", "t1",
                              "precip_sources", "precip_sinks", "open_system_activation", "local_activation",
@@ -157,6 +157,39 @@ def box_calibration_case(FT, model_settings: dict, cases: list[dict], u: np.ndar
     return M.with_parameter_sets(ens, overrides, column_to_set=np.arange(nc))
 
 
+def col_sed_calibration_case(FT, model_settings: dict, cases: list[dict], u: np.ndarray, u_names: list[str]) -> M.Case:
+    """run_KiD_col_sed_multiple_cases + run_KiD_col_sed (calibration/KiDUtils.jl:155-236) for a whole ensemble: column =
+    member * n_cases + case; a case is (qt, Nd, k), the initial condition is initial_condition_0d at every level and k is
+    also SB2006's cloud ν, so every (member, case) pair has its own parameter set."""
+    u = np.atleast_2d(np.asarray(u, dtype=np.float64))
+    if u.shape[0] != len(u_names):
+        raise ValueError("u must be [n_params, n_ensemble]")
+    ms = dict(model_settings)
+    n_ens, n_cases = u.shape[1], len(cases)
+    nc = n_ens * n_cases
+    col_case, col_member = np.arange(nc) % n_cases, np.arange(nc) // n_cases
+    kw = {k: ms[k] for k in ("precipitation_choice", "rain_formation_choice", "sedimentation_choice", "rhod", "z_min",
+                             "z_max", "n_elem", "dt", "t_end", "precip_sinks", "toml_overrides") if k in ms}
+    base = M.col_sed_case(FT, nc=nc, qt=[cases[i]["qt"] for i in col_case], prescribed_Nd=[cases[i]["Nd"] for i in col_case],
+                          k=cases[0]["k"], **kw)
+    base.meta.update(cases=cases, col_case=col_case, col_member=col_member)
+    deps = ms.get("param_dependencies") or []
+    overrides = []
+    for col in range(nc):
+        ov = {name: float(u[p, col_member[col]]) for p, name in enumerate(u_names)}
+        for dep in deps:
+            ov[dep["dependant"]] = ov.get(dep["base"], base.meta["toml"][dep["base"]]) * dep["ratio"]
+        ov["SB2006_cloud_gamma_distribution_parameter"] = float(cases[col_case[col]]["k"])
+        overrides.append(ov)
+    # the gamma initial condition depends on k as well: rebuild the state of the columns whose case has another k
+    ks = np.array([cases[i]["k"] for i in col_case], dtype=np.float64)
+    if np.unique(ks).size > 1:
+        full = M.col_sed_case(FT, nc=nc, qt=[cases[i]["qt"] for i in col_case],
+                              prescribed_Nd=[cases[i]["Nd"] for i in col_case], k=ks, **kw)
+        base.Y0, base.ρ_dry, base.T = full.Y0, full.ρ_dry, full.T
+    return M.with_parameter_sets(base, overrides, column_to_set=np.arange(nc))
+
+
 def run_ensembles(u, u_names, config: dict, n_ensemble: int | None = None, FT=np.float64, backend=Handle) -> list:
     """calibration/OptimizationUtils.jl:197-211 without the ReferenceStatistics transform (a host-side linear map):
     returns [G(u[:, i]) for i in 1:n_ensemble], each the concatenation over the cases (KiDUtils.jl:45-81)."""
@@ -174,6 +207,8 @@ def run_ensembles(u, u_names, config: dict, n_ensemble: int | None = None, FT=np
                              nt_per_filtered_cell=fcfg.get("nt_per_filtered_cell", 1))
     if ms.get("model", "KiD") == "Box":
         case = box_calibration_case(FT, ms, cases, u[:, :n_ensemble], list(u_names))
+    elif ms.get("model", "KiD") == "KiD_col_sed":
+        case = col_sed_calibration_case(FT, ms, cases, u[:, :n_ensemble], list(u_names))
     else:
         case = kid_calibration_case(FT, ms, cases, u[:, :n_ensemble], list(u_names))
     G = solve_gvector(case, variables, t_calib, filt, t_ini=float(ms.get("t_ini", 0.0)), backend=backend)

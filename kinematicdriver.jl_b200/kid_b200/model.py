@@ -186,6 +186,61 @@ def box_case(FT=np.float64, nc: int = 1, device: int = 0, precipitation_choice="
                 meta=dict(toml=td, moisture=moisture, precip=precip, TS=TimeStepping(dt, dt_output, t_end)))
 
 
+def col_sed_case(FT=np.float64, nc: int = 1, device: int = 0, precipitation_choice="Precipitation2M",
+                 rain_formation_choice=None, sedimentation_choice=None, qt=1e-3, prescribed_Nd=1e8, k=2.0, rhod=1.0,
+                 z_min=0.0, z_max=3000.0, n_elem=60, dt=1.0, dt_output=30.0, t_ini=0.0, t_end=3600.0,
+                 precip_sinks=0, toml_overrides=None) -> Case:
+    """test/experiments/KiD_col_sed_driver/run_KiD_col_sed_simulation.jl:13-128 (and calibration/KiDUtils.jl:181-236):
+    the 1-D column with collisions + sedimentation only (make_rhs_function_col_sed); the initial condition is the box
+    model's gamma-distribution state (initial_condition_0d) at EVERY level; qt, prescribed_Nd, k may be arrays of
+    length nc (ensemble of cases).  k is also SB2006's cloud ν, so columns with different k get their own parameter set."""
+    FT = np.dtype(FT).type
+    qt_a = np.broadcast_to(np.asarray(qt, dtype=np.float64), (nc,))
+    Nd_a = np.broadcast_to(np.asarray(prescribed_Nd, dtype=np.float64), (nc,))
+    k_a = np.broadcast_to(np.asarray(k, dtype=np.float64), (nc,))
+    td = PR.override_toml_dict(FT=FT, precip_sources=1, precip_sinks=precip_sinks, prescribed_Nd=float(Nd_a[0]))
+    td["SB2006_cloud_gamma_distribution_parameter"] = float(k_a[0])
+    for kk, v in (toml_overrides or {}).items():
+        if kk not in td:
+            raise KeyError(f"unknown ClimaParams name {kk}")
+        td[kk] = v
+    common_params = PR.create_common_parameters(td)
+    kid_params = PR.create_kid_parameters(td)
+    thermo_params = PR.create_thermodynamics_parameters(td)
+    moisture = ET.get_moisture_type("NonEquilibriumMoisture", td)
+    precip = ET.get_precipitation_type(precipitation_choice, td, rain_formation_choice=rain_formation_choice,
+                                       sedimentation_choice=sedimentation_choice)
+    names = ET.state_variable_names(moisture, precip)
+    nz = int(n_elem)
+    zc, _ = make_function_space(FT, z_min, z_max, nz)
+    Y0 = np.zeros((nc, len(names), nz), dtype=FT)
+    ρ_dry = np.zeros((nc, nz), dtype=FT)
+    T = np.zeros((nc, nz), dtype=FT)
+    cache = {}
+    for c in range(nc):
+        key = (qt_a[c], Nd_a[c], k_a[c])
+        if key not in cache:
+            cache[key] = IC.initial_condition_0d(FT, thermo_params, qt_a[c], Nd_a[c], k_a[c], rhod)
+        ip = cache[key]
+        Y0[c] = np.array([ip[n] for n in names], dtype=FT)[:, None]
+        ρ_dry[c], T[c] = ip["ρ_dry"], ip["T"]
+    cfg = make_config(
+        model=MODEL_K1D_COL_SED, moisture=moisture.kid_enum, precip=precip.kid_enum, rain_formation=precip.rain_formation,
+        sedimentation=precip.sedimentation, float_type=float_enum(FT), nz=nz, nc=nc,
+        precip_sources=int(common_params.precip_sources), precip_sinks=int(common_params.precip_sinks),
+        open_system_activation=0, local_activation=0, qtot_flux_correction=int(kid_params.qtot_flux_correction),
+        device=device, z_min=float(z_min), z_max=float(z_max), dt=float(dt))
+    case = Case(cfg=cfg, params=PR.flatten_params(td, precip.rain_formation), ρ_dry=ρ_dry, T=T, Y0=Y0, var_names=names,
+                col_scalars={COL_PRESCRIBED_ND: Nd_a.astype(FT), COL_Q_SURF: np.zeros(nc, dtype=FT)}, z_centers=zc,
+                meta=dict(toml=td, moisture=moisture, precip=precip, TS=TimeStepping(dt, dt_output, t_end),
+                          opts=dict(t_ini=t_ini, t_end=t_end, dt=dt, dt_output=dt_output)))
+    ks = np.unique(k_a)
+    if ks.size > 1:  # one parameter set per distinct k
+        case = with_parameter_sets(case, [{"SB2006_cloud_gamma_distribution_parameter": float(x)} for x in ks],
+                                   column_to_set=np.searchsorted(ks, k_a))
+    return case
+
+
 def apply_case(handle, case: Case):
     """Upload a Case into a backend handle (order matters: params and profiles before the state)."""
     handle.set_params(case.params, case.column_to_set)

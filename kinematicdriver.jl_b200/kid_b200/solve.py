@@ -182,6 +182,19 @@ def run_box_simulation(FT, opts: dict | None = None, nc: int = 1, backend=Handle
     return solve(case, (o["t_ini"], o["t_end"]), dt=o["dt"], saveat=o["dt_output"], backend=backend)
 
 
+def run_KiD_col_sed_simulation(FT, opts: dict | None = None, nc: int = 1, backend=Handle):
+    """test/experiments/KiD_col_sed_driver/run_KiD_col_sed_simulation.jl:13-146 (minus NetCDF/plots), with the script's
+    option names (qt, prescribed_Nd, k, rhod, precipitation_choice, rain_formation_choice, sedimentation_choice, z_min,
+    z_max, n_elem, dt, dt_output, t_ini, t_end)."""
+    o = dict(precipitation_choice="Precipitation2M", rain_formation_choice=None, sedimentation_choice=None)
+    o.update(opts or {})
+    if o["precipitation_choice"] == "CloudyPrecip":
+        raise NotImplementedError("CloudyPrecip is outside the device hot path of libkid_cuda.so and there is no CPU fallback")
+    case = M.col_sed_case(FT, nc=nc, **o)
+    oo = case.meta["opts"]
+    return solve(case, (oo["t_ini"], oo["t_end"]), dt=oo["dt"], saveat=oo["dt_output"], backend=backend)
+
+
 def run_K2D_simulation(FT, opts: dict | None = None, backend=Handle):
     """test/experiments/Ki2D_driver/run_kinematic2d_simulations.jl:15-171 (single-domain, minus NetCDF/plots)."""
     o = dict(opts or {})

@@ -83,3 +83,29 @@ def test_box_calibration_ensemble_on_the_oracle_backend():
     # rain forms from cloud water: ql decreases, qr increases over the run in every member/case
     g = G[0].reshape(2, 3, 4)   # [case][time][variable]
     assert np.all(g[:, -1, 0] < g[:, 0, 0]) and np.all(g[:, -1, 1] > g[:, 0, 1])
+
+
+def test_col_sed_driver_and_calibration_on_the_oracle_backend():
+    """KiD_col_sed: initial_condition_0d at every level, collisions + sedimentation only (run_KiD_col_sed_simulation.jl,
+    calibration/KiDUtils.jl:155-236)."""
+    from kid_b200.solve import run_KiD_col_sed_simulation
+    from oracle.oracle import OracleHandle
+    sol = run_KiD_col_sed_simulation(np.float64, dict(n_elem=12, z_max=1200.0, t_end=120.0, dt=2.0, dt_output=60.0),
+                                     backend=OracleHandle)
+    assert sol.t == [0.0, 60.0, 120.0]
+    l0, r1 = sol.variable("ρq_liq")[0, 0], sol.variable("ρq_rai")[-1, 0]
+    assert np.allclose(l0, l0[0]) and l0[0] > 0              # the same gamma-distribution state at every level
+    assert r1.max() > 0 and np.isfinite(sol.u[-1]).all()     # collisions produce rain, which sediments
+    config = {
+        "model": dict(model="KiD_col_sed", precipitation_choice="Precipitation2M", rain_formation_choice="SB2006",
+                      sedimentation_choice="SB2006", rhod=1.0, z_min=0.0, z_max=1200.0, n_elem=12, dt=2.0, t_end=120.0,
+                      t_calib=[0.0, 60.0, 120.0], filter=dict(apply=False, nz_unfiltered=[12, 12])),
+        "observations": dict(data_names=["qr", "Nr"], cases=[dict(qt=1e-3, Nd=1e8, k=2.0), dict(qt=2e-3, Nd=2e8, k=3.0)]),
+    }
+    u = np.array([[4.44e9, 6e9]])
+    G = CAL.run_ensembles(u, ["SB2006_collection_kernel_coeff_kcc"], config, 2, backend=OracleEnsembleHandle)
+    assert len(G) == 2 and G[0].shape == (2 * 3 * 2 * 12,) and np.isfinite(np.stack(G)).all()
+    case = CAL.col_sed_calibration_case(np.float64, config["model"], config["observations"]["cases"], u,
+                                        ["SB2006_collection_kernel_coeff_kcc"])
+    assert case.cfg.model == M.MODEL_K1D_COL_SED and case.params.shape[0] == 4
+    assert not np.allclose(case.Y0[0], case.Y0[1])  # the cases differ in qt, Nd and k

@@ -165,3 +165,26 @@ def test_box_calibration_ensemble_matches_the_oracle_backend():
     g, o = Gd.reshape(3, 2, 3, 4), Go.reshape(3, 2, 3, 4)  # [member][case][time][variable]
     for v in range(4):
         assert np.abs(g[..., v] - o[..., v]).max() <= 1e-7 * np.abs(o[..., v]).max(), v
+
+
+def test_col_sed_driver_and_calibration_match_the_oracle_backend():
+    from kid_b200.solve import run_KiD_col_sed_simulation
+    from oracle.oracle import OracleEnsembleHandle, OracleHandle
+    opts = dict(n_elem=24, z_max=2400.0, t_end=300.0, dt=2.0, dt_output=150.0, sedimentation_choice="Chen2022")
+    a = run_KiD_col_sed_simulation(np.float64, opts, nc=2)
+    b = run_KiD_col_sed_simulation(np.float64, opts, nc=2, backend=OracleHandle)
+    for ua, ub in zip(a.u, b.u):
+        assert np.abs(ua - ub).max() <= 1e-7 * np.abs(ub).max()
+    config = {
+        "model": dict(model="KiD_col_sed", precipitation_choice="Precipitation2M", rain_formation_choice="SB2006",
+                      sedimentation_choice="SB2006", rhod=1.0, z_min=0.0, z_max=1200.0, n_elem=12, dt=2.0, t_end=240.0,
+                      t_calib=[0.0, 120.0, 240.0], filter=dict(apply=False, nz_unfiltered=[12, 12])),
+        "observations": dict(data_names=["qr", "Nr"], cases=[dict(qt=1e-3, Nd=1e8, k=2.0), dict(qt=2e-3, Nd=2e8, k=3.0)]),
+    }
+    u = np.array([[4.44e9, 6e9]])
+    names = ["SB2006_collection_kernel_coeff_kcc"]
+    Gd = np.stack(CAL.run_ensembles(u, names, config, 2))
+    Go = np.stack(CAL.run_ensembles(u, names, config, 2, backend=OracleEnsembleHandle))
+    g, o = Gd.reshape(2, 2, 3, 2, 12), Go.reshape(2, 2, 3, 2, 12)  # [member][case][time][variable][level]
+    for v in range(2):
+        assert np.abs(g[:, :, :, v] - o[:, :, :, v]).max() <= 1e-6 * np.abs(o[:, :, :, v]).max(), v
