@@ -485,3 +485,18 @@ def test_chen2022_rain_sedimentation_parity(FT):
     e = errors(g2.get_state(), o2.get_state(), cs.var_names)
     tol = 1e-6 if FT is np.float64 else 5e-2
     assert max(e.values()) < tol, e
+
+
+def test_checkpoint_restart_is_bitwise():
+    """kid_get_state + kid_set_state on a fresh handle resume a K1D run exactly (restart for free)."""
+    cs = M.k1d_ensemble_case(np.float32, nc=40, n_profiles=3, n_elem=128, moisture_choice="NonEquilibriumMoisture",
+                             precipitation_choice="Precipitation2M")
+    a = M.make_handle(cs, Handle)
+    a.step(0.0, 240)
+    b = M.make_handle(cs, Handle)
+    b.step(0.0, 100)
+    ckpt = b.get_state()
+    c = M.make_handle(cs, Handle)
+    c.set_state(ckpt)
+    c.step(100.0, 140)
+    assert np.array_equal(a.get_state(), c.get_state())
