@@ -38,6 +38,16 @@ template <class FT> constexpr int tile_max_threads() { return sizeof(FT) == 4 ? 
 
 #include "kid_physics.cuh"
 
+// -DKID_DEBUG_BOUNDS (make debug): device-side asserts on the shared-memory rows the tile kernel addresses — the
+// stand-in for compute-sanitizer's memcheck on the hand-computed tile/stash indices (scripts/all_kernels_smoke.py runs
+// every kernel family against such a build).
+#ifdef KID_DEBUG_BOUNDS
+#include <cassert>
+#define KID_ASSERT_ROW(row, nrows) assert((row) >= 0 && (row) < (nrows))
+#else
+#define KID_ASSERT_ROW(row, nrows) ((void)0)
+#endif
+
 namespace kid {
 
 // compile-time loop: f(std::integral_constant<int, I>) for I in [0, N)
@@ -421,6 +431,8 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                     row_c = row(kc);
                     row_l = row(kc - 1);
                 }
+                KID_ASSERT_ROW(row_c, nz + 4); KID_ASSERT_ROW(row_l, nz + 4); KID_ASSERT_ROW(kc + 1, nz);
+                KID_ASSERT_ROW(kc - 1, nz); KID_ASSERT_ROW(c, C);
                 const FT* c_p = Ys + row_c * C + c;      // + variable · sV
                 const FT* l_p = Ys + row_l * C + c;
                 const FT* u_p = Ys + (kc + 1) * C + c;
@@ -488,6 +500,8 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                     static_for<0, NADV>([&](auto I) {
                         constexpr int i = decltype(I)::value;
                         constexpr int vi = adv_entry<MOIST, PRECIP>(i).idx;
+                        KID_ASSERT_ROW(nz + 2 * ((r + 1) & 1) + (NW - 1 - j), nz + 4);
+                        KID_ASSERT_ROW(nz + 2 * ((r + 1) & 1) + (NW - 1 - j) - nz, 4);
                         Ys[vi * sV + (nz + 2 * ((r + 1) & 1) + (NW - 1 - j)) * C + c] = Ys[sidx(vi, k)];
                     });
                 }
@@ -544,6 +558,7 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                     for (int v = 0; v < NV; ++v) {
                         const FT u = (stage == 0) ? y[v] : un[v];
                         const FT yn = rk_a * u + (rk_b * y[v] + rk_c * tend[v]);
+                        KID_ASSERT_ROW(k, nz);
                         Ys[sidx(v, k)] = yn;
                         if (stage == 2) gY[v * plane] = yn;
                     }
