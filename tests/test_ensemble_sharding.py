@@ -59,3 +59,24 @@ def test_two_rank_gloo_job_reproduces_the_single_process_ensemble(tmp_path):
     Y = h.get_state()
     got = np.concatenate([np.load(out + f".{r}.npy") for r in range(2)])
     assert np.array_equal(got, Y)
+
+
+def test_reordering_columns_does_not_change_any_member():
+    """warp_coherent_order + reorder_columns + inverse_permutation: results come back in the caller's order, unchanged."""
+    from oracle.oracle import OracleHandle
+    case = M.k1d_ensemble_case(np.float64, nc=24, n_profiles=3, order="hash", **KW)
+    perm = M.warp_coherent_order(case)
+    assert sorted(perm.tolist()) == list(range(24)) and not np.array_equal(perm, np.arange(24))
+    ordered = M.reorder_columns(case, perm)
+    a, b = M.make_handle(case, OracleHandle), M.make_handle(ordered, OracleHandle)
+    a.step(0.0, 60)
+    b.step(0.0, 60)
+    assert np.array_equal(b.get_state()[M.inverse_permutation(perm)], a.get_state())
+    # neighbours of the ordered ensemble are similar in every distinguishing scalar
+    w = np.asarray(ordered.col_scalars[COL_W1], dtype=np.float64)
+    assert np.abs(np.diff(w)).mean() < 0.5 * np.abs(np.diff(np.asarray(case.col_scalars[COL_W1], dtype=np.float64))).mean()
+    # device-built initial conditions reorder their per-member surface pressure too
+    dcase = M.k1d_ensemble_case(np.float32, nc=64, ic="device", order="hash", **KW)
+    dperm = M.warp_coherent_order(dcase)
+    dord = M.reorder_columns(dcase, dperm)
+    assert np.array_equal(dord.device_ic["p0"], dcase.device_ic["p0"][dperm])
