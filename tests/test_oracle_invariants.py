@@ -206,3 +206,27 @@ def test_chen2022_rain_velocity_is_a_plausible_fall_speed():
         assert m.any() and np.all(y >= 0) and np.all(y < 12.0)
         r = y[m] / x[m]
         assert lo < r.min() and r.max() < hi, (f, r.min(), r.max())
+
+
+def test_precipitation_susceptibility_to_droplet_number():
+    """test/test_precip_production.jl (a plot in the reference, not an assertion): the precipitation-production metric
+    Σ_t ρq_rai at the cloud-base level of the default KiD 2M/SB2006 run falls with the prescribed droplet number, with a
+    log-log slope of about -2 at high Nd (Glassmeier & Lohmann).  Here: all Nd as ONE ensemble, on the oracle."""
+    import numpy as np
+    from kid_b200 import model as M
+    from kid_b200.lib import COL_PRESCRIBED_ND
+    from oracle.oracle import OracleHandle
+    Nd = np.linspace(1e5, 1e8, 10)  # Nd_range of the reference script
+    case = M.k1d_case(np.float64, nc=10, moisture_choice="EquilibriumMoisture", precipitation_choice="Precipitation2M",
+                      rain_formation_scheme_choice="SB2006")
+    case.col_scalars[COL_PRESCRIBED_ND] = Nd
+    case.Y0[:, case.var_names.index("N_aer"), :] = Nd[:, None] * case.ρ_dry[None, :] / 1.225
+    o = M.make_handle(case, OracleHandle)
+    ir, cloud_base = case.var_names.index("ρq_rai"), 75 - 1  # Julia's 1-based level 75
+    P = o.get_state()[:, ir, cloud_base].astype(np.float64)
+    for i in range(120):  # saveat = dt_output = 30 s up to t_end = 3600 s
+        o.step(i * 30.0, 30)
+        P += o.get_state()[:, ir, cloud_base]
+    assert np.all(np.diff(P) < 0)                     # more droplets, less rain
+    slope = np.log(P[-1] / P[5]) / np.log(Nd[-1] / Nd[5])
+    assert -3.5 < slope < -1.0, slope                 # ≈ -2 at the polluted end
