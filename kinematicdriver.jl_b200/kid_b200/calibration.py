@@ -219,3 +219,76 @@ def run_ensembles(u, u_names, config: dict, n_ensemble: int | None = None, FT=np
 def run_dyn_model(u, u_names, config: dict, FT=np.float64, backend=Handle) -> np.ndarray:
     """calibration/KiDUtils.jl:10-43 with RS = nothing: the G vector of one parameter vector."""
     return run_ensembles(np.asarray(u, dtype=np.float64).reshape(-1, 1), u_names, config, 1, FT=FT, backend=backend)[0]
+
+
+# ------------------------------------------------------------------ G-vector bookkeeping and diagnostics (host, small)
+def get_numbers_from_config(config: dict) -> dict:
+    """calibration/HelperFuncs.jl:49-68."""
+    ms, cases = config["model"], config["observations"]["cases"]
+    f = ms["filter"]
+    n_heights = list(f["nz_filtered"] if f["apply"] else f["nz_unfiltered"])
+    n_default = len(ms["t_calib"]) - 1 if f["apply"] else len(ms["t_calib"])
+    n_times = [(len(c["t_cal"]) - 1 if f["apply"] else len(c["t_cal"])) if "t_cal" in c else n_default for c in cases]
+    assert len(n_heights) == len(config["observations"]["data_names"])
+    return dict(n_cases=len(cases), n_heights=n_heights, n_times=n_times)
+
+
+def get_case_i_vec(vec: np.ndarray, i: int, n_single_case) -> np.ndarray:
+    """calibration/HelperFuncs.jl:70-72 (i is 0-based here)."""
+    a = int(np.sum(n_single_case[:i]))
+    return np.asarray(vec)[a:a + int(n_single_case[i])]
+
+
+def get_single_case_fields(vec_single_case: np.ndarray, n_heights, n_times: int) -> tuple:
+    """calibration/HelperFuncs.jl:74-89: one [n_heights[j], n_times] array per variable."""
+    n_single_time = int(np.sum(n_heights))
+    if len(vec_single_case) != n_times * n_single_time:
+        raise ValueError("Inconsistent vector size and provided numbers!")
+    m = np.asarray(vec_single_case).reshape(n_times, n_single_time).T  # Julia's column-major reshape
+    offs = np.concatenate([[0], np.cumsum(n_heights)])
+    return tuple(m[offs[j]:offs[j + 1], :] for j in range(len(n_heights)))
+
+
+def _path_integral(vec, config, name: str):
+    names = config["observations"]["data_names"]
+    assert {"rho", name} <= set(names)
+    n = get_numbers_from_config(config)
+    i_rho, i_q = names.index("rho"), names.index(name)
+    dz = (config["model"]["z_max"] - config["model"]["z_min"]) / n["n_heights"][i_rho]
+    n_single = [int(np.sum(n["n_heights"])) * t for t in n["n_times"]]
+    out = []
+    for i in range(n["n_cases"]):
+        f = get_single_case_fields(get_case_i_vec(vec, i, n_single), n["n_heights"], n["n_times"][i])
+        out.append(np.sum(f[i_q] * f[i_rho], axis=0, keepdims=True) * dz)
+    return out
+
+
+def liquid_water_path(vec, config):
+    """calibration/Diagnostics.jl:11-32 [kg/m^2], one [1, n_times] array per case."""
+    return _path_integral(vec, config, "ql")
+
+
+def rainwater_path(vec, config):
+    """calibration/Diagnostics.jl:44-65."""
+    return _path_integral(vec, config, "qr")
+
+
+def rainrate(vec, config, height: float = 0.0):
+    """calibration/Diagnostics.jl:78-103 [mm/hr]: linear interpolation / extrapolation of the rainrate profile to `height`."""
+    names = config["observations"]["data_names"]
+    assert "rainrate" in names
+    n = get_numbers_from_config(config)
+    i_rr = names.index("rainrate")
+    nh = n["n_heights"][i_rr]
+    dz = (config["model"]["z_max"] - config["model"]["z_min"]) / nh
+    ind_z1 = min(nh - 1, max(1, int(np.ceil((height - config["model"]["z_min"]) / dz - 0.5))))  # 1-based, as in Julia
+    ind_z2 = ind_z1 + 1
+    a1 = ((ind_z2 - 0.5) * dz - height) / dz
+    a2 = (height - (ind_z1 - 0.5) * dz) / dz
+    n_single = [int(np.sum(n["n_heights"])) * t for t in n["n_times"]]
+    out = []
+    for i in range(n["n_cases"]):
+        f = get_single_case_fields(get_case_i_vec(vec, i, n_single), n["n_heights"], n["n_times"][i])
+        r = a1 * f[i_rr][ind_z1 - 1, :] + a2 * f[i_rr][ind_z2 - 1, :]
+        out.append(np.where(r < 0, 0.0, r))
+    return out

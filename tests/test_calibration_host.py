@@ -109,3 +109,73 @@ def test_col_sed_driver_and_calibration_on_the_oracle_backend():
                                         ["SB2006_collection_kernel_coeff_kcc"])
     assert case.cfg.model == M.MODEL_K1D_COL_SED and case.params.shape[0] == 4
     assert not np.allclose(case.Y0[0], case.Y0[1])  # the cases differ in qt, Nd and k
+
+
+# ---- the reference's own calibration tests, with its test configuration (calibration/tests/config.jl:40-112)
+def _reference_test_config():
+    t_calib = list(np.arange(0.0, 1200.0 + 1e-9, 300.0))
+    model = dict(model="KiD", moisture_choice="NonEquilibriumMoisture", precipitation_choice="Precipitation1M",
+                 rain_formation_choice="CliMA_1M", sedimentation_choice="CliMA_1M", precip_sources=True, precip_sinks=True,
+                 z_min=0.0, z_max=3000.0, n_elem=10, dt=10.0, t_ini=0.0, t_end=1200.0, t_calib=t_calib, t1=600.0,
+                 qtot_flux_correction=False, open_system_activation=False, local_activation=False, r_dry=0.04e-6,
+                 std_dry=1.4, κ=0.9, filter=dict(apply=False, nz_unfiltered=[10, 10]))
+    obs = dict(data_names=["rl", "qr"], cases=[dict(w1=2.0, p0=99000.0, Nd=50e6), dict(w1=3.0, p0=99000.0, Nd=50e6)])
+    return {"model": model, "observations": obs}
+
+
+def test_reference_known_answer_make_filter():
+    """calibration/tests/test_helper_funcs.jl:23-37 ("make filter")."""
+    f = CAL.make_filter_props([10], [0, 100, 500], apply=True, nz_per_filtered_cell=[2], nt_per_filtered_cell=2)
+    assert f["apply"] is True and list(f["nz_filtered"]) == [5] and f["nt_filtered"] == 2
+    assert list(f["saveat_t"]) == [25.0, 75.0, 200.0, 400.0]
+
+
+def test_reference_run_kid_and_gvector_shapes():
+    """calibration/tests/test_KiD_utils.jl:41-78 ("Run KiD") and :80-112 (multiple cases / run_dyn_model): the lengths the
+    reference asserts, and G of all cases = concatenation of the per-case G vectors."""
+    cfg = _reference_test_config()
+    u, u_names = np.array([1e-4]), ["cloud_liquid_water_specific_humidity_autoconversion_threshold"]
+    n_elem, n_times, n_cases = 10, 5, 2
+    one = dict(cfg, observations=dict(cfg["observations"], cases=cfg["observations"]["cases"][:1], data_names=["rlr", "rv"]))
+    G = CAL.run_dyn_model(u, u_names, one, backend=OracleEnsembleHandle)
+    assert G.shape == (2 * n_elem * n_times,)                       # length(G) == sum(n_heights) * n_times
+    filt = dict(apply=True, nz_unfiltered=[n_elem, n_elem], nz_per_filtered_cell=[2, 5], nt_per_filtered_cell=5)
+    onef = dict(one, model=dict(one["model"], filter=filt))
+    Gf = CAL.run_dyn_model(u, u_names, onef, backend=OracleEnsembleHandle)
+    assert Gf.shape == ((5 + 2) * (n_times - 1),)                    # sum(nz_filtered) * (n_times - 1)
+    G_all = CAL.run_dyn_model(u, u_names, cfg, backend=OracleEnsembleHandle)
+    assert G_all.shape == (n_elem * n_times * 2 * n_cases,)         # n_heights * n_times * n_vars * n_cases
+    first = dict(cfg, observations=dict(cfg["observations"], cases=cfg["observations"]["cases"][:1]))
+    G_1 = CAL.run_dyn_model(u, u_names, first, backend=OracleEnsembleHandle)
+    assert np.array_equal(G_all[:G_1.size], G_1) and np.isfinite(G_all).all()
+
+
+def test_reference_diagnostics_lwp_rwp_rainrate():
+    """calibration/tests/test_diagnostics.jl:1-52, with the same random-vector construction."""
+    cfg = _reference_test_config()
+    cfg["observations"]["data_names"] = ["rho", "ql", "qr", "rainrate"]
+    cfg["model"]["filter"] = CAL.make_filter_props([10] * 4, cfg["model"]["t_calib"])
+    n = CAL.get_numbers_from_config(cfg)
+    assert n["n_cases"] == 2 and n["n_heights"] == [10] * 4 and n["n_times"] == [5, 5]
+    n_single = [sum(n["n_heights"]) * t for t in n["n_times"]]
+    vec = np.random.default_rng(0).random(sum(n_single))
+    dz = 3000.0 / 10
+    lwp, rwp, rr = [], [], []
+    for i in range(2):
+        f = CAL.get_single_case_fields(CAL.get_case_i_vec(vec, i, n_single), n["n_heights"], n["n_times"][i])
+        lwp.append(np.sum(f[1] * f[0], axis=0, keepdims=True) * dz)
+        rwp.append(np.sum(f[2] * f[0], axis=0, keepdims=True) * dz)
+        r0 = 1.5 * f[3][0, :] - 0.5 * f[3][1, :]
+        rr.append(np.where(r0 < 0, 0.0, r0))
+    for a, b in ((CAL.liquid_water_path(vec, cfg), lwp), (CAL.rainwater_path(vec, cfg), rwp), (CAL.rainrate(vec, cfg, 0.0), rr)):
+        assert all(np.allclose(x, y, rtol=1e-15, atol=0) for x, y in zip(a, b))
+    cfg["observations"]["data_names"] = ["rho", "ql", "qr"]
+    with pytest.raises(AssertionError):
+        CAL.rainrate(vec, cfg, 0.0)
+    cfg["observations"]["data_names"] = ["ql", "qr", "rainrate"]
+    with pytest.raises(AssertionError):
+        CAL.liquid_water_path(vec, cfg)
+    # the field layout is the one solve_gvector / kid_obs_get produce: [time][variable][level] per case
+    g = np.arange(2 * (3 + 1), dtype=float)   # 2 times x (3 + 1) heights
+    f = CAL.get_single_case_fields(g, [3, 1], 2)
+    assert f[0].tolist() == [[0, 4], [1, 5], [2, 6]] and f[1].tolist() == [[3, 7]]
