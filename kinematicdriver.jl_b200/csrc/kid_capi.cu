@@ -496,23 +496,17 @@ int kid_create(const kid_config_t* cfg, kid_handle_t** out) {
 }
 
 void kid_destroy(kid_handle_t* h) {
-    if (h) {
-        if (h->obsG) cudaFree(h->obsG);
-        if (h->red) cudaFree(h->red);
-        if (h->zsin) cudaFree(h->zsin);
-        if (h->cosx) cudaFree(h->cosx);
-        if (h->cosz) cudaFree(h->cosz);
-        if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
-        for (int b = 0; b < 2; ++b) {
-            if (h->ostage[b]) cudaFree(h->ostage[b]);
-            if (h->ev_ready[b]) cudaEventDestroy(h->ev_ready[b]);
-            if (h->ev_done[b]) cudaEventDestroy(h->ev_done[b]);
-        }
-    }
     if (!h) return;
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (void* p : {h->ps_liq, h->ps_mix, h->prm_sets, h->col_to_set, h->Y, h->rho_dry, h->T, h->w1, h->q_surf, h->Nd, h->aux_Naer, h->out, h->staging, h->U, h->S,
-                    h->prev_aux, h->xc, h->out2, h->send_left, h->send_right, h->recv_left, h->recv_right})
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    for (int b = 0; b < 2; ++b) {
+        if (h->ostage[b]) cudaFree(h->ostage[b]);
+        if (h->ev_ready[b]) cudaEventDestroy(h->ev_ready[b]);
+        if (h->ev_done[b]) cudaEventDestroy(h->ev_done[b]);
+    }
+    for (void* p : {h->ps_liq, h->ps_mix, h->prm_sets, h->col_to_set, h->Y, h->rho_dry, h->T, h->w1, h->q_surf, h->Nd, h->aux_Naer,
+                    h->out, h->staging, h->U, h->S, h->prev_aux, h->xc, h->out2, h->send_left, h->send_right, h->recv_left,
+                    h->recv_right, (void*)h->obsG, (void*)h->red, (void*)h->zsin, (void*)h->cosx, (void*)h->cosz})
         if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
