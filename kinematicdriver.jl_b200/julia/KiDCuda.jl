@@ -13,6 +13,7 @@ Usage inside e.g. test/experiments/KiD_driver/run_KiD_simulation.jl, replacing l
 module KiDCuda
 
 import ClimaCore as CC
+import CloudMicrophysics.Parameters as CMP
 import KinematicDriver.Common as CO
 
 const libkid = get(ENV, "KID_CUDA_LIB", "libkid_cuda.so")
@@ -20,7 +21,7 @@ const libkid = get(ENV, "KID_CUDA_LIB", "libkid_cuda.so")
 # ---------------------------------------------------------------- C structs (include/kid_cuda.h)
 Base.@kwdef mutable struct KidConfig
     abi_version::Int32 = 1
-    params_version::Int32 = 1
+    params_version::Int32 = 2
     model::Int32 = 1
     moisture::Int32 = 0
     precip::Int32 = 0
@@ -61,6 +62,23 @@ precip_enum(::CO.Precipitation0M) = Int32(1)
 precip_enum(::CO.Precipitation1M) = Int32(2)
 precip_enum(::CO.Precipitation2M) = Int32(3)
 precip_enum(ps) = error("$(typeof(ps).name.name) is not on the device hot path of libkid_cuda (no CPU fallback)")
+
+# rain-formation / sedimentation choice -> enum kid_rain_formation / kid_sedimentation (src/Common/helper_functions.jl:22-93)
+rain_formation_enum(::Any) = Int32(0)
+function rain_formation_enum(ps::CO.Precipitation1M)
+    rf = ps.rain_formation
+    rf isa CMP.KK2000 && return Int32(1)
+    rf isa CMP.B1994 && return Int32(2)
+    rf isa CMP.TC1980 && return Int32(3)
+    rf isa CMP.LD2004 && return Int32(4)
+    rf isa CMP.VarTimescaleAcnv && return Int32(5)
+    return Int32(0)                                            # CMP.Rain: CliMA_1M
+end
+rain_formation_enum(ps::CO.Precipitation2M) = hasproperty(ps.rain_formation.pdf_r, :N0_min) ? Int32(6) : Int32(7)  # SB2006 / SB2006NL
+sedimentation_enum(::Any) = Int32(0)
+sedimentation_enum(ps::CO.Precipitation1M) =
+    ps.sedimentation isa CMP.Chen2022VelType ? error("Chen2022 sedimentation with Precipitation1M is not on the device path") : Int32(0)
+sedimentation_enum(ps::CO.Precipitation2M) = ps.sedimentation isa CMP.Chen2022VelTypeRain ? Int32(2) : Int32(1)
 
 # The flat parameter table: every entry of include/kid_params.h, read from the structs the reference
 # already built (thermo_params, air_params, activation_params, kid_params, common_params, the style
@@ -155,6 +173,7 @@ function solve(moisture, precip, Y, aux, tspan; model::Symbol, dt, saveat, nz, z
     FT = eltype(parent(Y))
     cfg = KidConfig(model = Int32(Dict(:Box => 0, :K1D => 1, :K1D_col_sed => 2, :K2D => 3)[model]),
                     moisture = moisture_enum(moisture), precip = precip_enum(precip),
+                    rain_formation = rain_formation_enum(precip), sedimentation = sedimentation_enum(precip),
                     float_type = Int32(FT == Float32 ? 0 : 1), nz = Int32(nz), nc = Int32(1),
                     precip_sources = Int32(aux.common_params.precip_sources), precip_sinks = Int32(aux.common_params.precip_sinks),
                     open_system_activation = Int32(aux.common_params.open_system_activation),
@@ -190,6 +209,72 @@ function solve(moisture, precip, Y, aux, tspan; model::Symbol, dt, saveat, nz, z
         ccall((:kid_destroy, libkid), Cvoid, (Ptr{Cvoid},), h[])
     end
 end
+
+# ------------------------------------------------------------------ batched ensembles (run_ensembles on one handle)
+"""
+    Ensemble: one device handle whose columns are independent simulations (ensemble member x case).
+
+    ens = create_ensemble(moisture, precip, Ys, auxs; model = :K1D, dt, nz, z_min, z_max)
+    step_to!(ens, t)                    # kid_step up to time t (a multiple of dt after the current time)
+    destroy!(ens)
+
+`Ys[i]`, `auxs[i]` are what the reference builds per simulation (`CO.initialise_state`, `K1D.initialise_aux`,
+calibration/KiDUtils.jl:83-144); column i takes its state, ρ_dry/T profiles, w1, q_surf, prescribed_Nd and its whole
+parameter set from them.  Replaces the `Threads.@threads` loop of `run_ensembles` (calibration/OptimizationUtils.jl:206-209).
+"""
+mutable struct Ensemble
+    h::Ptr{Cvoid}
+    t::Float64
+    dt::Float64
+    nc::Int
+    nz::Int
+end
+
+function create_ensemble(moisture, precip, Ys::Vector, auxs::Vector; model::Symbol = :K1D, dt, nz, z_min, z_max, t_ini = 0.0, device = 0)
+    FT = eltype(parent(Ys[1]))
+    nc = length(Ys)
+    a1 = auxs[1]
+    cfg = KidConfig(model = Int32(Dict(:Box => 0, :K1D => 1, :K1D_col_sed => 2)[model]),
+                    moisture = moisture_enum(moisture), precip = precip_enum(precip),
+                    rain_formation = rain_formation_enum(precip), sedimentation = sedimentation_enum(precip),
+                    float_type = Int32(FT == Float32 ? 0 : 1), nz = Int32(nz), nc = Int32(nc),
+                    precip_sources = Int32(a1.common_params.precip_sources), precip_sinks = Int32(a1.common_params.precip_sinks),
+                    open_system_activation = Int32(a1.common_params.open_system_activation),
+                    local_activation = Int32(a1.common_params.local_activation),
+                    qtot_flux_correction = Int32(hasproperty(a1, :kid_params) ? a1.kid_params.qtot_flux_correction : 0),
+                    device = Int32(device), z_min = z_min, z_max = z_max, dt = dt)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:kid_create, libkid), Cint, (Ref{KidConfig}, Ref{Ptr{Cvoid}}), cfg, h))
+    tables = reduce(hcat, [param_table(a, moisture, precip) for a in auxs])          # one parameter set per column
+    c2s = Int32.(0:(nc - 1))
+    check(ccall((:kid_set_params, libkid), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32, Int32, Ptr{Int32}),
+                h[], tables, size(tables, 1), nc, c2s))
+    ρ_dry = reduce(hcat, [Array(vec(parent(a.thermo_variables.ρ_dry))) for a in auxs])  # (nz, nc) column-major = [column][level]
+    T = reduce(hcat, [Array(vec(parent(a.thermo_variables.T))) for a in auxs])
+    check(ccall((:kid_set_profiles, libkid), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32), h[], ρ_dry, T, 1))
+    if hasproperty(a1, :kid_params)
+        check(ccall((:kid_set_column_scalar, libkid), Cint, (Ptr{Cvoid}, Int32, Ptr{Cvoid}), h[], 0, FT[a.kid_params.w1 for a in auxs]))
+    end
+    if hasproperty(a1, :q_surf)
+        check(ccall((:kid_set_column_scalar, libkid), Cint, (Ptr{Cvoid}, Int32, Ptr{Cvoid}), h[], 1, FT[a.q_surf for a in auxs]))
+    end
+    check(ccall((:kid_set_column_scalar, libkid), Cint, (Ptr{Cvoid}, Int32, Ptr{Cvoid}), h[], 2,
+                FT[a.common_params.prescribed_Nd for a in auxs]))
+    Yall = reduce((a, b) -> cat(a, b; dims = 3), [reshape(Array(parent(Y)), nz, :, 1) for Y in Ys])  # (nz, nvars, nc) = [column][variable][level]
+    check(ccall((:kid_set_state, libkid), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), h[], Yall))
+    return Ensemble(h[], Float64(t_ini), Float64(dt), nc, nz)
+end
+
+function step_to!(ens::Ensemble, t)
+    n = Int(round((t - ens.t) / ens.dt))
+    n >= 0 && abs(ens.t + n * ens.dt - t) < 1e-9 * max(1.0, abs(t)) ||
+        error("save time $t is not a multiple of dt after t = $(ens.t): the device path saves at step boundaries only")
+    n > 0 && check(ccall((:kid_step, libkid), Cint, (Ptr{Cvoid}, Float64, Int32), ens.h, ens.t, n))
+    ens.t += n * ens.dt
+    return ens
+end
+
+destroy!(ens::Ensemble) = ccall((:kid_destroy, libkid), Cvoid, (Ptr{Cvoid},), ens.h)
 
 # ------------------------------------------------------------------ initial condition on the device
 """
