@@ -1,19 +1,22 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the hot path (BASELINE.json metric: grid-point-steps/s).
 
-Workload (N = 1): BASELINE.json configs[3] — KiD 1-D NonEquilibriumMoisture + Precipitation2M (SB2006)
-ensemble of 1,048,576 columns x 128 levels, Float32, synthetic calibration-style ensemble of
-SURVEY §8(d) (per-column w1, prescribed Nd, surface pressure -> per-column ρ_dry/T profiles).
-N > 1: every rank steps its own 1,048,576-column shard (weak scaling, no data-path collective).
+Workload: BASELINE.json configs[3] — KiD 1-D NonEquilibriumMoisture + Precipitation2M (SB2006) ensemble of
+1,048,576 columns x 128 levels, Float32, the synthetic calibration-style ensemble of SURVEY §8(d) (per-column w1,
+prescribed Nd, surface pressure -> per-column ρ_dry/T profiles built on the device).
+--gpus N shards the SAME ensemble over the N ranks (strong scaling, `--columns` is the total; contiguous column blocks,
+no data-path collective).  --weak keeps `--columns` per GPU instead (round-1 mode).
 
-One "step" = one SSPRK33 step (3 rhs evaluations) of every column of the shard.
+One "step" = one SSPRK33 step (3 rhs evaluations) of every column of the ensemble.
 
     python bench.py --gpus N --steps K --warmup W          # ours  (libkid_cuda.so, sm_100a)
     python bench.py --impl reference ...                   # the reference's CPU path on the host cores
 
-Prints ONE JSON line (rank 0).  `value` is timed with CUDA events on the stream the kernels are
-launched on, state resident in HBM; `e2e` goes through the public host API with pinned HOST
-buffers (upload + K steps + download inside the timed region).
+Prints ONE JSON line (rank 0).  `value` is timed with CUDA events on the stream the kernels are launched on, state
+resident in HBM; `e2e` goes through the public host API with pinned HOST buffers (upload + K steps + download inside the
+timed region).  Both arms time the same model-time window [t_start + W, t_start + W + K) of the same member ordering; the
+CPU arm steps the first columns of that ensemble (a bounded sample), and the GPU arm checks its own result on those
+columns against the CPU arm's (`parity_sample`).
 """
 from __future__ import annotations
 
@@ -36,9 +39,8 @@ sys.path.insert(0, str(ROOT))
 NZ = 128
 BYTES_PER_GP_STEP = 2 * 8 * 4 + 2 * 4  # NonEq+2M f32: read+write 8 prognostics, read per-column ρ_dry, T
 METRIC = "grid-point-steps/s"
-ORDER = "sorted"
-IC = "device"
 PREROLL_SPL = 60  # the untimed pre-roll runs in launches of 60 fused steps
+WORKLOAD = "KiD 1D NonEq+Precipitation2M(SB2006) ensemble, 128 levels, Float32 (BASELINE configs[3])"
 
 
 def measured_peaks():
@@ -47,6 +49,28 @@ def measured_peaks():
         d = json.loads(p.read_text())
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def kernel_profile():
+    """ncu-derived constants of the dominant kernel (profiles/traffic.json): DRAM bytes per launch and executed
+    thread-instructions per grid point per rhs.  Re-captured whenever the kernel changes (profiles/README.md)."""
+    tp = ROOT / "profiles" / "traffic.json"
+    try:
+        return json.loads(tp.read_text())
+    except Exception:
+        return {}
+
+
+def flops_per_gp_step():
+    """Arithmetic operations of the REFERENCE formulation per grid-point-step (oracle/opcount.py)."""
+    try:
+        d = json.loads((ROOT / "profiles" / "r01_opcounts.json").read_text())
+        vals = [v["arithmetic_flops_per_gp_step"] for v in d if v["style"].startswith("NonEquilibrium") and "2M" in v["style"]]
+        if vals:
+            return float(np.mean(vals)), "profiles/r01_opcounts.json (operation-counting oracle, NonEq+2M)"
+    except Exception:
+        pass
+    return 1965.0, "DESIGN.md §3.4 (operation-counting oracle, NonEq+2M: 1939-1991)"
 
 
 class ClockSampler:
@@ -85,85 +109,137 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def build_case(nc: int, column_offset: int, device: int, host_ic: bool = False):
-    """SURVEY §8(d) ensemble: member c has w1, Nd, p0 from the counter hash.  --ic device (default): every member its own
-    p0, hydrostatic profile and initial state built on the device (kid_init_shipway_hill); --ic host: p0 quantised to 16
-    soundings solved on the host.  Member order: "sorted" stores the members along a Z-order curve through
-    (w1, log Nd, p0) (--ic host: lexicographically by sounding, w1, Nd), so that neighbouring columns — the 32 lanes of a
-    warp — follow the same microphysics branches; --order hash keeps the hash order of §8(d)."""
-    from kid_b200 import model as M
-    kw = dict(column_offset=column_offset, device=device, n_elem=NZ, order=ORDER,
-              moisture_choice="NonEquilibriumMoisture", precipitation_choice="Precipitation2M")
-    if IC == "device" and not host_ic:
-        return M.k1d_ensemble_case(np.float32, nc=nc, ic="device", **kw)
-    # host IC; the CPU arm of a device-IC run keeps the exact per-member p0 (one host IVP per member of its small sample)
-    return M.k1d_ensemble_case(np.float32, nc=nc, n_profiles=None if IC == "device" else 16, **kw)
+# ------------------------------------------------------------------ workload shared by both arms
+def total_columns(args, world: int) -> int:
+    return args.columns * world if args.weak else args.columns
 
 
-def cpu_reference_throughput(case, Y_dev_sample, t_start: float, target_s: float = 15.0):
-    """The reference's CPU path (restated: oracle/kid_oracle.cpp, OpenMP over columns) on a bounded
-    sample of the same workload: the first `ncpu` columns of the developed ensemble state."""
+def global_case(args, world: int, device: int = 0):
+    """The whole SURVEY §8(d) ensemble (numpy only: member c has w1, Nd, p0 from the counter hash; hydrostatic profile and
+    initial state are built on the device).  Member order: "sorted" stores the members along a Z-order curve through
+    (w1, log Nd, p0), so that neighbouring columns — the 32 lanes of a warp — follow the same microphysics branches;
+    "hash" keeps the member-index order of §8(d)."""
     from kid_b200 import model as M
-    from oracle.oracle import OracleHandle
-    cores = os.cpu_count() or 1
-    ncpu = Y_dev_sample.shape[0]
-    import copy
-    sub = copy.copy(M.materialise(M.slice_columns(case, 0, ncpu)))  # device-built profiles of the sample -> host
-    sub.Y0 = Y_dev_sample
-    o = M.make_handle(sub, OracleHandle)
-    t0 = time.perf_counter()
-    o.step(t_start, 4)
-    per_step = (time.perf_counter() - t0) / 4
-    nsteps = int(max(8, min(2000, target_s / max(per_step, 1e-6))))
-    t0 = time.perf_counter()
-    o.step(t_start + 4, nsteps)
-    dt = time.perf_counter() - t0
-    return {"value": ncpu * NZ * nsteps / dt, "unit": METRIC, "cores": cores, "kind": "port",
-            "sample": f"{ncpu} columns x {NZ} levels x {nsteps} SSPRK33 steps of the same developed ensemble state "
-                      f"(t={t_start:g}s), OpenMP over columns, g++ -O2, Float32; restated CPU path, not Julia"}
+    return M.k1d_ensemble_case(np.float32, nc=total_columns(args, world), ic="device", order=args.order, device=device, n_elem=NZ,
+                               moisture_choice="NonEquilibriumMoisture", precipitation_choice="Precipitation2M")
+
+
+def shard_range(total: int, rank: int, world: int):
+    per = (total // world) // 32 * 32 if world > 1 else total
+    a = rank * per
+    return a, (total if rank == world - 1 else a + per)
+
+
+def workload_config(args, world: int) -> dict:
+    """The `config` object of the JSON line — identical in both arms (same ensemble, same member order, same window)."""
+    total = total_columns(args, world)
+    return {"workload": WORKLOAD, "columns": total, "levels": NZ,
+            "window_model_time_s": [args.t_start + args.warmup, args.t_start + args.warmup + args.steps],
+            "member_order": ("hash (SURVEY 8d counter hash)" if args.order == "hash"
+                             else "sorted along a Z-order curve through (w1, log Nd, p0)"),
+            "initial_condition": "every member its own p0 (SURVEY 8d), hydrostatic profile + initial state per column",
+            "parallelism": f"columns sharded x{world}, contiguous blocks, no collective"}
+
+
+def sample_errors(a, b, var_names) -> dict:
+    """max |a - b| per prognostic variable, relative to the field maximum (floor: 1e-6 of the largest field of the same
+    kind, mass or number densities) — the metric of tests/parity.py."""
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    kind = lambda v: "N" if v.startswith("N_") else "q"
+    scale = {}
+    for i, v in enumerate(var_names):
+        scale[kind(v)] = max(scale.get(kind(v), 0.0), float(np.max(np.abs(b[:, i]))))
+    out = {}
+    for i, v in enumerate(var_names):
+        den = max(float(np.max(np.abs(b[:, i]))), 1e-6 * scale[kind(v)], 1e-300)
+        out[v] = float("%.3e" % (np.max(np.abs(a[:, i] - b[:, i])) / den))
+    return out
+
+
+def cpu_arm_threads(lib) -> int:
+    """All host cores, explicitly: torch.distributed.run exports OMP_NUM_THREADS=1 to its workers."""
+    from oracle import oracle as O
+    return O.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1), lib)
+
+
+def cpu_sample_columns(total: int) -> int:
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return int(min(total, 32 * cores))
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path.  Julia and the reference's
-    un-vendored dependencies are absent (no oracle/_ref can be built), so this arm times the restated CPU
-    path (oracle/) with all host threads on a bounded sample of the arm's workload."""
+    """--impl reference: the reference's own CPU implementation of the path.  Julia and the reference's un-vendored
+    dependencies are absent (no oracle/_ref can be built), so this arm times the restated CPU path (oracle/, built
+    -O3 -march=native on this host) with all host threads on a bounded sample of the arm's workload: the first columns of
+    the same ensemble in the same member order, over the same model-time window."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
     from kid_b200 import model as M
-    from oracle.oracle import OracleHandle
-    cores = os.cpu_count() or 1
-    ncpu = 32 * cores
-    case = build_case(ncpu, 0, 0, host_ic=True)
-    o = M.make_handle(case, OracleHandle)
-    t_start = float(args.t_start)
-    # bring the sample to the same developed state the device arm times (untimed)
-    o.step(0.0, int(t_start))
-    for _ in range(args.warmup):
-        o.step(t_start, 1)
-        t_start += 1
+    from oracle import oracle as O
+    lib, build = O.load_native()
+    threads = cpu_arm_threads(lib)
+    total = total_columns(args, world)
+    ncpu = cpu_sample_columns(total)
+    case = M.materialise_on_host(M.slice_columns(global_case(args, world), 0, ncpu))
+    o = M.apply_case(O.OracleHandle(case.cfg, lib), case)
+    # bring the sample to the developed state the device arm times (untimed), then the same warm-up steps
+    o.step(0.0, int(args.t_start))
+    t = float(args.t_start)
+    o.step(t, args.warmup)
+    t += args.warmup
     t0 = time.perf_counter()
-    o.step(t_start, args.steps)
+    o.step(t, args.steps)
     dt = time.perf_counter() - t0
     value = ncpu * NZ * args.steps / dt
+    sample = (f"first {ncpu} columns of the ensemble x {NZ} levels x {args.steps} SSPRK33 steps over the same model-time window; "
+              f"restated CPU path (oracle/, {build}), OpenMP over columns on {threads} threads; "
+              "Julia + CloudMicrophysics/ClimaCore are not installable here")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "KiD 1D NonEq+Precipitation2M(SB2006) ensemble, 128 levels, Float32 (BASELINE configs[3])",
-                   "columns_per_step": ncpu, "t_start_s": args.t_start},
-        "cpu_baseline": {"value": value, "unit": METRIC, "cores": cores, "kind": "port",
-                         "sample": f"{ncpu} columns x {NZ} levels x {args.steps} steps; restated CPU path (oracle/), "
-                                   "OpenMP over columns; Julia + CloudMicrophysics/ClimaCore are not installable here"},
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": value, "unit": METRIC, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
 
 
+def cpu_check_and_baseline(case_sample, Y_start, Y_gpu_end, t_start: float, nsteps: int, target_s: float):
+    """Rank 0 of the device arm: step the sampled columns on the CPU oracle from the state the timed region started
+    from, compare with what the GPU produced for them (parity_sample), and time the CPU path on the same columns."""
+    from kid_b200 import model as M
+    from oracle import oracle as O
+    import copy
+    lib, build = O.load_native()
+    threads = cpu_arm_threads(lib)
+    sub = copy.copy(case_sample)
+    sub.Y0 = Y_start
+    o = M.apply_case(O.OracleHandle(sub.cfg, lib), sub)
+    ncpu = Y_start.shape[0]
+    t0 = time.perf_counter()
+    o.step(t_start, nsteps)
+    per_step = (time.perf_counter() - t0) / nsteps
+    parity = sample_errors(Y_gpu_end, o.get_state(), case_sample.var_names)
+    cpu = None
+    if target_s > 0:
+        n2 = int(max(8, min(4000, target_s / max(per_step, 1e-6))))
+        t0 = time.perf_counter()
+        o.step(t_start + nsteps, n2)
+        dt = time.perf_counter() - t0
+        cpu = {"value": ncpu * NZ * n2 / dt, "unit": METRIC, "cores": threads, "kind": "port",
+               "sample": f"first {ncpu} columns x {NZ} levels x {n2} SSPRK33 steps continuing the same developed ensemble state "
+                         f"(t={t_start + nsteps:g}s); restated CPU path (oracle/, {build}), OpenMP over columns on {threads} threads; not Julia"}
+    return parity, cpu
+
+
 def run_ours(args):
     import torch
     from kid_b200 import model as M
+    from kid_b200 import lib as KL
     from kid_b200.lib import Handle
 
     rank = int(os.environ.get("RANK", "0"))
@@ -178,17 +254,19 @@ def run_ours(args):
     numa = {}
     if world > 1:
         # several ranks share the host: keep each rank and its pinned staging buffers on its GPU's NUMA node
-        from kid_b200.lib import bind_to_gpu_numa_node
         pr = torch.cuda.get_device_properties(local)
-        numa = bind_to_gpu_numa_node(f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0")
+        numa = KL.bind_to_gpu_numa_node(f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0")
         import torch.distributed as dist
         # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    nc = args.columns
-    case = build_case(nc, rank * nc, local)
+    total = total_columns(args, world)
+    ca, cb = shard_range(total, rank, world)
+    nc = cb - ca
+    gcase = global_case(args, world, local)
+    case = M.slice_columns(gcase, ca, cb)
     h = M.make_handle(case, Handle)
     spl = args.steps_per_launch
     stream = torch.cuda.ExternalStream(h.stream, device=local)
@@ -199,18 +277,27 @@ def run_ours(args):
         if dist is not None:
             dist.barrier()
 
-    # untimed pre-roll into the developed state (updraft on: activation, condensation, collisions, advection)
-    t = 0.0
+    # untimed pre-roll into the developed state (updraft on: activation, condensation, collisions, advection), then W warm-up steps
     h.set_steps_per_launch(PREROLL_SPL)
-    h.step(t, int(args.t_start))
+    h.step(0.0, int(args.t_start))
     h.set_steps_per_launch(spl)
     t = float(args.t_start)
-    for _ in range(args.warmup):
-        h.step(t, spl)
-        t += spl
+    h.step(t, args.warmup)
+    t += args.warmup
     barrier()
 
+    state_shape = (nc, len(case.var_names), NZ)
+    Yh = torch.empty(state_shape, dtype=torch.float32).pin_memory()
+    Yn = Yh.numpy()
+    ncpu = cpu_sample_columns(total) if rank == 0 else 0
+    ncpu = min(ncpu, nc)
+    Y_start = None
+    if rank == 0 and (args.cpu_seconds > 0 or args.parity):
+        h.get_state(Yn)
+        Y_start = Yn[:ncpu].copy()  # what the CPU arm starts from
+
     # ---------------- device-resident timing (value)
+    fp32_peak = KL.measure_fp32_peak(local)
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(1.0)  # let nvidia-smi finish initialising (it briefly holds driver locks) before the timed region
@@ -236,7 +323,7 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms_max = float(tt.item())
-    gp_steps_total = world * nc * NZ * args.steps
+    gp_steps_total = total * NZ * args.steps
     value = gp_steps_total / (ms_max * 1e-3)
 
     # ---------------- end-to-end through the host API with pinned host buffers (e2e)
@@ -244,10 +331,9 @@ def run_ours(args):
     # H2D upload, the K steps and the D2H download of different chunks overlap (kid_set_state_async / kid_step /
     # kid_get_state_async).  Everything — copies included — is inside the timed region.
     from kid_b200.solve import PipelinedEnsemble
-    state_shape = (nc, len(case.var_names), NZ)
-    Yh = torch.empty(state_shape, dtype=torch.float32).pin_memory()
-    Yn = Yh.numpy()
     h.get_state(Yn)  # developed state as the "user's" host input
+    Y_gpu_end = Yn[:ncpu].copy() if Y_start is not None else None
+    finite = bool(np.isfinite(Yn[:: max(1, nc // 4096)]).all())
     pipe = PipelinedEnsemble(case, nchunks=args.e2e_chunks)
     pipe.set_steps_per_launch(spl)
     e2e_steps = args.steps
@@ -267,50 +353,59 @@ def run_ours(args):
     e2e_value = gp_steps_total / (float(te.item()) * 1e-3)
     state_bytes = Yn.nbytes
 
-    finite = bool(np.isfinite(Yn[:: max(1, nc // 4096)]).all())
-
     if rank == 0:
         peak, peak_src = measured_peaks()
         avg_launch_ms = statistics.mean(launch_ms)
         steps_per = args.steps / n_launch
         achieved = BYTES_PER_GP_STEP * nc * NZ * steps_per / (avg_launch_ms * 1e-3) / 1e9
-        cpu = None
-        if world == 1 or rank == 0:
-            ncpu = min(nc, 32 * (os.cpu_count() or 1))
-            cpu = cpu_reference_throughput(case, Yn[:ncpu].copy(), t, target_s=args.cpu_seconds) if args.cpu_seconds > 0 else None
-        traffic = None
-        tp = ROOT / "profiles" / "traffic.json"
-        if tp.exists():
-            try:
-                traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch_per_step")
-                traffic = traffic * steps_per if traffic else None
-            except Exception:
-                traffic = None
+        parity, cpu = None, None
+        if Y_start is not None:
+            sample_case = M.materialise(M.slice_columns(case, 0, ncpu))  # device-built profiles of the sample -> host
+            parity, cpu = cpu_check_and_baseline(sample_case, Y_start, Y_gpu_end, t_timed0, args.steps, args.cpu_seconds)
+        prof = kernel_profile()
+        traffic = prof.get("dram_bytes_per_gp_step")
+        traffic = traffic * nc * NZ * steps_per if traffic else None
+        # Float32 roofline: the reference formulation's arithmetic per grid-point-step (operation-counting oracle) over
+        # the FFMA rate measured in this run; issue roofline: executed warp-instructions (ncu count of the committed
+        # capture) over 4 issue slots per cycle per SM at the SM clock sampled during the timed region
+        fl, fl_src = flops_per_gp_step()
+        per_gpu_rate = nc * NZ * steps_per / (avg_launch_ms * 1e-3)  # grid-point-steps/s of this GPU's kernel
+        fp32_frac = fl * per_gpu_rate / fp32_peak["flops_per_s"]
+        inst = prof.get("thread_inst_per_gp_rhs")
+        sm_mhz = clocks.get("sm_mhz") or fp32_peak["sm_clock_khz"] / 1e3
+        issue = None
+        if inst:
+            wipc = inst * 3 * per_gpu_rate / 32 / (fp32_peak["sm_count"] * sm_mhz * 1e6)
+            issue = {"warp_inst_per_clk_per_sm": wipc, "peak": 4.0, "frac": wipc / 4.0, "thread_inst_per_gp_rhs": inst,
+                     "source": prof.get("source")}
+        fracs = {"hbm": achieved / peak, "fp32": fp32_frac, "issue": issue["frac"] if issue else 0.0}
         line = {
             "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "KiD 1D NonEq+Precipitation2M(SB2006) ensemble, 128 levels, Float32 (BASELINE configs[3])",
-                       "columns_per_gpu": nc, "levels": NZ, "steps_per_launch": spl, "t_start_s": t_timed0,
-                       "member_order": ("hash (SURVEY 8d counter hash)" if ORDER == "hash" else
-                                        "sorted along a Z-order curve through (w1, log Nd, p0)" if IC == "device" else
-                                        "sorted by (sounding, w1, Nd)"),
-                       "initial_condition": ("built on the device, every member its own p0 (SURVEY 8d)" if IC == "device" else
-                                             "host, p0 quantised to 16 soundings"),
-                       "l2": "state per GPU (%.2f GiB) is far larger than the 126 MB L2; no flush needed" % (state_bytes / 2**30),
-                       "parallelism": f"columns sharded x{world}, no collective", "state_finite": finite,
-                       **({"host_numa_binding": numa} if numa else {})},
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak" if args.weak else "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "run": {"columns_per_gpu": nc, "steps_per_launch": spl, "state_finite": finite,
+                    "l2": "state per GPU (%.2f GiB) is far larger than the 126 MB L2; no flush needed" % (state_bytes / 2**30),
+                    **({"host_numa_binding": numa} if numa else {})},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": state_bytes / e2e_steps,
-                    "d2h_bytes_per_step": state_bytes / e2e_steps,
+            "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": world * state_bytes / e2e_steps,
+                    "d2h_bytes_per_step": world * state_bytes / e2e_steps, "resident_fraction": e2e_value / value,
                     "call": f"PipelinedEnsemble.solve: {args.e2e_chunks} column chunks x [set_state_async(pinned) + step({e2e_steps}) + get_state_async(pinned)], per rank"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": max(fracs, key=fracs.get), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_gp_step": BYTES_PER_GP_STEP,
-                         "kernel": "k1d_tile_kernel<float,NonEq,2M>", "avg_launch_ms": avg_launch_ms,
+                         "kernel": prof.get("kernel", "k1d_pair_kernel<NonEq>"), "avg_launch_ms": avg_launch_ms,
                          "launch_ms": [round(x, 3) for x in launch_ms], "timed_region_ms": ms_total,
-                         "note": "the fused kernel is FP32/MUFU-pipe bound, not HBM bound: see profiles/ for pipe utilisation"},
+                         "hbm": {"achieved_gbs": achieved, "peak_gbs": peak, "frac": achieved / peak},
+                         "fp32": {"achieved_tflops": fl * per_gpu_rate / 1e12, "peak_tflops": fp32_peak["flops_per_s"] / 1e12,
+                                  "frac": fp32_frac, "flops_per_gp_step": fl, "flops_source": fl_src,
+                                  "peak_source": "FFMA micro-benchmark in this run (kid_measure_fp32_peak)"},
+                         "issue": issue,
+                         "note": "top-level achieved/peak/frac are the HBM figures the contract asks for (algorithmic bytes, not DRAM traffic: "
+                                 "several steps are fused per launch); `bound` names the largest of the hbm / fp32 / issue fractions"},
+            "parity_sample": ({"columns": ncpu, "steps": args.steps, "vs": "CPU oracle from the same start state",
+                               "max_err_rel_field_max": parity} if parity else None),
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))
@@ -326,17 +421,15 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--columns", type=int, default=1 << 20, help="columns per GPU")
+    ap.add_argument("--columns", type=int, default=1 << 20, help="columns of the ensemble (total; per GPU with --weak)")
+    ap.add_argument("--weak", action="store_true", help="weak scaling: --columns per GPU instead of in total")
     ap.add_argument("--steps-per-launch", type=int, default=10)
-    ap.add_argument("--t-start", type=int, default=480, help="model time [s] at which the timed window starts")
+    ap.add_argument("--t-start", type=int, default=480, help="model time [s] the pre-roll ends at (the timed window starts W steps later)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample length (0 = skip)")
+    ap.add_argument("--no-parity", dest="parity", action="store_false", help="skip the in-bench parity sample")
     ap.add_argument("--e2e-chunks", type=int, default=32, help="column chunks (handles/streams) of the end-to-end pipelined call")
-    ap.add_argument("--ic", default="device", choices=["device", "host"], help="where the initial condition is built")
     ap.add_argument("--order", default="sorted", choices=["sorted", "hash"], help="storage order of the ensemble members")
     args = ap.parse_args()
-    global ORDER, IC
-    ORDER = args.order
-    IC = args.ic
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     return run_reference(args) if args.impl == "reference" else run_ours(args)

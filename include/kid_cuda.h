@@ -111,7 +111,7 @@ typedef struct kid_config {
     int32_t local_activation;
     int32_t qtot_flux_correction;
     int32_t device;          /* CUDA device ordinal */
-    int32_t reserved[8];     /* reserved[0..2]: tuning overrides (0 = library default): max level-warps per tile, columns per tile, 1 = never use the compile-time-shape kernel */
+    int32_t reserved[8];     /* reserved[0..3]: tuning overrides (0 = library default): max level-warps per tile (>= 2), columns per tile, 1 = never use the compile-time-shape kernel, 1 = never use the packed two-levels-per-thread 2M kernel */
     double z_min, z_max;     /* make_function_space (K1DModel/ode_utils.jl:9-21) */
     double dt;               /* TimeStepping.dt (src/Common/ode_utils.jl:12-16) */
     double domain_width;     /* K2D aux.domain_width  */
@@ -242,6 +242,10 @@ int64_t kid_launch_count(kid_handle_t* h);    /* kernels launched by this handle
 const char* kid_last_error(void);
 const char* kid_version(void);
 int kid_device_count(void);
+/* Measurement support for the roofline of bench.py ("measure with a FMA micro-benchmark on the box"): runs a
+ * register-resident FFMA loop on `device` for a few milliseconds and returns the achieved Float32 rate in flop/s (2 per
+ * FFMA), with the SM count and the SM clock (kHz) the driver reports.  No handle needed. */
+int kid_measure_fp32_peak(int32_t device, double* flops_per_s, int32_t* sm_count, int32_t* sm_clock_khz);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,7 @@ struct kid_handle {
     void *aux_Naer = nullptr, *out = nullptr, *staging = nullptr;
     void *prm_sets = nullptr, *col_to_set = nullptr;  // per-column parameter sets (calibration ensembles)
     void *ps_liq = nullptr, *ps_mix = nullptr;        // p_sat(T) per grid point (profile constants)
+    void* gconst = nullptr;                            // float4 per grid point: constants of the packed 2M kernel (kid_pair_kernel.cuh)
     bool consts_dirty = true;
     size_t staging_bytes = 0, out_bytes = 0;
     int prof_per_column = 0;
@@ -236,6 +237,15 @@ K2DArgs<FT> make_k2d_args(kid_handle* h, double t_stage, int stage, int use_recv
     return a;
 }
 
+// The packed two-levels-per-thread step kernel serves the headline configuration: K1DModel / col_sed, Precipitation2M with
+// SB2006 sedimentation, Float32, the default 128-level grid, one shared parameter set, full 32-column tiles.
+// cfg.reserved[3] = 1 opts out (A/B measurements against the scalar tile kernel).
+bool pair_capable(const kid_handle* h) {
+    return !h->f64 && h->cfg.precip == KID_PRECIP_2M && h->cfg.nz == 128 && h->prm_sets == nullptr && h->lt->pair_f != nullptr &&
+           (h->cfg.model == KID_MODEL_K1D || h->cfg.model == KID_MODEL_K1D_COL_SED) && h->cfg.sedimentation != KID_SED_CHEN2022 &&
+           h->C == 32 && h->cfg.reserved[3] == 0;
+}
+
 int check_ready(kid_handle* h) {
     if (!h) return fail("null handle");
     if (!h->params_set) return fail("kid_set_params has not been called");
@@ -249,6 +259,16 @@ int check_ready(kid_handle* h) {
         else e = h->lt->consts_f(make_args<float>(h, 0.0, 0, 0, 0), h->prm_f, (float*)h->ps_liq, (float*)h->ps_mix, h->stream);
         if (e != cudaSuccess) return fail(std::string("profile_consts_kernel launch: ") + cudaGetErrorString(e));
         h->launches++;
+        if (pair_capable(h)) {
+            const size_t n = h->prof_per_column ? size_t(h->cfg.nz) * h->ncp : size_t(h->cfg.nz);
+            if (h->gconst) cudaFree(h->gconst);
+            h->gconst = nullptr;
+            KID_CUDA(cudaMalloc(&h->gconst, n * sizeof(float4)));
+            KID_CUDA(cudaMemsetAsync(h->gconst, 0, n * sizeof(float4), h->stream));
+            e = h->lt->gconsts_f(make_args<float>(h, 0.0, 0, 0, 0), h->prm_f, (float4*)h->gconst, h->stream);
+            if (e != cudaSuccess) return fail(std::string("grid_consts_kernel launch: ") + cudaGetErrorString(e));
+            h->launches++;
+        }
         h->consts_dirty = false;
     }
     return 0;
@@ -285,6 +305,12 @@ int choose_tile(kid_handle* h) {
 int launch_tile(kid_handle* h, double t0, int nsteps, int diag_mode, int field, int update_prev = 0) {
     if (diag_mode == 2 && field >= 0) { h->diag_nfields = 1; h->diag_fields[0] = field; }  // field < 0: h->diag_fields preset
     cudaError_t e;
+    if (diag_mode == 0 && pair_capable(h) && h->gconst) {
+        e = h->lt->pair_f(h->cfg.moisture, make_args<float>(h, t0, nsteps, 0, 0), (const float4*)h->gconst, h->prm_f, h->stream);
+        if (e != cudaSuccess) return fail(std::string("k1d_pair_kernel launch: ") + cudaGetErrorString(e));
+        h->launches++;
+        return 0;
+    }
     if (h->f64) {
         auto a = make_args<double>(h, t0, nsteps, diag_mode, field);
         a.update_prev = update_prev;
@@ -396,6 +422,21 @@ int k2d_setup(kid_handle* h) {
     return 0;
 }
 
+// FFMA issue-rate probe (kid_measure_fp32_peak): 8 independent accumulators per thread, 2 CTAs of 1024 threads per SM
+__global__ void __launch_bounds__(1024) fp32_peak_kernel(float* out, int iters, float a, float b) {
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = threadIdx.x * 1e-3f + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = fmaf(x[i], a, b);
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <class FT>
 int obs_launch(kid_handle_t* h, int time_cell) {
     ObsArgs<FT> a{};
@@ -440,6 +481,36 @@ int kid_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
+}
+
+int kid_measure_fp32_peak(int32_t device, double* flops_per_s, int32_t* sm_count, int32_t* sm_clock_khz) {
+    if (!flops_per_s) return fail("null argument");
+    if (kid_device_count() < 1) return fail("no CUDA device visible: libkid_cuda has no CPU fallback");
+    int prev = 0;
+    KID_CUDA(cudaGetDevice(&prev));
+    KID_CUDA(cudaSetDevice(device));
+    int sms = 0, khz = 0;
+    KID_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    KID_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
+    const int blocks = sms * 2, threads = 1024, iters = 40000;
+    float* out = nullptr;
+    KID_CUDA(cudaMalloc(&out, size_t(blocks) * threads * sizeof(float)));
+    cudaEvent_t e0, e1;
+    KID_CUDA(cudaEventCreate(&e0));
+    KID_CUDA(cudaEventCreate(&e1));
+    fp32_peak_kernel<<<blocks, threads>>>(out, iters / 8, 1.0001f, 1e-7f);  // warm-up
+    KID_CUDA(cudaEventRecord(e0));
+    fp32_peak_kernel<<<blocks, threads>>>(out, iters, 1.0001f, 1e-7f);
+    KID_CUDA(cudaEventRecord(e1));
+    KID_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    KID_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+    cudaSetDevice(prev);
+    *flops_per_s = double(blocks) * threads * double(iters) * 8 * 2 / (double(ms) * 1e-3);
+    if (sm_count) *sm_count = sms;
+    if (sm_clock_khz) *sm_clock_khz = khz;
+    return 0;
 }
 
 int kid_create(const kid_config_t* cfg, kid_handle_t** out) {
@@ -504,7 +575,7 @@ void kid_destroy(kid_handle_t* h) {
         if (h->ev_ready[b]) cudaEventDestroy(h->ev_ready[b]);
         if (h->ev_done[b]) cudaEventDestroy(h->ev_done[b]);
     }
-    for (void* p : {h->ps_liq, h->ps_mix, h->prm_sets, h->col_to_set, h->Y, h->rho_dry, h->T, h->w1, h->q_surf, h->Nd, h->aux_Naer,
+    for (void* p : {h->gconst, h->ps_liq, h->ps_mix, h->prm_sets, h->col_to_set, h->Y, h->rho_dry, h->T, h->w1, h->q_surf, h->Nd, h->aux_Naer,
                     h->out, h->staging, h->U, h->S, h->prev_aux, h->xc, h->out2, h->send_left, h->send_right, h->recv_left,
                     h->recv_right, (void*)h->obsG, (void*)h->red, (void*)h->zsin, (void*)h->cosx, (void*)h->cosz})
         if (p) cudaFree(p);

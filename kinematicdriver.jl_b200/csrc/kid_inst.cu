@@ -3,6 +3,9 @@
 #error "compile with -DKID_PRECIP=<enum kid_precip value>"
 #endif
 #include "kid_launch.h"
+#if KID_PRECIP == 3
+#include "kid_pair_kernel.cuh"
+#endif
 
 namespace kid {
 namespace {
@@ -79,8 +82,34 @@ size_t smem_bytes(int moisture, int nz, int C, bool pcp) {
                                     : k1d_tile_smem_bytes<FT, KID_MOIST_NONEQ, KID_PRECIP>(nz, C, pcp);
 }
 
+#if KID_PRECIP == 3
+template <int MOIST>
+cudaError_t pair_m(const KArgs<float>& a, const float4* gconst, const DevParams<float>& P, cudaStream_t s) {
+    auto kern = k1d_pair_kernel<MOIST>;
+    const size_t smem = k1d_pair_smem_bytes<MOIST>();
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return e;
+    dim3 block(PAIR_C, PAIR_TJ), grid((a.nc + PAIR_C - 1) / PAIR_C);
+    kern<<<grid, block, smem, s>>>(a, gconst, P);
+    return cudaGetLastError();
+}
+cudaError_t pair(int moisture, const KArgs<float>& a, const float4* gconst, const DevParams<float>& P, cudaStream_t s) {
+    return moisture == KID_MOIST_EQ ? pair_m<KID_MOIST_EQ>(a, gconst, P, s) : pair_m<KID_MOIST_NONEQ>(a, gconst, P, s);
+}
+cudaError_t gconsts(const KArgs<float>& a, const DevParams<float>& P, float4* out, cudaStream_t s) {
+    const int ncol = a.prof_per_column ? a.nc : 1;
+    dim3 block(128), grid((ncol + 127) / 128, a.nz);
+    grid_consts_kernel<ConstPrm<float>><<<grid, block, 0, s>>>(a.T, out, a.nz, a.nc, a.ncp, a.prof_per_column, P);
+    return cudaGetLastError();
+}
+#define KID_PAIR_ENTRIES pair, gconsts
+#else
+#define KID_PAIR_ENTRIES nullptr, nullptr
+#endif
+
 const LaunchTable table = {k1d<float>, k1d<double>, box<float>, box<double>,
-                           consts<float>, consts<double>, obs<float>, obs<double>, smem_bytes<float>, smem_bytes<double>};
+                           consts<float>, consts<double>, obs<float>, obs<double>, smem_bytes<float>, smem_bytes<double>,
+                           KID_PAIR_ENTRIES};
 }  // namespace
 
 #define KID_CAT2(a, b) a##b

@@ -22,6 +22,10 @@ struct LaunchTable {
     cudaError_t (*obs_d)(int moisture, const ObsArgs<double>&, const DevParams<double>&, cudaStream_t);
     size_t (*k1d_smem_f)(int moisture, int nz, int C, bool per_column_params);
     size_t (*k1d_smem_d)(int moisture, int nz, int C, bool per_column_params);
+    // Precipitation2M, Float32, 128 levels, shared parameter set: the packed two-levels-per-thread step kernel
+    // (kid_pair_kernel.cuh) and its per-grid-point constants; null for the other precipitation styles
+    cudaError_t (*pair_f)(int moisture, const KArgs<float>&, const float4* gconst, const DevParams<float>&, cudaStream_t);
+    cudaError_t (*gconsts_f)(const KArgs<float>&, const DevParams<float>&, float4* out, cudaStream_t);
 };
 
 const LaunchTable* launch_table_precip0();

@@ -1,0 +1,301 @@
+// k1d_pair_kernel — the headline kernel: K1DModel / col_sed, Precipitation2M (SB2006), Float32, 128 levels, one
+// parameter set shared by the ensemble (BASELINE configs[3]).
+//
+// Same tile design as k1d_tile_kernel (kid_kernels.cuh: one CTA owns 32 columns x all levels in shared memory for all
+// SSPRK33 stages of a launch; lanes = neighbouring columns; rounds over blocks of levels with a READ phase that turns
+// the OLD neighbours into advective tendencies, a barrier, and a WRITE phase that applies sources + stage combine in
+// place), with two changes that cut the issued instructions per grid point (the kernel is issue-bound):
+//
+//  * every thread works on TWO vertically adjacent levels (k0, k0+1) and keeps their arithmetic in the packed
+//    Float32 instructions of sm_100a (FFMA2 / FADD2 / FMUL2, kid_f2.cuh, kid_physics_x2.cuh): one issue slot per two
+//    results, and all per-thread overhead — addressing, parameter loads, branches, loop control — is paid once per
+//    two grid points.  The two cells share their middle face, so the stencil needs 3 face fluxes and 4 loads per
+//    variable for 2 cells instead of 4 and 6.  512 threads x 128 registers per tile (16 level-pairs x 32 columns per
+//    round, 4 rounds per stage).
+//  * there is no separate pass 1: the WRITE phase of stage s evaluates the terminal velocities, the ARG activation rate
+//    and the cloud-base candidate of the NEW state it has just formed, i.e. the aux fields stage s+1 needs
+//    (precompute_aux_precip!, precompute_aux_activation!; K1DModel/ode_utils.jl:30-47 evaluates them at the start of
+//    the next rhs! call from the same state).  The terminal velocities are two more planes of the shared-memory tile
+//    with their own round-boundary stash row.  A launch starts with a pseudo-stage that only does this evaluation.
+//
+// Time-invariant functions of T per grid point (q_vs ρ, λ(T), R_v T / p_sat, G(T)) come from a float4 array filled at
+// upload (grid_consts_kernel), so T itself is only read by the rare ARG evaluation.
+#pragma once
+#include "kid_kernels.cuh"
+#include "kid_physics_x2.cuh"
+
+namespace kid {
+
+constexpr int PAIR_NZ = 128, PAIR_C = 32, PAIR_TJ = 16;
+
+template <int MOIST>
+inline size_t k1d_pair_smem_bytes() {
+    using L = Lay<MOIST, KID_PRECIP_2M>;
+    return (size_t(L::NV + 2) * (PAIR_NZ + 2) * PAIR_C + size_t(2) * PAIR_NZ * PAIR_C) * sizeof(float) + size_t(2) * PAIR_C * sizeof(int);
+}
+
+// per-grid-point constants (see GridConst2): computed in double from the Float32 temperature
+template <class PRMSRC>
+__global__ void grid_consts_kernel(const float* __restrict__ T, float4* __restrict__ out, int nz, int nc, int ncp, int per_column,
+                                   const __grid_constant__ DevParams<float> P) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (c >= (per_column ? nc : 1)) return;
+    TD<double, DevParams<float>> td(P);
+    const size_t i = per_column ? size_t(k) * ncp + c : size_t(k);
+    const double t = double(T[i]);
+    const double lam = td.liquid_fraction_T(t);
+    const double ps_l = td.psat_liquid(t), ps_m = td.psat_mixed(t, lam);
+    const double RvT = double(P.td_R_v) * t;
+    out[i] = make_float4(float(ps_m / RvT), float(lam), float(RvT / ps_l), float(td.G_func(t, td.latent_heat_vapor(t), ps_l)));
+}
+
+template <int MOIST>
+__global__ void __launch_bounds__(PAIR_C * PAIR_TJ, 1)
+k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const __grid_constant__ DevParams<float> P) {
+    using L = Lay<MOIST, KID_PRECIP_2M>;
+    constexpr int NV = L::NV, NZ = PAIR_NZ, C = PAIR_C, TJ = PAIR_TJ;
+    constexpr int LPR = 2 * TJ, R = NZ / LPR, NR = NZ + 2;  // levels per round, rounds per stage, rows per plane (2 stash rows)
+    constexpr int VT1 = NV, VT2 = NV + 1, NP = NV + 2;       // planes: state variables, vt of ρq_rai, vt of N_rai
+    constexpr int sV = NR * C;
+    constexpr int NADV = adv_count<MOIST, KID_PRECIP_2M>();
+    static_assert(R >= 3, "the stage loop relies on two barriers between a block's WRITE phase and its next readers");
+    const int c = threadIdx.x, j = threadIdx.y;
+    const int gc = blockIdx.x * C + c;
+    const bool active = gc < A.nc;
+    const int ncp = A.ncp;
+    const size_t plane = size_t(NZ) * ncp;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* Ys = reinterpret_cast<float*>(smem_raw);  // [NP][NR][C]; rows NZ, NZ+1: old values of the level below a block (2 parities)
+    float* rds = Ys + NP * sV;                       // [NZ][C] ρ_dry
+    float* acts = rds + NZ * C;                      // [NZ][C] activation rate of the state the NEXT rhs is evaluated at
+    int* cb = reinterpret_cast<int*>(acts + NZ * C); // [2][C] cloud-base level (lowest activating level), two stages in flight
+
+    float w1c = 0, qsurf = 0, Ndc = 0;
+    if (active) {
+        for (int k = j; k < NZ; k += TJ) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) Ys[v * sV + k * C + c] = A.Y[v * plane + size_t(k) * ncp + gc];
+            rds[k * C + c] = A.rho_dry[A.prof_per_column ? size_t(k) * ncp + gc : size_t(k)];
+        }
+        w1c = A.w1[gc]; qsurf = A.q_surf[gc]; Ndc = A.Nd[gc];
+    }
+    if (j == 0) { cb[c] = INT_MAX; cb[C + c] = INT_MAX; }
+    __syncthreads();
+
+    const DevSwitches sw = A.sw;
+    const bool k1d = (A.model == KID_MODEL_K1D);  // velocity, activation, condensation on; col_sed: sedimentation only
+    const bool stale_Naer = (A.model == KID_MODEL_K1D_COL_SED) && A.aux_Naer != nullptr;
+    const float dt = A.dt, inv_dt = 1.f / dt, inv_dz = 1.f / A.dz;
+    const float half_inv_dz = 0.5f * inv_dz, fs = P.num_fcc_scale * inv_dz;
+    const float closed = sw.open_system_activation ? 0.f : -1.f;
+    const int nst = 3 * A.nsteps;
+    int first = INT_MAX;  // lowest activation candidate among this thread's levels, for the stage being prepared
+
+#pragma unroll 1
+    for (int it = -1; it < nst; ++it) {
+        const bool real = it >= 0;                 // it = -1: only the aux fields of the first stage are evaluated
+        const int stage = real ? it % 3 : 0;
+        const int itn = it + 1, stage_n = itn % 3;
+        const bool do_post = itn < nst;
+        const int parn = itn & 1, par = parn ^ 1;
+        const float tn = float(A.t0 + double(real ? it / 3 : 0) * double(dt));
+        const float ts = stage_time(stage, tn, dt);
+        const float tsn = stage_time(stage_n, float(A.t0 + double(itn / 3) * double(dt)), dt);
+        const float rk_b = stage == 0 ? 1.f : (stage == 1 ? 0.25f : 2.f / 3.f);
+        const float rk_a = 1.f - rk_b, rk_c = rk_b * dt;
+        const float rw = k1d ? rho_w_of_t(ts, w1c, P.kid_t1) : 0.f;
+        const float rw_n = k1d ? rho_w_of_t(tsn, w1c, P.kid_t1) : 0.f;
+        const float rw2 = 2.f * rw;
+        const float surf_flux[3] = {0.f, rw * qsurf, rw * Ndc * (1.f - qsurf) / 1.225f};
+        const bool fcc_tot = sw.qtot_flux_correction != 0;
+        int cbk = INT_MAX;
+
+#pragma unroll 1
+        for (int r = 0; r < R; ++r) {
+            const int k0 = r * LPR + 2 * j;  // this thread's pair: levels k0, k0 + 1
+            float* pa = Ys + k0 * C + c;     // + plane · sV
+            F2 adv[NADV];
+            F2 un[NV];
+            GridConst2 g;
+            if (active) {
+                if (real && stage != 0) {  // u^n of the stage combine (L2): requested first, consumed at the end of the WRITE phase
+                    const float* gU = A.Y + size_t(k0) * ncp + gc;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) un[v] = f2(gU[v * plane], gU[v * plane + ncp]);
+                }
+                {   // grid-point constants of the pair (L2): requested first, used after the barrier
+                    const size_t i0 = A.prof_per_column ? size_t(k0) * ncp + gc : size_t(k0);
+                    const float4 g0 = gconst[i0], g1 = gconst[i0 + (A.prof_per_column ? size_t(ncp) : size_t(1))];
+                    g.qvs_rho = f2(g0.x, g1.x); g.lam = f2(g0.y, g1.y); g.S_fac = f2(g0.z, g1.z); g.G = f2(g0.w, g1.w);
+                }
+                if (real) {
+                    // ---- READ phase.  OLD values of levels k0-1 .. k0+2: the level below a block was overwritten by the
+                    // previous round and sits in the stash row; at the domain boundaries the row is clamped (the value is
+                    // not used: the boundary cells are fixed up below).
+                    const bool bot = (k0 == 0), top = (k0 == NZ - 2);
+                    const int row_m = (j == 0) ? (r == 0 ? 0 : NZ + (r & 1)) : k0 - 1;
+                    const float* pm = Ys + row_m * C + c;
+                    const float* pu = Ys + (top ? NZ - 1 : k0 + 2) * C + c;
+                    const int km = bot ? 0 : k0 - 1, ku = top ? NZ - 1 : k0 + 2;
+                    // faces: f0 = (k0-1 | k0), f1 = (k0 | k0+1), f2 = (k0+1 | k0+2); f0 and f2 packed, f1 scalar.
+                    // Face velocities (air, air - vt_q, air - vt_N) pre-multiplied: wh = w / (2 dz) for the centred flux,
+                    // aw = fcc_scale |w| / dz for the first-order correction; Q_f = wh (y_hi + y_lo) - aw (y_hi - y_lo) is
+                    // the flux through face f (over dz), and the tendency of a cell is Q_lower - Q_upper.
+                    F2 wh02[3], aw02[3];
+                    float wh1[3], aw1[3];
+                    {
+                        const float rho_m = rds[km * C + c] + pm[L::tot * sV], rho_a = rds[k0 * C + c] + pa[L::tot * sV];
+                        const float rho_b = rds[(k0 + 1) * C + c] + pa[L::tot * sV + C], rho_u = rds[ku * C + c] + pu[L::tot * sV];
+                        const F2 wa02 = rw2 * vrcp(f2(rho_m, rho_b) + f2(rho_a, rho_u));
+                        const float wa1 = rw2 * rcp1(rho_a + rho_b);
+                        const F2 v1lo = f2(pm[VT1 * sV], pa[VT1 * sV + C]), v1hi = f2(pa[VT1 * sV], pu[VT1 * sV]);
+                        const F2 v2lo = f2(pm[VT2 * sV], pa[VT2 * sV + C]), v2hi = f2(pa[VT2 * sV], pu[VT2 * sV]);
+                        const F2 wv02[3] = {wa02, fma2(v1lo + v1hi, -0.5f, wa02), fma2(v2lo + v2hi, -0.5f, wa02)};
+                        const float wv1[3] = {wa1, fmaf(v1hi.x + v1lo.y, -0.5f, wa1), fmaf(v2hi.x + v2lo.y, -0.5f, wa1)};
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) {
+                            wh02[q] = wv02[q] * half_inv_dz; aw02[q] = vabs(wv02[q]) * fs;
+                            wh1[q] = wv1[q] * half_inv_dz; aw1[q] = fabsf(wv1[q]) * fs;
+                        }
+                    }
+                    static_for<0, NADV>([&](auto I) {
+                        constexpr int i = decltype(I)::value;
+                        constexpr AdvVar e = adv_entry<MOIST, KID_PRECIP_2M>(i);
+                        const bool fcc_on = (e.fcc == FCC_ALWAYS) || fcc_tot;
+                        const float ym = pm[e.idx * sV], ya = pa[e.idx * sV], yb = pa[e.idx * sV + C], yu = pu[e.idx * sV];
+                        const F2 lo = f2(ym, yb), hi = f2(ya, yu);
+                        const F2 G02 = fcc_on ? aw02[e.vel] * (hi - lo) : f2(0.f);
+                        const float G1 = fcc_on ? aw1[e.vel] * (yb - ya) : 0.f;
+                        const F2 F02 = wh02[e.vel] * (hi + lo);
+                        const float F1 = wh1[e.vel] * (ya + yb);
+                        const F2 Q02 = F02 - G02;
+                        const float Q1 = F1 - G1;
+                        adv[i] = f2(Q02.x - Q1, Q1 - Q02.y);
+                        // domain boundaries (one warp each, warp-uniform).  Extrapolate: the boundary cell takes the tendency of
+                        // its inner neighbour; SetValue: the boundary face flux of the divergence is prescribed, the flux
+                        // correction still extrapolates (DivergenceF2C / FluxCorrectionC2C, K1DModel/tendency.jl:274-435).
+                        if (bot) adv[i].x = (e.bot == BC_SET) ? (surf_flux[e.botval] * inv_dz - F1) + (G02.y - G1) : adv[i].y;
+                        if (top) adv[i].y = (e.top == BC_SET) ? F1 + (G1 - G02.x) : adv[i].x;
+                    });
+                    // the next round needs the OLD values of this block's last level (state and terminal velocities)
+                    if (j == TJ - 1 && r + 1 < R) {
+#pragma unroll
+                        for (int p = 0; p < NP; ++p) Ys[p * sV + (NZ + ((r + 1) & 1)) * C + c] = pa[p * sV + C];
+                    }
+                }
+            }
+#ifndef KID_PAIR_NOSYNC_EXPERIMENT
+            __syncthreads();  // every thread of the tile has read its old neighbours
+#endif
+            if constexpr (L::is2m) {
+                if (r == 0) {
+                    cbk = cb[par * C + c];  // complete: its last atomicMin precedes the barrier above
+                    // slot of the stage after next: its last readers (this read, one stage ago) passed two barriers since
+                }
+            }
+            if (!active) continue;
+
+            // ---- WRITE phase: sources + SSPRK33 stage combine in place, then the aux fields of the next stage
+            F2 y[NV];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) y[v] = f2(pa[v * sV], pa[v * sV + C]);
+            const F2 rd = f2(rds[k0 * C + c], rds[(k0 + 1) * C + c]);
+            if (real) {
+                PointX2 a;
+                thermo_point_x2<MOIST>(y, rd, g, a);
+                if (stale_Naer) a.N_aer = f2(A.aux_Naer[size_t(k0) * ncp + gc], A.aux_Naer[size_t(k0 + 1) * ncp + gc]);
+                F2 act = f2(0.f);
+                if (k1d) {
+                    const bool loc = sw.local_activation != 0;
+                    act = f2((loc || k0 == cbk) ? acts[k0 * C + c] : 0.f, (loc || k0 + 1 == cbk) ? acts[(k0 + 1) * C + c] : 0.f);
+                }
+                F2 tend[NV];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) tend[v] = f2(0.f);
+                if constexpr (L::neq) {
+                    if (k1d) {
+                        F2 cs_liq, cs_ice;
+                        cloud_sources_x2(P.inv_tau_relax_liq, P.inv_tau_relax_ice, a, g, cs_liq, cs_ice);
+                        tend[L::liq] = a.rho * cs_liq;
+                        tend[L::ice] = a.rho * cs_ice;
+                    }
+                }
+                Src2M s;
+                precip_sources_2m_x2(P, sw, a, g, inv_dt, s);
+                // precip_sources_tendency! (src/Common/tendency.jl:787-805)
+                tend[L::rai] = a.rho * s.s_rai;
+                tend[L::Na] = fma2(act, closed, s.s_Na);
+                tend[L::Nl] = s.s_Nl + act;
+                tend[L::Nr] = s.s_Nr;
+                if constexpr (L::neq) tend[L::liq] = fma2(a.rho, s.s_liq, tend[L::liq]);
+                static_for<0, NADV>([&](auto I) {
+                    constexpr int i = decltype(I)::value;
+                    constexpr AdvVar e = adv_entry<MOIST, KID_PRECIP_2M>(i);
+                    tend[e.idx] += adv[i];
+                    if (e.to_tot) tend[L::tot] += adv[i];  // precipitation also moves ρq_tot (K1DModel/tendency.jl:431-432)
+                });
+                // SSPRK33 as a convex combination  u_new = a·u^n + b·(y + dt·f(y))
+                float* gY = A.Y + size_t(k0) * ncp + gc;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const F2 yb = fma2(y[v], rk_b, tend[v] * rk_c);
+                    y[v] = (stage == 0) ? yb : fma2(un[v], rk_a, yb);
+                    pa[v * sV] = y[v].x;
+                    pa[v * sV + C] = y[v].y;
+                    if (stage == 2) { gY[v * plane] = y[v].x; gY[v * plane + ncp] = y[v].y; }
+                }
+            }
+            if (do_post) {
+                // aux of the state just formed, as the next rhs! call starts with (precompute_aux_thermo!,
+                // precompute_aux_precip!, precompute_aux_activation!: K1DModel/ode_utils.jl:33-38)
+                PointX2 a;
+                thermo_point_x2<MOIST>(y, rd, g, a);
+                F2 vq, vN;
+                terminal_velocities_x2(P, sw, a, vq, vN);
+                pa[VT1 * sV] = vq.x; pa[VT1 * sV + C] = vq.y;
+                pa[VT2 * sV] = vN.x; pa[VT2 * sV + C] = vN.y;
+                if (k1d) {
+                    // ARG activation rate (get_aerosol_activation_rate, K1DModel/tendency.jl:35-96).  Non-local activation
+                    // keeps only the LOWEST activating level: once this thread has a candidate its higher levels are skipped.
+                    const F2 S = fma2((a.q_tot - (a.q_liq + a.q_rai)) - a.q_ice, a.rho * g.S_fac, -1.f);
+                    const bool loc = sw.local_activation != 0;
+#pragma unroll 1
+                    for (int e = 0; e < 2; ++e) {  // rare, scalar: one copy of the ARG code
+                        const int k = k0 + e;
+                        float S_Nl = 0.f;
+                        const float Se = e ? S.y : S.x, Na = e ? a.N_aer.y : a.N_aer.x;
+                        if ((loc || first == INT_MAX) && !(Se < 0.f) && !(Na < 1.1920929e-07f)) {
+                            const size_t pi = A.prof_per_column ? size_t(k) * ncp + gc : size_t(k);
+                            const float T = A.T[pi], ps_l = A.ps_liq[pi];
+                            const float rho = e ? a.rho.y : a.rho.x, q_tot = e ? a.q_tot.y : a.q_tot.x;
+                            const float q_liq = e ? a.q_liq.y : a.q_liq.x, q_ice = e ? a.q_ice.y : a.q_ice.x;
+                            const float q_rai = e ? a.q_rai.y : a.q_rai.x, q_sno = e ? a.q_sno.y : a.q_sno.x;
+                            const float N_liq = e ? a.N_liq.y : a.N_liq.x, N_rai = e ? a.N_rai.y : a.N_rai.x;
+                            TD<float, DevParams<float>> td(P);
+                            const float p = L::neq ? td.air_pressure(T, rho, q_tot, q_liq + q_rai, q_ice + q_sno)
+                                                   : td.air_pressure(T, rho, q_tot, 0.f, 0.f);
+                            S_Nl = aerosol_activation_rate<float>(P, sw, q_tot, q_liq + q_rai, q_ice, N_liq + N_rai, Na, T, ps_l, p,
+                                                                  rho, rw_n, dt);
+                            // find_cloud_base! (K1DModel/tendency.jl:21-32): the accumulator starts at level 1 and is replaced
+                            // only while its S is 0 and the candidate's S is > 0
+                            const bool cand = (k == 0) ? (S_Nl != 0.f) : (S_Nl > 0.f);
+                            if (cand && first == INT_MAX) first = k;
+                        }
+                        acts[k * C + c] = S_Nl;
+                    }
+                    if (r == R - 1) {
+                        if (!loc && first != INT_MAX) atomicMin(&cb[parn * C + c], first);
+                        first = INT_MAX;
+                    }
+                }
+            }
+        }
+        // the slot just consumed serves the stage after next: every thread read it after this stage's first barrier and
+        // has passed at least two more barriers; the next writers (atomicMin above, next stage) come after the next barrier
+        if constexpr (L::is2m) { if (j == 0) cb[par * C + c] = INT_MAX; }
+    }
+}
+
+}  // namespace kid

@@ -125,6 +125,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         "kid_last_error": (C.c_char_p, []),
         "kid_version": (C.c_char_p, []),
         "kid_device_count": (C.c_int, []),
+        "kid_measure_fp32_peak": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
@@ -184,6 +185,15 @@ def bind_to_gpu_numa_node(pci_bus_id: str) -> dict:
 
 def _ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def measure_fp32_peak(device: int = 0, lib: C.CDLL | None = None) -> dict:
+    """FFMA micro-benchmark on the device (kid_measure_fp32_peak): the Float32 roofline denominator, measured in the run."""
+    lib = lib or load_library()
+    f, sms, khz = C.c_double(), C.c_int32(), C.c_int32()
+    if lib.kid_measure_fp32_peak(int(device), C.byref(f), C.byref(sms), C.byref(khz)) != 0:
+        raise KidCudaError(lib.kid_last_error().decode())
+    return {"flops_per_s": f.value, "sm_count": sms.value, "sm_clock_khz": khz.value}
 
 
 class Handle:

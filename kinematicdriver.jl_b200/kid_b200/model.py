@@ -9,6 +9,7 @@ profiles (aux.thermo_variables.{ρ_dry,T}), per-column scalars and the initial s
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -339,6 +340,41 @@ def materialise(case: Case, handle=None) -> Case:
     out.Y0 = h.get_state()
     out.col_scalars = dict(case.col_scalars)
     out.col_scalars[COL_Q_SURF] = np.full(case.cfg.nc, case.device_ic["q_surf"], dtype=case.dtype)
+    return out
+
+
+def _host_member_ic(job):
+    FT, opts = job
+    cs = k1d_case(FT, nc=1, **opts)
+    return cs.ρ_dry, cs.T, cs.Y0[0], cs.col_scalars[COL_Q_SURF][0]
+
+
+def materialise_on_host(case: Case) -> Case:
+    """The same, without a GPU: the hydrostatic profile and initial state of every member from the host restatement
+    (initial_condition.py: one ρ_ivp solve per member — small samples only; the CPU arm of bench.py)."""
+    if case.Y0 is not None:
+        return case
+    import copy
+    opts = {k: v for k, v in case.meta["opts"].items() if k in _K1D_DEFAULTS}
+    FT = case.dtype
+    p0 = np.asarray(case.device_ic["p0"], dtype=np.float64)
+    Nd = np.asarray(case.col_scalars[COL_PRESCRIBED_ND], dtype=np.float64)
+    jobs = [(FT, {**opts, "p0": float(p0[c])}) for c in range(case.cfg.nc)]
+    workers = min(len(jobs), len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 1)
+    if workers > 1 and len(jobs) >= 16:
+        import concurrent.futures as cf
+        import multiprocessing as mp
+        with cf.ProcessPoolExecutor(workers, mp_context=mp.get_context("fork")) as ex:
+            res = list(ex.map(_host_member_ic, jobs, chunksize=max(1, len(jobs) // (4 * workers))))
+    else:
+        res = [_host_member_ic(j) for j in jobs]
+    ρ, T, Y, q = map(list, zip(*res))
+    out = copy.copy(case)
+    out.ρ_dry, out.T, out.Y0 = np.asarray(ρ, dtype=FT), np.asarray(T, dtype=FT), np.asarray(Y, dtype=FT)
+    if "N_aer" in case.var_names:  # IC N_aer = prescribed_Nd·ρ_dry/1.225 (initial_condition.jl:171)
+        out.Y0[:, case.var_names.index("N_aer"), :] = (Nd[:, None] * out.ρ_dry.astype(np.float64) / 1.225).astype(FT)
+    out.col_scalars = dict(case.col_scalars)
+    out.col_scalars[COL_Q_SURF] = np.asarray(q, dtype=FT)
     return out
 
 

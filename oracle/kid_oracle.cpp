@@ -12,9 +12,13 @@
 // Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl
 // reference) may load the resulting liboracle; libkid_cuda.so never does.
 //
-// Build: see oracle/Makefile (g++ -O2 -fopenmp -ffp-contract=off).
+// Build: see oracle/Makefile (portable: g++ -O2 -fopenmp -ffp-contract=off; `make native`: -O3 -march=native, built on the
+// machine that times it — the CPU arm of bench.py).
 #include <cstdint>
 #include <cstring>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <string>
 #include <vector>
 
@@ -421,7 +425,8 @@ struct Model {
     }
     // out[k] += −∂(w̃ · If(x)), ∂ = DivergenceF2C(bottom, top)
     void add_minus_div(const std::vector<FT>& wf, const FT* x, BC bot, FT bot_val, BC top, FT top_val, FT* out) {
-        std::vector<FT> F(nz + 1, FT(0)), D(nz, FT(0));
+        static thread_local std::vector<FT> F, D;  // scratch: no allocation inside the column loop
+        F.assign(nz + 1, FT(0)); D.assign(nz, FT(0));
         for (int f = 1; f < nz; ++f) F[f] = wf[f] * ((x[f] + x[f - 1]) / FT(2));
         for (int k = 1; k < nz - 1; ++k) D[k] = (F[k + 1] - F[k]) / dz;
         if (bot == SET_VALUE) D[0] = (F[1] - bot_val) / dz; else D[0] = D[1];
@@ -430,7 +435,8 @@ struct Model {
     }
     // out[k] += fcc(w̃, x), FluxCorrectionC2C(bottom = Extrapolate, top = Extrapolate)
     void add_fcc(const std::vector<FT>& wf, const FT* x, FT* out) {
-        std::vector<FT> C(nz, FT(0));
+        static thread_local std::vector<FT> C;
+        C.assign(nz, FT(0));
         for (int k = 1; k < nz - 1; ++k)
             C[k] = P.num_fcc_scale * (kidm::fabs(wf[k + 1]) * (x[k + 1] - x[k]) - kidm::fabs(wf[k]) * (x[k] - x[k - 1])) / dz;
         C[0] = C[1];
@@ -441,7 +447,7 @@ struct Model {
     // K1D src/K1DModel/tendency.jl:274-289 (Eq), :306-332 (NonEq);
     // K2D src/K2DModel/tendency.jl:57-112 (vertical part; fcc on q_tot always)
     void advection_tendency_moisture(FT* dY, const FT* Yc, ColAux<FT>& a, bool k2d) {
-        std::vector<FT> wf;
+        static thread_local std::vector<FT> wf;
         face_velocity(a, nullptr, wf);
         bool fc_tot = k2d ? true : sw.qtot_flux_correction;
         add_minus_div(wf, var(Yc, L.tot), SET_VALUE, a.rho_w0 * a.q_surf, EXTRAPOLATE, 0, var(dY, L.tot));
@@ -462,7 +468,7 @@ struct Model {
                                    std::vector<FT>& S2) {
         S1.assign(nz, FT(0));
         S2.assign(nz, FT(0));
-        std::vector<FT> wf;
+        static thread_local std::vector<FT> wf;
         BC top = k2d ? EXTRAPOLATE : SET_VALUE;
         if (sw.precip == KID_PRECIP_1M) {
             face_velocity(a, a.vt_rai.data(), wf);
@@ -513,7 +519,7 @@ struct Model {
         }
         precip_sources_tendency(dY, a);
         if (cfg.model == KID_MODEL_K1D || cfg.model == KID_MODEL_K1D_COL_SED) {
-            std::vector<FT> S1, S2;
+            static thread_local std::vector<FT> S1, S2;
             advection_tendency_moisture(dY, Yc, a, false);
             advection_tendency_precip(dY, Yc, a, false, S1, S2);
             accumulate_precip_advection(dY, S1, S2);
@@ -835,6 +841,17 @@ struct Oracle : OracleBase {
 using namespace kidoracle;
 
 extern "C" {
+// OpenMP threads of the column loops.  torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: bench.py sets the
+// count explicitly so that the CPU arm uses all host cores under torchrun too.  Returns the count in effect.
+int kidoracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 void* kidoracle_create(const kid_config_t* cfg) {
     Layout L;
     if (!make_layout(cfg->moisture, cfg->precip, L)) return nullptr;

@@ -31,13 +31,10 @@ def build(force: bool = False) -> Path:
     return so
 
 
-def load() -> C.CDLL:
-    global _LIB
-    if _LIB is None:
-        so = _HERE / "libkid_oracle.so"
-        if not so.exists():
-            build()
-        lib = C.CDLL(str(so))
+def _bind(so: Path) -> C.CDLL:
+    if True:
+        if True:
+            lib = C.CDLL(str(so))
         H = C.c_void_p
         lib.kidoracle_create.restype = H
         lib.kidoracle_create.argtypes = [C.POINTER(KidConfig)]
@@ -56,8 +53,42 @@ def load() -> C.CDLL:
         lib.kidoracle_expint_E1.restype = C.c_double
         lib.kidoracle_expint_E1.argtypes = [C.c_double]
         lib.kidoracle_gll.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-        _LIB = lib
+        lib.kidoracle_set_threads.argtypes = [C.c_int]
+        lib.kidoracle_set_threads.restype = C.c_int
+    return lib
+
+
+def load() -> C.CDLL:
+    """The portable build (g++ -O2): the parity checker of the test-suite."""
+    global _LIB
+    if _LIB is None:
+        so = _HERE / "libkid_oracle.so"
+        if not so.exists():
+            build()
+        _LIB = _bind(so)
     return _LIB
+
+
+_NATIVE = None
+
+
+def load_native():
+    """(library, description): `make native` (g++ -O3 -march=native) built ON THIS MACHINE — the CPU-baseline build of
+    bench.py; falls back to the portable build when the host has no compiler."""
+    global _NATIVE
+    if _NATIVE is None:
+        so = _HERE / "_native" / "libkid_oracle.so"
+        try:
+            subprocess.run(["make", "-C", str(_HERE), "native"], check=True, capture_output=True)
+            _NATIVE = (_bind(so), "g++ -O3 -march=native -fopenmp -ffp-contract=off, built on this host")
+        except Exception:  # no compiler on the box: time the portable build and say so
+            _NATIVE = (load(), "g++ -O2 -fopenmp -ffp-contract=off (portable build)")
+    return _NATIVE
+
+
+def set_threads(n: int, lib=None) -> int:
+    """OpenMP threads of the column loops (torchrun exports OMP_NUM_THREADS=1 to its workers); returns the count in effect."""
+    return int((lib or load()).kidoracle_set_threads(int(n)))
 
 
 def _ptr(a):
@@ -65,8 +96,8 @@ def _ptr(a):
 
 
 class OracleHandle:
-    def __init__(self, cfg: KidConfig):
-        self.lib = load()
+    def __init__(self, cfg: KidConfig, lib=None):
+        self.lib = lib or load()
         self.cfg = cfg
         self.dtype = dtype_of(cfg.float_type)
         self._h = C.c_void_p(self.lib.kidoracle_create(C.byref(cfg)))
