@@ -267,6 +267,8 @@ def run_ours(args):
     nc = cb - ca
     gcase = global_case(args, world, local)
     case = M.slice_columns(gcase, ca, cb)
+    if args.kernel == "scalar":
+        case.cfg.reserved[3] = 1  # A/B: the scalar tile kernel instead of the packed two-levels-per-thread kernel
     h = M.make_handle(case, Handle)
     spl = args.steps_per_launch
     stream = torch.cuda.ExternalStream(h.stream, device=local)
@@ -428,6 +430,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample length (0 = skip)")
     ap.add_argument("--no-parity", dest="parity", action="store_false", help="skip the in-bench parity sample")
     ap.add_argument("--e2e-chunks", type=int, default=32, help="column chunks (handles/streams) of the end-to-end pipelined call")
+    ap.add_argument("--kernel", default="pair", choices=["pair", "scalar"], help="step kernel of the resident leg (A/B measurements)")
     ap.add_argument("--order", default="sorted", choices=["sorted", "hash"], help="storage order of the ensemble members")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -57,6 +57,8 @@ struct kid_handle {
     void *prm_sets = nullptr, *col_to_set = nullptr;  // per-column parameter sets (calibration ensembles)
     void *ps_liq = nullptr, *ps_mix = nullptr;        // p_sat(T) per grid point (profile constants)
     void* gconst = nullptr;                            // float4 per grid point: constants of the packed 2M kernel (kid_pair_kernel.cuh)
+    CUtensorMap state_map{};                           // TMA descriptor of the device state [var][level][column] (box 32 x 32 x nv)
+    bool state_map_ok = false;
     bool consts_dirty = true;
     size_t staging_bytes = 0, out_bytes = 0;
     int prof_per_column = 0;
@@ -246,6 +248,29 @@ bool pair_capable(const kid_handle* h) {
            h->C == 32 && h->cfg.reserved[3] == 0;
 }
 
+// TMA descriptor of the device state for k1d_pair_kernel: 3-D tensor (columns, levels, variables), Float32, box = one
+// round of one tile (32 columns x 32 levels x all variables).  cuTensorMapEncodeTiled is a driver entry point: fetched
+// through the runtime so that the library keeps linking against the static cudart only.
+int make_state_map(kid_handle* h) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    KID_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t gdim[3] = {cuuint64_t(h->ncp), cuuint64_t(h->cfg.nz), cuuint64_t(h->nv)};
+    const cuuint64_t gstride[2] = {cuuint64_t(h->ncp) * 4, cuuint64_t(h->ncp) * h->cfg.nz * 4};
+    const cuuint32_t box[3] = {cuuint32_t(PAIR_C), 2 * cuuint32_t(PAIR_TJ), cuuint32_t(h->nv)};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = reinterpret_cast<EncodeFn>(fn)(&h->state_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, h->Y, gdim, gstride, box, estr,
+                                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (" + std::to_string(int(r)) + ")");
+    h->state_map_ok = true;
+    return 0;
+}
+
 int check_ready(kid_handle* h) {
     if (!h) return fail("null handle");
     if (!h->params_set) return fail("kid_set_params has not been called");
@@ -260,6 +285,7 @@ int check_ready(kid_handle* h) {
         if (e != cudaSuccess) return fail(std::string("profile_consts_kernel launch: ") + cudaGetErrorString(e));
         h->launches++;
         if (pair_capable(h)) {
+            if (!h->state_map_ok && make_state_map(h)) return 1;
             const size_t n = h->prof_per_column ? size_t(h->cfg.nz) * h->ncp : size_t(h->cfg.nz);
             if (h->gconst) cudaFree(h->gconst);
             h->gconst = nullptr;
@@ -305,8 +331,8 @@ int choose_tile(kid_handle* h) {
 int launch_tile(kid_handle* h, double t0, int nsteps, int diag_mode, int field, int update_prev = 0) {
     if (diag_mode == 2 && field >= 0) { h->diag_nfields = 1; h->diag_fields[0] = field; }  // field < 0: h->diag_fields preset
     cudaError_t e;
-    if (diag_mode == 0 && pair_capable(h) && h->gconst) {
-        e = h->lt->pair_f(h->cfg.moisture, make_args<float>(h, t0, nsteps, 0, 0), (const float4*)h->gconst, h->prm_f, h->stream);
+    if (diag_mode == 0 && pair_capable(h) && h->gconst && h->state_map_ok) {
+        e = h->lt->pair_f(h->cfg.moisture, make_args<float>(h, t0, nsteps, 0, 0), (const float4*)h->gconst, h->state_map, h->prm_f, h->stream);
         if (e != cudaSuccess) return fail(std::string("k1d_pair_kernel launch: ") + cudaGetErrorString(e));
         h->launches++;
         return 0;

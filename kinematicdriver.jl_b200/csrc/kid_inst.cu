@@ -84,17 +84,17 @@ size_t smem_bytes(int moisture, int nz, int C, bool pcp) {
 
 #if KID_PRECIP == 3
 template <int MOIST>
-cudaError_t pair_m(const KArgs<float>& a, const float4* gconst, const DevParams<float>& P, cudaStream_t s) {
+cudaError_t pair_m(const KArgs<float>& a, const float4* gconst, const CUtensorMap& tmY, const DevParams<float>& P, cudaStream_t s) {
     auto kern = k1d_pair_kernel<MOIST>;
     const size_t smem = k1d_pair_smem_bytes<MOIST>();
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     dim3 block(PAIR_C, PAIR_TJ), grid((a.nc + PAIR_C - 1) / PAIR_C);
-    kern<<<grid, block, smem, s>>>(a, gconst, P);
+    kern<<<grid, block, smem, s>>>(a, gconst, tmY, P);
     return cudaGetLastError();
 }
-cudaError_t pair(int moisture, const KArgs<float>& a, const float4* gconst, const DevParams<float>& P, cudaStream_t s) {
-    return moisture == KID_MOIST_EQ ? pair_m<KID_MOIST_EQ>(a, gconst, P, s) : pair_m<KID_MOIST_NONEQ>(a, gconst, P, s);
+cudaError_t pair(int moisture, const KArgs<float>& a, const float4* gconst, const CUtensorMap& tmY, const DevParams<float>& P, cudaStream_t s) {
+    return moisture == KID_MOIST_EQ ? pair_m<KID_MOIST_EQ>(a, gconst, tmY, P, s) : pair_m<KID_MOIST_NONEQ>(a, gconst, tmY, P, s);
 }
 cudaError_t gconsts(const KArgs<float>& a, const DevParams<float>& P, float4* out, cudaStream_t s) {
     const int ncol = a.prof_per_column ? a.nc : 1;

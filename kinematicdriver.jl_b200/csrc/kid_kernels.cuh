@@ -36,6 +36,7 @@ template <class FT> constexpr int tile_max_threads() { return sizeof(FT) == 4 ? 
 }
 #include <type_traits>
 
+#include "kid_f2.cuh"
 #include "kid_physics.cuh"
 
 // -DKID_DEBUG_BOUNDS (make debug): device-side asserts on the shared-memory rows the tile kernel addresses — the
@@ -457,13 +458,13 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                     face_w(kc + 1, rho_u, rho_c, wh_up, aw_up);
                     face_w(kc, rho_c, rho_l, wh_lo, aw_lo);
                 }
-                static_for<0, NADV>([&](auto I) {
+                // one advected variable: centred flux divergence + first-order correction from the pre-scaled face velocities
+                auto stencil_one = [&](auto I) {
                     constexpr int i = decltype(I)::value;
                     constexpr AdvVar e = adv_entry<MOIST, PRECIP>(i);
                     // K2D (K2DModel/tendency.jl:114-213): N_liq and N_aer are not advected, the precipitation
                     // divergence extrapolates at BOTH ends, q_tot always gets the flux correction
                     if (k2d && (e.idx == L::Nl || e.idx == L::Na)) return;
-                    const int top_bc = (k2d && e.vel != VEL_AIR) ? BC_EXTRAP : e.top;
                     const FT yk = c_p[e.idx * sV], yu = u_p[e.idx * sV], yl = l_p[e.idx * sV];
                     const FT Fup = wh_up[e.vel] * (yu + yk), Flo = wh_lo[e.vel] * (yk + yl);  // face fluxes / dz
                     const FT fc = aw_up[e.vel] * (yu - yk) - aw_lo[e.vel] * (yk - yl);
@@ -471,7 +472,28 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                     FT a_i = Flo - Fup;
                     if (fcc_on) a_i += fc;
                     adv[i] = a_i;
-                });
+                };
+                if constexpr (sizeof(FT) == 4) {
+                    // Float32: two variables per packed instruction (FADD2 / FFMA2, kid_f2.cuh) — 4 adds + 4 fmas for two
+                    // stencils; the per-variable face coefficients are paired (the flux correction switched off = coefficient 0)
+                    static_for<0, NADV / 2>([&](auto I) {
+                        constexpr int i = 2 * decltype(I)::value, i2 = i + 1;
+                        constexpr AdvVar e = adv_entry<MOIST, PRECIP>(i), e2 = adv_entry<MOIST, PRECIP>(i2);
+                        const bool f1 = (e.fcc == FCC_ALWAYS) || A.sw.qtot_flux_correction || k2d;
+                        const bool f2on = (e2.fcc == FCC_ALWAYS) || A.sw.qtot_flux_correction || k2d;
+                        const F2 yk = f2(c_p[e.idx * sV], c_p[e2.idx * sV]), yu = f2(u_p[e.idx * sV], u_p[e2.idx * sV]);
+                        const F2 yl = f2(l_p[e.idx * sV], l_p[e2.idx * sV]);
+                        const F2 whu = f2(wh_up[e.vel], wh_up[e2.vel]), whl = f2(wh_lo[e.vel], wh_lo[e2.vel]);
+                        const F2 awu = f2(f1 ? aw_up[e.vel] : 0.f, f2on ? aw_up[e2.vel] : 0.f);
+                        const F2 awl = f2(f1 ? aw_lo[e.vel] : 0.f, f2on ? aw_lo[e2.vel] : 0.f);
+                        const F2 r = fma2(whl, yk + yl, fma2(-whu, yu + yk, fma2(awu, yu - yk, -(awl * (yk - yl)))));
+                        adv[i] = (k2d && (e.idx == L::Nl || e.idx == L::Na)) ? 0.f : r.x;
+                        adv[i2] = (k2d && (e2.idx == L::Nl || e2.idx == L::Na)) ? 0.f : r.y;
+                    });
+                    if constexpr (NADV % 2 == 1) stencil_one(std::integral_constant<int, NADV - 1>{});
+                } else {
+                    static_for<0, NADV>(stencil_one);
+                }
                 // SetValue boundaries (two warps of the tile, warp-uniform branch): one face flux of D is prescribed
                 if (is_bot || is_top) {
                     static_for<0, NADV>([&](auto I) {
@@ -554,13 +576,24 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
                     // SSPRK33 as a convex combination  u_new = a·u^n + b·(y + dt·f(y)),  (a, b) = (0, 1), (3/4, 1/4),
                     // (1/3, 2/3): OrdinaryDiffEq's (3u + y + dt k)/4 and (u + 2y + 2dt k)/3 with the division folded in
                     FT* gY = A.Y + size_t(k) * ncp + gc;
+                    FT yn[NV];
+                    if constexpr (sizeof(FT) == 4) {  // two variables per packed instruction
+#pragma unroll
+                        for (int v = 0; v + 1 < NV; v += 2) {
+                            const F2 u2 = (stage == 0) ? f2(y[v], y[v + 1]) : f2(un[v], un[v + 1]);
+                            const F2 r = fma2(u2, rk_a, fma2(f2(y[v], y[v + 1]), rk_b, f2(tend[v], tend[v + 1]) * rk_c));
+                            yn[v] = r.x; yn[v + 1] = r.y;
+                        }
+                        if constexpr (NV % 2 == 1) yn[NV - 1] = rk_a * ((stage == 0) ? y[NV - 1] : un[NV - 1]) + (rk_b * y[NV - 1] + rk_c * tend[NV - 1]);
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) yn[v] = rk_a * ((stage == 0) ? y[v] : un[v]) + (rk_b * y[v] + rk_c * tend[v]);
+                    }
 #pragma unroll
                     for (int v = 0; v < NV; ++v) {
-                        const FT u = (stage == 0) ? y[v] : un[v];
-                        const FT yn = rk_a * u + (rk_b * y[v] + rk_c * tend[v]);
                         KID_ASSERT_ROW(k, nz);
-                        Ys[sidx(v, k)] = yn;
-                        if (stage == 2) gY[v * plane] = yn;
+                        Ys[sidx(v, k)] = yn[v];
+                        if (stage == 2) gY[v * plane] = yn[v];
                     }
                 }
             }

@@ -2,12 +2,17 @@
 // kernel translation units (kid_inst.cu compiled once per KID_PRECIP value, so the four
 // heavy instantiation sets build in parallel).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "kid_diag.cuh"
 #include "kid_kernels.cuh"
 
 namespace kid {
+
+// tile of k1d_pair_kernel (kid_pair_kernel.cuh): 128 levels x 16 columns, 16 level-pair rows (256 threads, 128 registers):
+// two tiles are resident per SM, so the barrier waits of one overlap with the work of the other
+constexpr int PAIR_NZ = 128, PAIR_C = 16, PAIR_TJ = 16, PAIR_CTAS_PER_SM = 2;
 
 struct LaunchTable {
     // K1D / col_sed / (diag of) Box: tile kernel.  diag = false: step; true: rhs / aux mode.
@@ -24,7 +29,7 @@ struct LaunchTable {
     size_t (*k1d_smem_d)(int moisture, int nz, int C, bool per_column_params);
     // Precipitation2M, Float32, 128 levels, shared parameter set: the packed two-levels-per-thread step kernel
     // (kid_pair_kernel.cuh) and its per-grid-point constants; null for the other precipitation styles
-    cudaError_t (*pair_f)(int moisture, const KArgs<float>&, const float4* gconst, const DevParams<float>&, cudaStream_t);
+    cudaError_t (*pair_f)(int moisture, const KArgs<float>&, const float4* gconst, const CUtensorMap& state_map, const DevParams<float>&, cudaStream_t);
     cudaError_t (*gconsts_f)(const KArgs<float>&, const DevParams<float>&, float4* out, cudaStream_t);
 };
 

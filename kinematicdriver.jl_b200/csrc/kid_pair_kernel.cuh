@@ -12,6 +12,10 @@
 //    two grid points.  The two cells share their middle face, so the stencil needs 3 face fluxes and 4 loads per
 //    variable for 2 cells instead of 4 and 6.  512 threads x 128 registers per tile (16 level-pairs x 32 columns per
 //    round, 4 rounds per stage).
+//  * the two global inputs of a round never pass through registers: u^n of the stage combine — a 32 columns x 32 levels x
+//    NV variables box of the state — is fetched by ONE TMA instruction (cp.async.bulk.tensor.3d, completion on an
+//    mbarrier) while the sources are evaluated, the grid-point constants by cp.async during the READ phase.  (As register loads they tied up scoreboard slots that the
+//    shared-memory loads of the stencil then had to wait on: 12 % of the issue stalls of the first version.)
 //  * there is no separate pass 1: the WRITE phase of stage s evaluates the terminal velocities, the ARG activation rate
 //    and the cloud-base candidate of the NEW state it has just formed, i.e. the aux fields stage s+1 needs
 //    (precompute_aux_precip!, precompute_aux_activation!; K1DModel/ode_utils.jl:30-47 evaluates them at the start of
@@ -21,17 +25,73 @@
 // Time-invariant functions of T per grid point (q_vs ρ, λ(T), R_v T / p_sat, G(T)) come from a float4 array filled at
 // upload (grid_consts_kernel), so T itself is only read by the rare ARG evaluation.
 #pragma once
+#include <cuda.h>  // CUtensorMap
+
 #include "kid_kernels.cuh"
 #include "kid_physics_x2.cuh"
 
 namespace kid {
 
-constexpr int PAIR_NZ = 128, PAIR_C = 32, PAIR_TJ = 16;
 
+constexpr int PAIR_LPR = 2 * PAIR_TJ;  // levels per round
+
+// shared memory of one tile: state + terminal-velocity planes (NZ levels + 2 stash rows each), ρ_dry, the staging buffers
+// of one round (u^n of the stage combine: bulk copies; grid-point constants: cp.async), cloud-base slots, one mbarrier
 template <int MOIST>
 inline size_t k1d_pair_smem_bytes() {
     using L = Lay<MOIST, KID_PRECIP_2M>;
-    return (size_t(L::NV + 2) * (PAIR_NZ + 2) * PAIR_C + size_t(2) * PAIR_NZ * PAIR_C) * sizeof(float) + size_t(2) * PAIR_C * sizeof(int);
+    return (size_t(L::NV + 2) * (PAIR_NZ + 2) * PAIR_C + size_t(PAIR_NZ) * PAIR_C + size_t(L::NV) * PAIR_LPR * PAIR_C) * sizeof(float) +
+           size_t(PAIR_LPR) * PAIR_C * (sizeof(float2) + sizeof(float)) + size_t(2) * PAIR_C * sizeof(int) + 16;
+}
+
+// ---- sm_90+/sm_100 asynchronous-copy plumbing (PTX): mbarrier, bulk copy global -> shared (UBLKCP), cp.async (LDGSTS)
+namespace pairasync {
+KID_DEV unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+KID_DEV void mbar_init(void* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+KID_DEV void mbar_arrive_expect_tx(void* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+KID_DEV void mbar_wait(void* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "KID_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra KID_MBAR_DONE;\n"
+        "bra KID_MBAR_WAIT;\n"
+        "KID_MBAR_DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA: one 3-D box (columns x levels x variables) global -> shared; completion is signalled on the mbarrier
+KID_DEV void tma_load_3d(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, void* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                     smem_u32(dst_smem)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+KID_DEV void cp_async8(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+KID_DEV void cp_async4(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+KID_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+KID_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// generic-proxy writes to global memory (the stage-3 state store) before later bulk copies (async proxy) read them
+KID_DEV void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+}  // namespace pairasync
+
+// ARG activation rate of one grid point (get_aerosol_activation_rate, K1DModel/tendency.jl:35-96).  Rare (cloud-base
+// candidates only) and large: kept out of line so that the hot loop stays small.
+template <bool NEQ>
+__device__ __noinline__ float pair_activation_rate(const DevParams<float>& P, const DevSwitches& sw, float T, float ps_l, float rho,
+                                                   float q_tot, float q_liq, float q_ice, float q_rai, float q_sno, float N_liq,
+                                                   float N_rai, float N_aer, float rw, float dt) {
+    TD<float, DevParams<float>> td(P);
+    const float p = NEQ ? td.air_pressure(T, rho, q_tot, q_liq + q_rai, q_ice + q_sno) : td.air_pressure(T, rho, q_tot, 0.f, 0.f);
+    return aerosol_activation_rate<float>(P, sw, q_tot, q_liq + q_rai, q_ice, N_liq + N_rai, N_aer, T, ps_l, p, rho, rw, dt);
 }
 
 // per-grid-point constants (see GridConst2): computed in double from the Float32 temperature
@@ -47,51 +107,78 @@ __global__ void grid_consts_kernel(const float* __restrict__ T, float4* __restri
     const double lam = td.liquid_fraction_T(t);
     const double ps_l = td.psat_liquid(t), ps_m = td.psat_mixed(t, lam);
     const double RvT = double(P.td_R_v) * t;
-    out[i] = make_float4(float(ps_m / RvT), float(lam), float(RvT / ps_l), float(td.G_func(t, td.latent_heat_vapor(t), ps_l)));
+    out[i] = make_float4(float(ps_m / RvT), float(RvT / ps_l), float(lam), float(td.G_func(t, td.latent_heat_vapor(t), ps_l)));  // (qvs_rho, S_fac, lam, G)
 }
 
 template <int MOIST>
-__global__ void __launch_bounds__(PAIR_C * PAIR_TJ, 1)
-k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const __grid_constant__ DevParams<float> P) {
+__global__ void __launch_bounds__(PAIR_C * PAIR_TJ, PAIR_CTAS_PER_SM)
+k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const __grid_constant__ CUtensorMap tmY,
+                const __grid_constant__ DevParams<float> P) {
     using L = Lay<MOIST, KID_PRECIP_2M>;
+    using namespace pairasync;
     constexpr int NV = L::NV, NZ = PAIR_NZ, C = PAIR_C, TJ = PAIR_TJ;
-    constexpr int LPR = 2 * TJ, R = NZ / LPR, NR = NZ + 2;  // levels per round, rounds per stage, rows per plane (2 stash rows)
-    constexpr int VT1 = NV, VT2 = NV + 1, NP = NV + 2;       // planes: state variables, vt of ρq_rai, vt of N_rai
+    constexpr int LPR = PAIR_LPR, R = NZ / LPR, NR = NZ + 2;  // levels per round, rounds per stage, rows per plane (2 stash rows)
+    constexpr int VT1 = NV, VT2 = NV + 1, NP = NV + 2;         // planes: state variables, vt of ρq_rai, vt of N_rai
     constexpr int sV = NR * C;
+    constexpr int HO = (NZ / 2) * C;  // a plane stores its even levels first, then the odd ones: offset of level k0 + 1 from level k0
     constexpr int NADV = adv_count<MOIST, KID_PRECIP_2M>();
+    constexpr unsigned UN_BYTES = NV * LPR * C * sizeof(float);
     static_assert(R >= 3, "the stage loop relies on two barriers between a block's WRITE phase and its next readers");
     const int c = threadIdx.x, j = threadIdx.y;
-    const int gc = blockIdx.x * C + c;
+    const int tid = j * C + c;
+    const int gc0 = blockIdx.x * C, gc = gc0 + c;
     const bool active = gc < A.nc;
     const int ncp = A.ncp;
     const size_t plane = size_t(NZ) * ncp;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* Ys = reinterpret_cast<float*>(smem_raw);  // [NP][NR][C]; rows NZ, NZ+1: old values of the level below a block (2 parities)
-    float* rds = Ys + NP * sV;                       // [NZ][C] ρ_dry
-    float* acts = rds + NZ * C;                      // [NZ][C] activation rate of the state the NEXT rhs is evaluated at
-    int* cb = reinterpret_cast<int*>(acts + NZ * C); // [2][C] cloud-base level (lowest activating level), two stages in flight
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* Ys = reinterpret_cast<float*>(smem_raw);    // [NP][NR][C]; rows NZ, NZ+1: old values of the level below a block (2 parities)
+    float* rds = Ys + NP * sV;                         // [NZ][C] ρ_dry
+    float* uns = rds + NZ * C;                         // [NV][LPR][C] u^n of this round's levels (bulk copies)
+    float2* gca = reinterpret_cast<float2*>(uns + NV * LPR * C);  // [LPR][C] (q_vs ρ, S_fac) of this round's levels (cp.async)
+    float* gcb = reinterpret_cast<float*>(gca + LPR * C);        // [LPR][C] λ(T)
+    int* cb = reinterpret_cast<int*>(gcb + LPR * C);   // [2][C] cloud-base level (lowest activating level), two stages in flight
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(cb + 2 * C);
 
+    // row of level k inside a plane: even levels first, then the odd ones.  The pair rows (k0, k0 + 1) of consecutive
+    // threadIdx.y are then contiguous, so a warp that spans two pair-rows (C = 16) still reads conflict-free.
+    auto lrow = [](int k) { return (k & 1) * (NZ / 2) + (k >> 1); };
     float w1c = 0, qsurf = 0, Ndc = 0;
     if (active) {
         for (int k = j; k < NZ; k += TJ) {
 #pragma unroll
-            for (int v = 0; v < NV; ++v) Ys[v * sV + k * C + c] = A.Y[v * plane + size_t(k) * ncp + gc];
-            rds[k * C + c] = A.rho_dry[A.prof_per_column ? size_t(k) * ncp + gc : size_t(k)];
+            for (int v = 0; v < NV; ++v) Ys[v * sV + lrow(k) * C + c] = A.Y[v * plane + size_t(k) * ncp + gc];
+            rds[lrow(k) * C + c] = A.rho_dry[A.prof_per_column ? size_t(k) * ncp + gc : size_t(k)];
         }
         w1c = A.w1[gc]; qsurf = A.q_surf[gc]; Ndc = A.Nd[gc];
     }
     if (j == 0) { cb[c] = INT_MAX; cb[C + c] = INT_MAX; }
+    if (tid == 0) mbar_init(mbar, 1);
     __syncthreads();
 
     const DevSwitches sw = A.sw;
     const bool k1d = (A.model == KID_MODEL_K1D);  // velocity, activation, condensation on; col_sed: sedimentation only
+    const bool loc = sw.local_activation != 0;
     const bool stale_Naer = (A.model == KID_MODEL_K1D_COL_SED) && A.aux_Naer != nullptr;
     const float dt = A.dt, inv_dt = 1.f / dt, inv_dz = 1.f / A.dz;
     const float half_inv_dz = 0.5f * inv_dz, fs = P.num_fcc_scale * inv_dz;
     const float closed = sw.open_system_activation ? 0.f : -1.f;
+    // The ARG evaluation is gated by the supersaturation.  The cheap estimate from the staged constants only screens (with a
+    // margin); the sign that decides — and with it the cloud-base level — is taken by aerosol_activation_rate from the same
+    // formula as everywhere else (TD.supersaturation with T and p_sat(T)).
+    constexpr float S_SCREEN = -1e-4f;
     const int nst = 3 * A.nsteps;
-    int first = INT_MAX;  // lowest activation candidate among this thread's levels, for the stage being prepared
+    int first = INT_MAX;      // lowest activation candidate among this thread's levels, for the stage being prepared
+    unsigned un_phase = 0;    // parity of the mbarrier phase the next u^n fetch completes
+
+    // ARG rate of component e of the pair (scalar, rare)
+    auto arg_rate = [&](const PointX2& a, int e, int k, float rwx) -> float {
+        const size_t pi = A.prof_per_column ? size_t(k) * ncp + gc : size_t(k);
+        return pair_activation_rate<L::neq>(P, sw, A.T[pi], A.ps_liq[pi], e ? a.rho.y : a.rho.x, e ? a.q_tot.y : a.q_tot.x,
+                                            e ? a.q_liq.y : a.q_liq.x, e ? a.q_ice.y : a.q_ice.x, e ? a.q_rai.y : a.q_rai.x,
+                                            e ? a.q_sno.y : a.q_sno.x, e ? a.N_liq.y : a.N_liq.x, e ? a.N_rai.y : a.N_rai.x,
+                                            e ? a.N_aer.y : a.N_aer.x, rwx, dt);
+    };
 
 #pragma unroll 1
     for (int it = -1; it < nst; ++it) {
@@ -99,6 +186,7 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const _
         const int stage = real ? it % 3 : 0;
         const int itn = it + 1, stage_n = itn % 3;
         const bool do_post = itn < nst;
+        const bool fetch_un = real && stage != 0;
         const int parn = itn & 1, par = parn ^ 1;
         const float tn = float(A.t0 + double(real ? it / 3 : 0) * double(dt));
         const float ts = stage_time(stage, tn, dt);
@@ -115,30 +203,29 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const _
 #pragma unroll 1
         for (int r = 0; r < R; ++r) {
             const int k0 = r * LPR + 2 * j;  // this thread's pair: levels k0, k0 + 1
-            float* pa = Ys + k0 * C + c;     // + plane · sV
+            float* pa = Ys + (k0 >> 1) * C + c;  // level k0 (even); level k0 + 1 at + HO; + plane · sV
+            const float* rda = rds + (k0 >> 1) * C + c;
             F2 adv[NADV];
-            F2 un[NV];
-            GridConst2 g;
             if (active) {
-                if (real && stage != 0) {  // u^n of the stage combine (L2): requested first, consumed at the end of the WRITE phase
-                    const float* gU = A.Y + size_t(k0) * ncp + gc;
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) un[v] = f2(gU[v * plane], gU[v * plane + ncp]);
-                }
-                {   // grid-point constants of the pair (L2): requested first, used after the barrier
+                {   // grid-point constants of this thread's pair -> its own two staging slots (consumed after the barrier)
                     const size_t i0 = A.prof_per_column ? size_t(k0) * ncp + gc : size_t(k0);
-                    const float4 g0 = gconst[i0], g1 = gconst[i0 + (A.prof_per_column ? size_t(ncp) : size_t(1))];
-                    g.qvs_rho = f2(g0.x, g1.x); g.lam = f2(g0.y, g1.y); g.S_fac = f2(g0.z, g1.z); g.G = f2(g0.w, g1.w);
+                    const float* g0 = reinterpret_cast<const float*>(gconst + i0);
+                    const float* g1 = reinterpret_cast<const float*>(gconst + i0 + (A.prof_per_column ? size_t(ncp) : size_t(1)));
+                    cp_async8(gca + (2 * j) * C + c, g0);
+                    cp_async8(gca + (2 * j + 1) * C + c, g1);
+                    cp_async4(gcb + (2 * j) * C + c, g0 + 2);
+                    cp_async4(gcb + (2 * j + 1) * C + c, g1 + 2);
+                    cp_async_commit();
                 }
                 if (real) {
                     // ---- READ phase.  OLD values of levels k0-1 .. k0+2: the level below a block was overwritten by the
                     // previous round and sits in the stash row; at the domain boundaries the row is clamped (the value is
                     // not used: the boundary cells are fixed up below).
                     const bool bot = (k0 == 0), top = (k0 == NZ - 2);
-                    const int row_m = (j == 0) ? (r == 0 ? 0 : NZ + (r & 1)) : k0 - 1;
-                    const float* pm = Ys + row_m * C + c;
-                    const float* pu = Ys + (top ? NZ - 1 : k0 + 2) * C + c;
-                    const int km = bot ? 0 : k0 - 1, ku = top ? NZ - 1 : k0 + 2;
+                    const float* pm = (j == 0) ? (r == 0 ? pa : Ys + (NZ + (r & 1)) * C + c) : pa + HO - C;  // level k0 - 1 (odd)
+                    const float* pu = top ? pa + HO : pa + C;                                               // level k0 + 2 (even)
+                    const float* rdm = bot ? rda : rda + HO - C;
+                    const float* rdu = top ? rda + HO : rda + C;
                     // faces: f0 = (k0-1 | k0), f1 = (k0 | k0+1), f2 = (k0+1 | k0+2); f0 and f2 packed, f1 scalar.
                     // Face velocities (air, air - vt_q, air - vt_N) pre-multiplied: wh = w / (2 dz) for the centred flux,
                     // aw = fcc_scale |w| / dz for the first-order correction; Q_f = wh (y_hi + y_lo) - aw (y_hi - y_lo) is
@@ -146,12 +233,12 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const _
                     F2 wh02[3], aw02[3];
                     float wh1[3], aw1[3];
                     {
-                        const float rho_m = rds[km * C + c] + pm[L::tot * sV], rho_a = rds[k0 * C + c] + pa[L::tot * sV];
-                        const float rho_b = rds[(k0 + 1) * C + c] + pa[L::tot * sV + C], rho_u = rds[ku * C + c] + pu[L::tot * sV];
+                        const float rho_m = rdm[0] + pm[L::tot * sV], rho_a = rda[0] + pa[L::tot * sV];
+                        const float rho_b = rda[HO] + pa[L::tot * sV + HO], rho_u = rdu[0] + pu[L::tot * sV];
                         const F2 wa02 = rw2 * vrcp(f2(rho_m, rho_b) + f2(rho_a, rho_u));
                         const float wa1 = rw2 * rcp1(rho_a + rho_b);
-                        const F2 v1lo = f2(pm[VT1 * sV], pa[VT1 * sV + C]), v1hi = f2(pa[VT1 * sV], pu[VT1 * sV]);
-                        const F2 v2lo = f2(pm[VT2 * sV], pa[VT2 * sV + C]), v2hi = f2(pa[VT2 * sV], pu[VT2 * sV]);
+                        const F2 v1lo = f2(pm[VT1 * sV], pa[VT1 * sV + HO]), v1hi = f2(pa[VT1 * sV], pu[VT1 * sV]);
+                        const F2 v2lo = f2(pm[VT2 * sV], pa[VT2 * sV + HO]), v2hi = f2(pa[VT2 * sV], pu[VT2 * sV]);
                         const F2 wv02[3] = {wa02, fma2(v1lo + v1hi, -0.5f, wa02), fma2(v2lo + v2hi, -0.5f, wa02)};
                         const float wv1[3] = {wa1, fmaf(v1hi.x + v1lo.y, -0.5f, wa1), fmaf(v2hi.x + v2lo.y, -0.5f, wa1)};
 #pragma unroll
@@ -164,7 +251,7 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const _
                         constexpr int i = decltype(I)::value;
                         constexpr AdvVar e = adv_entry<MOIST, KID_PRECIP_2M>(i);
                         const bool fcc_on = (e.fcc == FCC_ALWAYS) || fcc_tot;
-                        const float ym = pm[e.idx * sV], ya = pa[e.idx * sV], yb = pa[e.idx * sV + C], yu = pu[e.idx * sV];
+                        const float ym = pm[e.idx * sV], ya = pa[e.idx * sV], yb = pa[e.idx * sV + HO], yu = pu[e.idx * sV];
                         const F2 lo = f2(ym, yb), hi = f2(ya, yu);
                         const F2 G02 = fcc_on ? aw02[e.vel] * (hi - lo) : f2(0.f);
                         const float G1 = fcc_on ? aw1[e.vel] * (yb - ya) : 0.f;
@@ -182,34 +269,54 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const _
                     // the next round needs the OLD values of this block's last level (state and terminal velocities)
                     if (j == TJ - 1 && r + 1 < R) {
 #pragma unroll
-                        for (int p = 0; p < NP; ++p) Ys[p * sV + (NZ + ((r + 1) & 1)) * C + c] = pa[p * sV + C];
+                        for (int p = 0; p < NP; ++p) Ys[p * sV + (NZ + ((r + 1) & 1)) * C + c] = pa[p * sV + HO];
                     }
                 }
             }
-#ifndef KID_PAIR_NOSYNC_EXPERIMENT
-            __syncthreads();  // every thread of the tile has read its old neighbours
-#endif
-            if constexpr (L::is2m) {
-                if (r == 0) {
-                    cbk = cb[par * C + c];  // complete: its last atomicMin precedes the barrier above
-                    // slot of the stage after next: its last readers (this read, one stage ago) passed two barriers since
+            __syncthreads();  // every thread of the tile has read its old neighbours (and last round's u^n staging rows)
+            if (fetch_un) {
+                // u^n of this round's block — a (32 columns x 32 levels x NV variables) box of the device state — straight
+                // into shared memory with ONE TMA instruction; it lands while the sources are evaluated and is waited for just
+                // before the stage combine
+                if (tid == 0) {
+                    mbar_arrive_expect_tx(mbar, UN_BYTES);
+                    tma_load_3d(uns, &tmY, gc0, r * LPR, 0, mbar);
                 }
             }
+            if (r == 0) cbk = cb[par * C + c];  // complete: its last atomicMin precedes the barrier above
             if (!active) continue;
 
             // ---- WRITE phase: sources + SSPRK33 stage combine in place, then the aux fields of the next stage
             F2 y[NV];
 #pragma unroll
-            for (int v = 0; v < NV; ++v) y[v] = f2(pa[v * sV], pa[v * sV + C]);
-            const F2 rd = f2(rds[k0 * C + c], rds[(k0 + 1) * C + c]);
+            for (int v = 0; v < NV; ++v) y[v] = f2(pa[v * sV], pa[v * sV + HO]);
+            const F2 rd = f2(rda[0], rda[HO]);
+            GridConst2 g;
+            {
+                cp_async_wait_all();
+                const float2 a0 = gca[(2 * j) * C + c], a1 = gca[(2 * j + 1) * C + c];
+                g.qvs_rho = f2(a0.x, a1.x); g.S_fac = f2(a0.y, a1.y);
+                g.lam = f2(gcb[(2 * j) * C + c], gcb[(2 * j + 1) * C + c]);
+                // G(T): only rain evaporation reads it; straight from global memory inside that branch
+                const size_t i0 = A.prof_per_column ? size_t(k0) * ncp + gc : size_t(k0);
+                g.G0 = &gconst[i0].w;
+                g.G1 = &gconst[i0 + (A.prof_per_column ? size_t(ncp) : size_t(1))].w;
+            }
             if (real) {
                 PointX2 a;
                 thermo_point_x2<MOIST>(y, rd, g, a);
                 if (stale_Naer) a.N_aer = f2(A.aux_Naer[size_t(k0) * ncp + gc], A.aux_Naer[size_t(k0 + 1) * ncp + gc]);
+                // activation source: the rate at the cloud-base level found one stage ago (or at every level, local_activation);
+                // re-evaluated here from the same state instead of being stored per level
                 F2 act = f2(0.f);
                 if (k1d) {
-                    const bool loc = sw.local_activation != 0;
-                    act = f2((loc || k0 == cbk) ? acts[k0 * C + c] : 0.f, (loc || k0 + 1 == cbk) ? acts[(k0 + 1) * C + c] : 0.f);
+                    if (loc) {
+                        const F2 S = fma2((a.q_tot - (a.q_liq + a.q_rai)) - a.q_ice, a.rho * g.S_fac, -1.f);
+                        if (!(S.x < S_SCREEN) && !(a.N_aer.x < 1.1920929e-07f)) act.x = arg_rate(a, 0, k0, rw);
+                        if (!(S.y < S_SCREEN) && !(a.N_aer.y < 1.1920929e-07f)) act.y = arg_rate(a, 1, k0 + 1, rw);
+                    } else if ((cbk >> 1) == (k0 >> 1)) {
+                        if (cbk & 1) act.y = arg_rate(a, 1, k0 + 1, rw); else act.x = arg_rate(a, 0, k0, rw);
+                    }
                 }
                 F2 tend[NV];
 #pragma unroll
@@ -237,15 +344,19 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const _
                     if (e.to_tot) tend[L::tot] += adv[i];  // precipitation also moves ρq_tot (K1DModel/tendency.jl:431-432)
                 });
                 // SSPRK33 as a convex combination  u_new = a·u^n + b·(y + dt·f(y))
+                if (fetch_un) { mbar_wait(mbar, un_phase); un_phase ^= 1u; }  // one mbarrier phase per round
                 float* gY = A.Y + size_t(k0) * ncp + gc;
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
                     const F2 yb = fma2(y[v], rk_b, tend[v] * rk_c);
-                    y[v] = (stage == 0) ? yb : fma2(un[v], rk_a, yb);
+                    if (stage == 0) y[v] = yb;
+                    else y[v] = fma2(f2(uns[(v * LPR + 2 * j) * C + c], uns[(v * LPR + 2 * j + 1) * C + c]), rk_a, yb);
                     pa[v * sV] = y[v].x;
-                    pa[v * sV + C] = y[v].y;
+                    pa[v * sV + HO] = y[v].y;
                     if (stage == 2) { gY[v * plane] = y[v].x; gY[v * plane + ncp] = y[v].y; }
                 }
+                // the stored state is the u^n the TMA loads of the next step read: one proxy fence per thread and step
+                if (stage == 2 && r == R - 1) fence_proxy_async();
             }
             if (do_post) {
                 // aux of the state just formed, as the next rhs! call starts with (precompute_aux_thermo!,
@@ -254,39 +365,24 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const _
                 thermo_point_x2<MOIST>(y, rd, g, a);
                 F2 vq, vN;
                 terminal_velocities_x2(P, sw, a, vq, vN);
-                pa[VT1 * sV] = vq.x; pa[VT1 * sV + C] = vq.y;
-                pa[VT2 * sV] = vN.x; pa[VT2 * sV + C] = vN.y;
-                if (k1d) {
-                    // ARG activation rate (get_aerosol_activation_rate, K1DModel/tendency.jl:35-96).  Non-local activation
-                    // keeps only the LOWEST activating level: once this thread has a candidate its higher levels are skipped.
-                    const F2 S = fma2((a.q_tot - (a.q_liq + a.q_rai)) - a.q_ice, a.rho * g.S_fac, -1.f);
-                    const bool loc = sw.local_activation != 0;
-#pragma unroll 1
-                    for (int e = 0; e < 2; ++e) {  // rare, scalar: one copy of the ARG code
-                        const int k = k0 + e;
-                        float S_Nl = 0.f;
-                        const float Se = e ? S.y : S.x, Na = e ? a.N_aer.y : a.N_aer.x;
-                        if ((loc || first == INT_MAX) && !(Se < 0.f) && !(Na < 1.1920929e-07f)) {
-                            const size_t pi = A.prof_per_column ? size_t(k) * ncp + gc : size_t(k);
-                            const float T = A.T[pi], ps_l = A.ps_liq[pi];
-                            const float rho = e ? a.rho.y : a.rho.x, q_tot = e ? a.q_tot.y : a.q_tot.x;
-                            const float q_liq = e ? a.q_liq.y : a.q_liq.x, q_ice = e ? a.q_ice.y : a.q_ice.x;
-                            const float q_rai = e ? a.q_rai.y : a.q_rai.x, q_sno = e ? a.q_sno.y : a.q_sno.x;
-                            const float N_liq = e ? a.N_liq.y : a.N_liq.x, N_rai = e ? a.N_rai.y : a.N_rai.x;
-                            TD<float, DevParams<float>> td(P);
-                            const float p = L::neq ? td.air_pressure(T, rho, q_tot, q_liq + q_rai, q_ice + q_sno)
-                                                   : td.air_pressure(T, rho, q_tot, 0.f, 0.f);
-                            S_Nl = aerosol_activation_rate<float>(P, sw, q_tot, q_liq + q_rai, q_ice, N_liq + N_rai, Na, T, ps_l, p,
-                                                                  rho, rw_n, dt);
-                            // find_cloud_base! (K1DModel/tendency.jl:21-32): the accumulator starts at level 1 and is replaced
-                            // only while its S is 0 and the candidate's S is > 0
-                            const bool cand = (k == 0) ? (S_Nl != 0.f) : (S_Nl > 0.f);
-                            if (cand && first == INT_MAX) first = k;
+                pa[VT1 * sV] = vq.x; pa[VT1 * sV + HO] = vq.y;
+                pa[VT2 * sV] = vN.x; pa[VT2 * sV + HO] = vN.y;
+                if (k1d && !loc) {
+                    // find_cloud_base! (K1DModel/tendency.jl:21-32): the lowest level with a positive ARG rate; the
+                    // accumulator starts at level 1 and is replaced only while its S is 0 and the candidate's S is > 0 (so a
+                    // NEGATIVE rate at level 1 sticks).  Once this thread has a candidate its higher levels are skipped.
+                    if (first == INT_MAX) {
+                        const F2 S = fma2((a.q_tot - (a.q_liq + a.q_rai)) - a.q_ice, a.rho * g.S_fac, -1.f);
+                        if (!(S.x < S_SCREEN) && !(a.N_aer.x < 1.1920929e-07f)) {
+                            const float S_Nl = arg_rate(a, 0, k0, rw_n);
+                            if ((k0 == 0) ? (S_Nl != 0.f) : (S_Nl > 0.f)) first = k0;
                         }
-                        acts[k * C + c] = S_Nl;
+                        if (first == INT_MAX && !(S.y < S_SCREEN) && !(a.N_aer.y < 1.1920929e-07f)) {
+                            if (arg_rate(a, 1, k0 + 1, rw_n) > 0.f) first = k0 + 1;
+                        }
                     }
                     if (r == R - 1) {
-                        if (!loc && first != INT_MAX) atomicMin(&cb[parn * C + c], first);
+                        if (first != INT_MAX) atomicMin(&cb[parn * C + c], first);
                         first = INT_MAX;
                     }
                 }
@@ -294,7 +390,7 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const _
         }
         // the slot just consumed serves the stage after next: every thread read it after this stage's first barrier and
         // has passed at least two more barriers; the next writers (atomicMin above, next stage) come after the next barrier
-        if constexpr (L::is2m) { if (j == 0) cb[par * C + c] = INT_MAX; }
+        if (j == 0) cb[par * C + c] = INT_MAX;
     }
 }
 

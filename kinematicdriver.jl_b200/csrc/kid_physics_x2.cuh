@@ -19,8 +19,11 @@ struct PointX2 {
 //   qvs_rho = p_sat,mixed(T) / (R_v T)       q_vap_saturation(T, ρ) = qvs_rho / ρ
 //   lam     = liquid_fraction(T)             condensate_partition
 //   S_fac   = R_v T / p_sat,liq(T)           supersaturation_over_liquid + 1 = q_vap ρ S_fac
-//   G       = G_func_liquid(T)               CM2.rain_evaporation
-struct GridConst2 { F2 qvs_rho, lam, S_fac, G; };
+//   G       = G_func_liquid(T)               CM2.rain_evaporation (read from global memory inside that branch)
+struct GridConst2 {
+    F2 qvs_rho, lam, S_fac;
+    const float *G0, *G1;  // G(T) of the two points: read from global memory where rain evaporates
+};
 
 // precompute_aux_thermo! + the q/N part of precompute_aux_precip! (src/Common/tendency.jl:34-73, :104-135, :203-206)
 template <int MOIST>
@@ -156,8 +159,12 @@ KID_DEV void precip_sources_2m_x2(const PRM& P, const DevSwitches& sw, const Poi
     const B2 live = has_liq || has_Nl || has_rai || has_Nr;
     if (!any(live)) return;
     const F2 L_liq = rho * q_liq, L_rai = rho * q_rai;
+    // Few, large basic blocks: everything that needs cloud water in one, everything that needs rain in another, so that
+    // the independent dependency chains of the processes (pow = lg2 -> mul -> ex2, limiter = rsqrt -> Newton step) overlap;
+    // the per-process conditions of the scalar code are applied as selects on the results.
     F2 lam_r = z, x_r = z, sq_rho0 = z;
-    if (any(has_rai)) {
+    const bool do_rai = any(has_rai);
+    if (do_rai) {
         sb_pdf_rain_x2(P, sw.sb_limited != 0, L_rai, N_rai, lam_r, x_r);
         sq_rho0 = vsqrt_fast(P.sb_rho0 * a.inv_rho);
     }
@@ -167,7 +174,7 @@ KID_DEV void precip_sources_2m_x2(const PRM& P, const DevSwitches& sw, const Poi
         // autoconversion (mass, number): CM2.autoconversion
         F2 S2au = z;
         const B2 m_au = has_liq && has_Nl;
-        if (any(m_au)) {
+        if (any(has_liq)) {
             const F2 x_liq = vmin(L_liq / N_liq, P.sb_x_star);
             const F2 tau = vmax(1.f - q_liq / (q_liq + vmax(q_rai, 0.f)), 0.f);
             const F2 tau_a = vpow(tau, P.sb_a);
@@ -178,15 +185,13 @@ KID_DEV void precip_sources_2m_x2(const PRM& P, const DevSwitches& sw, const Poi
             S2au = sel(m_au, tri_x2(dL * P.inv_sb_x_star, limit_x2(N_liq * 0.5f, inv_dt)), 0.f);
             s_liq -= S1; s_rai += S1;
             s_Nl = fma2(S2au, -2.f, s_Nl); s_Nr += S2au;
-        }
-        // cloud liquid self-collection
-        if (any(has_liq)) {
+            // cloud liquid self-collection
             const F2 sc_l = fma2(S2au, 2.f, (-P.sb_sc_pref * (P.sb_rho0 * a.inv_rho)) * L_liq * L_liq);
             s_Nl -= sel(has_liq, tri_x2(-sc_l, limit_x2(N_liq, inv_dt)), 0.f);
         }
         // rain self-collection and breakup
         const B2 m_r = has_rai && has_Nr;
-        if (any(m_r)) {
+        if (do_rai) {
             const F2 lam_x = lam_r * P.sb_c6pr;
             const F2 sc_r = (-P.sb_krr * N_rai) * L_rai * sq_rho0 * vpow(1.f + P.sb_kappa_rr / lam_x, P.sb_d);
             const F2 S1 = -sel(m_r, tri_x2(-sc_r, limit_x2(N_rai, inv_dt)), 0.f);
@@ -195,17 +200,15 @@ KID_DEV void precip_sources_2m_x2(const PRM& P, const DevSwitches& sw, const Poi
             const F2 phi_br = sel(Dr < P.sb_Dr_th, -1.f, sel(dD <= 0.f, P.sb_kbr * dD, 2.f * (vexp(P.sb_kappa_br * dD) - 1.f)));
             const F2 br = -(phi_br + 1.f) * S1;  // takes the LIMITED self-collection value
             s_Nr += S1 + sel(m_r, tri_x2(br, limit_x2(N_rai, inv_dt)), 0.f);
-        }
-        // accretion
-        const B2 m_ac = has_liq && has_rai && has_Nl;
-        if (any(m_ac)) {
+            // accretion
+            const B2 m_ac = has_liq && has_rai && has_Nl;
             const F2 tau = vmax(1.f - q_liq / (q_liq + q_rai), 0.f);
             const F2 phi_ac = vpow(tau / (tau + P.sb_tau0), P.sb_c);
             const F2 dL = P.sb_kcr * L_liq * L_rai * phi_ac * sq_rho0;
             const F2 dN = dL * N_liq / L_liq;   // dL / x_liq, x_liq = L_liq / N_liq  (= -dN_ac)
-            const F2 S1 = sel(m_ac, tri_x2(dL * a.inv_rho, limit_x2(q_liq, inv_dt)), 0.f);
-            const F2 S2 = sel(m_ac, tri_x2(dN, limit_x2(N_liq, inv_dt)), 0.f);
-            s_liq -= S1; s_rai += S1; s_Nl -= S2;
+            const F2 A1 = sel(m_ac, tri_x2(dL * a.inv_rho, limit_x2(q_liq, inv_dt)), 0.f);
+            const F2 A2 = sel(m_ac, tri_x2(dN, limit_x2(N_liq, inv_dt)), 0.f);
+            s_liq -= A1; s_rai += A1; s_Nl -= A2;
         }
         // number adjustment for mass limits, cloud liquid then rain
         {
@@ -242,7 +245,7 @@ KID_DEV void precip_sources_2m_x2(const PRM& P, const DevSwitches& sw, const Poi
                 const F2 sre = P.sc3 * vsqrt_fast(N_Re);
                 const F2 Fv0 = fma2(P.sb_bv0 * gb0, sre, P.sb_av0 * ga0);
                 const F2 Fv1 = fma2(sre, P.sb_bv1, P.sb_av1);
-                const F2 common = (2.f * float(M_PI)) * g.G * S * N_rai * Dr;
+                const F2 common = (2.f * float(M_PI)) * f2(__ldg(g.G0), __ldg(g.G1)) * S * N_rai * Dr;
                 F2 e0 = vmin(common * Fv0 / xr, 0.f);
                 const F2 e1 = vmin(common * Fv1 * a.inv_rho, 0.f);
                 e0 = sel(N_rai < eps, 0.f, e0);

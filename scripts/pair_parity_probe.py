@@ -31,3 +31,14 @@ f = lambda e: {k: float("%.2e" % v) for k, v in e.items()}
 print("scalar vs oracle:", f(errors(out["scalar"], Yo, cs.var_names)))
 print("pair   vs oracle:", f(errors(out["pair"], Yo, cs.var_names)))
 print("pair   vs scalar:", f(errors(out["pair"], out["scalar"], cs.var_names)))
+# where do the largest differences sit?
+from kid_b200.lib import COL_W1, COL_PRESCRIBED_ND
+for name in ("scalar", "pair"):
+    print(name)
+    for i, v in enumerate(cs.var_names):
+        d = np.abs(out[name][:, i].astype(np.float64) - Yo[:, i])
+        if d.max() == 0: continue
+        c, k = np.unravel_index(np.argmax(d), d.shape)
+        print(f"  {v}: max |d| {d.max():.3e} (field max {np.abs(Yo[:, i]).max():.3e}) at column {c} level {k}: w1={cs.col_scalars[COL_W1][c]:.3f} "
+              f"Nd={cs.col_scalars[COL_PRESCRIBED_ND][c]:.3e} gpu={out[name][c, i, k]:.6e} oracle={Yo[c, i, k]:.6e}; columns with err > 1e-3 of max: "
+              f"{int((d.max(axis=1) > 1e-3 * np.abs(Yo[:, i]).max()).sum())}")

@@ -22,6 +22,7 @@ ap.add_argument("--tile-c", type=int, default=0)
 ap.add_argument("--no-fixed", type=int, default=0)
 ap.add_argument("--order", default="hash", choices=["hash", "sorted", "uniform", "morton"])
 ap.add_argument("--ic", default="host", choices=["host", "device"])
+ap.add_argument("--no-pair", type=int, default=0, help="1: scalar tile kernel instead of the packed pair kernel")
 ap.add_argument("--reorder", type=int, default=0, help="store the members in model.warp_coherent_order")
 a = ap.parse_args()
 FT = np.float32 if a.ft == "f32" else np.float64
@@ -34,6 +35,7 @@ if a.reorder: cs = M.reorder_columns(cs, M.warp_coherent_order(cs))
 if a.nw: cs.cfg.reserved[0] = a.nw
 if a.tile_c: cs.cfg.reserved[1] = a.tile_c
 if a.no_fixed: cs.cfg.reserved[2] = 1
+if a.no_pair: cs.cfg.reserved[3] = 1
 h = M.make_handle(cs, Handle)
 h.step(0.0, a.t_start); h.synchronize()
 t = float(a.t_start)
