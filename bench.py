@@ -269,6 +269,8 @@ def run_ours(args):
     case = M.slice_columns(gcase, ca, cb)
     if args.kernel == "scalar":
         case.cfg.reserved[3] = 1  # A/B: the scalar tile kernel instead of the packed two-levels-per-thread kernel
+    if args.direct_host:
+        case.cfg.reserved[4] = 2  # A/B: layout kernels access the page-locked host arrays in place instead of copy engine + staging
     h = M.make_handle(case, Handle)
     spl = args.steps_per_launch
     stream = torch.cuda.ExternalStream(h.stream, device=local)
@@ -353,6 +355,29 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = gp_steps_total / (float(te.item()) * 1e-3)
+    # The same call for a caller whose host arrays are in MEMBER-INDEX order (SURVEY 8d hash order) while the device keeps the
+    # warp-coherent storage order: the layout kernels gather / scatter through the column map (kid_set_column_map), no host gather.
+    e2e_user = None
+    if args.order == "sorted":
+        del pipe
+        members = np.asarray(gcase.meta["column_perm"])[ca:cb]      # member index of every device column of this rank
+        host_row = np.argsort(np.argsort(members)).astype(np.int32)  # its row in the rank's member-ordered host array
+        pipe = PipelinedEnsemble(case, nchunks=args.e2e_chunks, host_column_of=host_row)
+        pipe.set_steps_per_launch(spl)
+        Yu = torch.empty(state_shape, dtype=torch.float32).pin_memory().numpy()
+        Yu[host_row] = Yn
+        pipe.solve(Yu, t, spl)  # warm-up
+        Yu[host_row] = Yn
+        barrier()
+        w0 = time.perf_counter()
+        pipe.solve(Yu, t + e2e_steps, e2e_steps)
+        wall = time.perf_counter() - w0
+        barrier()
+        tu = torch.tensor([wall * 1e3], dtype=torch.float64, device=f"cuda:{local}")
+        if dist is not None:
+            dist.all_reduce(tu, op=dist.ReduceOp.MAX)
+        e2e_user = gp_steps_total / (float(tu.item()) * 1e-3)
+        del Yu
     state_bytes = Yn.nbytes
 
     if rank == 0:
@@ -392,6 +417,9 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": world * state_bytes / e2e_steps,
                     "d2h_bytes_per_step": world * state_bytes / e2e_steps, "resident_fraction": e2e_value / value,
+                    "member_index_order_host_arrays": ({"value": e2e_user, "of_sorted_host_arrays": e2e_user / e2e_value,
+                                                        "how": "kid_set_column_map: the layout kernels gather/scatter the page-locked host array"}
+                                                       if e2e_user else None),
                     "call": f"PipelinedEnsemble.solve: {args.e2e_chunks} column chunks x [set_state_async(pinned) + step({e2e_steps}) + get_state_async(pinned)], per rank"},
             "gpu_launches": int(launches),
             "roofline": {"bound": max(fracs, key=fracs.get), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -431,6 +459,7 @@ def main():
     ap.add_argument("--no-parity", dest="parity", action="store_false", help="skip the in-bench parity sample")
     ap.add_argument("--e2e-chunks", type=int, default=32, help="column chunks (handles/streams) of the end-to-end pipelined call")
     ap.add_argument("--kernel", default="pair", choices=["pair", "scalar"], help="step kernel of the resident leg (A/B measurements)")
+    ap.add_argument("--direct-host", action="store_true", help="A/B: in-place PCIe access to the page-locked host arrays instead of copy engine + staging")
     ap.add_argument("--order", default="sorted", choices=["sorted", "hash"], help="storage order of the ensemble members")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -111,7 +111,7 @@ typedef struct kid_config {
     int32_t local_activation;
     int32_t qtot_flux_correction;
     int32_t device;          /* CUDA device ordinal */
-    int32_t reserved[8];     /* reserved[0..3]: tuning overrides (0 = library default): max level-warps per tile (>= 2), columns per tile, 1 = never use the compile-time-shape kernel, 1 = never use the packed two-levels-per-thread 2M kernel */
+    int32_t reserved[8];     /* reserved[0..4]: tuning overrides (0 = library default): max level-warps per tile (>= 2), columns per tile, 1 = never use the compile-time-shape kernel, 1 = never use the packed two-levels-per-thread 2M kernel, 2 = layout kernels access page-locked host buffers in place even without a column map */
     double z_min, z_max;     /* make_function_space (K1DModel/ode_utils.jl:9-21) */
     double dt;               /* TimeStepping.dt (src/Common/ode_utils.jl:12-16) */
     double domain_width;     /* K2D aux.domain_width  */
@@ -157,6 +157,15 @@ int kid_get_state(kid_handle_t* h, void* Y);
  * several handles).  The buffer must stay valid and untouched until kid_synchronize(h) returns. */
 int kid_set_state_async(kid_handle_t* h, const void* Y_pinned);
 int kid_get_state_async(kid_handle_t* h, void* Y_pinned);
+/* Column map (optional): device column i holds HOST column host_column_of[i] (nc entries; NULL = identity).  The order of
+ * ensemble members is arbitrary for the caller (OptimizationUtils.jl:197-211 loops over members), but it decides which
+ * members share a warp: with a map the caller keeps its own order in the host arrays of kid_set_state* / kid_get_state*
+ * while the device stores similar members next to each other (kid_b200.model.warp_coherent_order).  Host entries may point
+ * anywhere into a larger page-locked array (column chunks of a pipelined ensemble).  Profiles, per-column scalars and aux
+ * output stay in device column order.  Needs page-locked host buffers (kid_host_alloc, cudaHostAlloc, cudaHostRegister): the
+ * layout kernels then gather / scatter the host rows in place over PCIe (plain transfers use the copy engine + staging,
+ * which is faster for contiguous arrays; cfg.reserved[4] = 2 forces in-place access). */
+int kid_set_column_map(kid_handle_t* h, const int32_t* host_column_of);
 
 /* replaces: ρ_ivp + initial_condition_1d + initialise_state and the ρ_dry, T, q_surf fields of initialise_aux
  * (src/Common/initial_condition.jl:50-231, src/Common/ode_utils.jl:23-54, src/K1DModel/ode_utils.jl:80-117) for the

@@ -55,6 +55,7 @@ struct kid_handle {
     void *Y = nullptr, *rho_dry = nullptr, *T = nullptr, *w1 = nullptr, *q_surf = nullptr, *Nd = nullptr;
     void *aux_Naer = nullptr, *out = nullptr, *staging = nullptr;
     void *prm_sets = nullptr, *col_to_set = nullptr;  // per-column parameter sets (calibration ensembles)
+    void* colmap = nullptr;                            // kid_set_column_map: host column of every device column
     void *ps_liq = nullptr, *ps_mix = nullptr;        // p_sat(T) per grid point (profile constants)
     void* gconst = nullptr;                            // float4 per grid point: constants of the packed 2M kernel (kid_pair_kernel.cuh)
     CUtensorMap state_map{};                           // TMA descriptor of the device state [var][level][column] (box 32 x 32 x nv)
@@ -140,33 +141,62 @@ int upload_columns(kid_handle* h, void* dst, const void* src_ft, double fallback
     return 0;
 }
 
-// host [nc][nv][nz] -> device [nv][nz][ncp]
-int to_device_layout(kid_handle* h, const void* host, void* dev, int nv) {
-    const int nc = h->cfg.nc, nz = h->cfg.nz;
-    size_t bytes = size_t(nc) * nv * nz * h->fsz;
-    if (ensure_staging(h, bytes)) return 1;
-    KID_CUDA(cudaMemcpyAsync(h->staging, host, bytes, cudaMemcpyHostToDevice, h->stream));
-    dim3 block(32, 8), grid((h->ncp + 31) / 32, (nv * nz + 31) / 32);
-    if (h->f64)
-        host_to_device_layout<double><<<grid, block, 0, h->stream>>>((const double*)h->staging, (double*)dev, nc, h->ncp, nv, nz);
-    else
-        host_to_device_layout<float><<<grid, block, 0, h->stream>>>((const float*)h->staging, (float*)dev, nc, h->ncp, nv, nz);
+// Is `p` page-locked host memory the device can address (cudaHostAlloc / kid_host_alloc / cudaHostRegister)?  Then the layout
+// kernels CAN read / write it in place over PCIe.  Measured on B200 (profiles/README.md, round 2): the copy engine + a
+// transpose from device staging moves a 4 GiB state at 97 % of the resident stepping rate end to end, in-place access from
+// the kernels (512-byte requests) at 73 % — so in-place access is used where it is needed (column maps: scattered host rows)
+// or asked for (cfg.reserved[4] = 2), and plain transfers stage through device memory.
+const void* device_view_of_pinned(const kid_handle* h, const void* p, bool needed) {
+    if (!needed && h->cfg.reserved[4] != 2) return nullptr;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return (a.type == cudaMemoryTypeHost && a.devicePointer) ? a.devicePointer : nullptr;
+}
+template <bool TO_DEVICE>
+int launch_layout(kid_handle* h, const void* hostside, void* devside, int nv, const int* perm) {
+    const int nc = h->cfg.nc, nz = h->cfg.nz, R = nv * nz;
+    if (!h->f64 && R % 128 == 0 && (reinterpret_cast<size_t>(hostside) % 16) == 0) {
+        dim3 grid((h->ncp + 31) / 32, R / 128);
+        if (TO_DEVICE) host_to_device_layout_wide<<<grid, 256, 0, h->stream>>>((const float*)hostside, (float*)devside, perm, nc, h->ncp, R);
+        else device_to_host_layout_wide<<<grid, 256, 0, h->stream>>>((const float*)devside, (float*)hostside, perm, nc, h->ncp, R);
+    } else {
+        dim3 block(32, 8), grid((h->ncp + 31) / 32, (R + 31) / 32);
+        if (h->f64) {
+            if (TO_DEVICE) host_to_device_layout<double><<<grid, block, 0, h->stream>>>((const double*)hostside, (double*)devside, perm, nc, h->ncp, nv, nz);
+            else device_to_host_layout<double><<<grid, block, 0, h->stream>>>((const double*)devside, (double*)hostside, perm, nc, h->ncp, nv, nz);
+        } else {
+            if (TO_DEVICE) host_to_device_layout<float><<<grid, block, 0, h->stream>>>((const float*)hostside, (float*)devside, perm, nc, h->ncp, nv, nz);
+            else device_to_host_layout<float><<<grid, block, 0, h->stream>>>((const float*)devside, (float*)hostside, perm, nc, h->ncp, nv, nz);
+        }
+    }
     KID_CUDA(cudaGetLastError());
     h->launches++;
     return 0;
 }
-// device [nv][nz][ncp] -> host [nc][nv][nz]
-int to_host_layout(kid_handle* h, const void* dev, void* host, int nv, bool sync = true) {
+// host [nc][nv][nz] -> device [nv][nz][ncp]; with a column map: device column i <- host column map[i]
+int to_device_layout(kid_handle* h, const void* host, void* dev, int nv, bool use_map = false) {
     const int nc = h->cfg.nc, nz = h->cfg.nz;
+    const int* perm = use_map ? (const int*)h->colmap : nullptr;
+    if (const void* hv = device_view_of_pinned(h, host, perm != nullptr)) return launch_layout<true>(h, hv, dev, nv, perm);
+    if (perm) return fail("a column map (kid_set_column_map) needs page-locked host buffers: allocate them with kid_host_alloc");
     size_t bytes = size_t(nc) * nv * nz * h->fsz;
     if (ensure_staging(h, bytes)) return 1;
-    dim3 block(32, 8), grid((h->ncp + 31) / 32, (nv * nz + 31) / 32);
-    if (h->f64)
-        device_to_host_layout<double><<<grid, block, 0, h->stream>>>((const double*)dev, (double*)h->staging, nc, h->ncp, nv, nz);
-    else
-        device_to_host_layout<float><<<grid, block, 0, h->stream>>>((const float*)dev, (float*)h->staging, nc, h->ncp, nv, nz);
-    KID_CUDA(cudaGetLastError());
-    h->launches++;
+    KID_CUDA(cudaMemcpyAsync(h->staging, host, bytes, cudaMemcpyHostToDevice, h->stream));
+    return launch_layout<true>(h, h->staging, dev, nv, nullptr);
+}
+// device [nv][nz][ncp] -> host [nc][nv][nz]
+int to_host_layout(kid_handle* h, const void* dev, void* host, int nv, bool sync = true, bool use_map = false) {
+    const int nc = h->cfg.nc, nz = h->cfg.nz;
+    const int* perm = use_map ? (const int*)h->colmap : nullptr;
+    if (const void* hv = device_view_of_pinned(h, host, perm != nullptr)) {
+        if (launch_layout<false>(h, hv, const_cast<void*>(dev), nv, perm)) return 1;
+        if (sync) KID_CUDA(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    if (perm) return fail("a column map (kid_set_column_map) needs page-locked host buffers: allocate them with kid_host_alloc");
+    size_t bytes = size_t(nc) * nv * nz * h->fsz;
+    if (ensure_staging(h, bytes)) return 1;
+    if (launch_layout<false>(h, h->staging, const_cast<void*>(dev), nv, nullptr)) return 1;
     KID_CUDA(cudaMemcpyAsync(host, h->staging, bytes, cudaMemcpyDeviceToHost, h->stream));
     if (sync) KID_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
@@ -601,7 +631,7 @@ void kid_destroy(kid_handle_t* h) {
         if (h->ev_ready[b]) cudaEventDestroy(h->ev_ready[b]);
         if (h->ev_done[b]) cudaEventDestroy(h->ev_done[b]);
     }
-    for (void* p : {h->gconst, h->ps_liq, h->ps_mix, h->prm_sets, h->col_to_set, h->Y, h->rho_dry, h->T, h->w1, h->q_surf, h->Nd, h->aux_Naer,
+    for (void* p : {h->colmap, h->gconst, h->ps_liq, h->ps_mix, h->prm_sets, h->col_to_set, h->Y, h->rho_dry, h->T, h->w1, h->q_surf, h->Nd, h->aux_Naer,
                     h->out, h->staging, h->U, h->S, h->prev_aux, h->xc, h->out2, h->send_left, h->send_right, h->recv_left,
                     h->recv_right, (void*)h->obsG, (void*)h->red, (void*)h->zsin, (void*)h->cosx, (void*)h->cosz})
         if (p) cudaFree(p);
@@ -710,11 +740,11 @@ int kid_set_state_async(kid_handle_t* h, const void* Y) { return set_state_impl(
 int kid_get_state_async(kid_handle_t* h, void* Y) {
     if (!h || !Y) return fail("null argument");
     if (!h->state_set) return fail("kid_set_state has not been called");
-    return to_host_layout(h, h->Y, Y, h->nv, false);
+    return to_host_layout(h, h->Y, Y, h->nv, false, true);
 }
 static int set_state_impl(kid_handle_t* h, const void* Y, bool sync) {
     if (!h || !Y) return fail("null argument");
-    if (to_device_layout(h, Y, h->Y, h->nv)) return 1;
+    if (to_device_layout(h, Y, h->Y, h->nv, true)) return 1;
     // aux.microph_variables.N_aer is built from the initial profile and never refreshed by
     // the Box / col_sed rhs (no precompute_aux_activation! call): snapshot it
     int na = na_index(h->cfg.moisture, h->cfg.precip);
@@ -743,7 +773,19 @@ static int set_state_impl(kid_handle_t* h, const void* Y, bool sync) {
 int kid_get_state(kid_handle_t* h, void* Y) {
     if (!h || !Y) return fail("null argument");
     if (!h->state_set) return fail("kid_set_state has not been called");
-    return to_host_layout(h, h->Y, Y, h->nv);
+    return to_host_layout(h, h->Y, Y, h->nv, true, true);
+}
+
+int kid_set_column_map(kid_handle_t* h, const int32_t* host_column_of) {
+    if (!h) return fail("null handle");
+    if (h->colmap) { cudaFree(h->colmap); h->colmap = nullptr; }
+    if (!host_column_of) return 0;
+    for (int c = 0; c < h->cfg.nc; ++c)
+        if (host_column_of[c] < 0) return fail("kid_set_column_map: negative host column");
+    KID_CUDA(cudaMalloc(&h->colmap, size_t(h->cfg.nc) * sizeof(int)));
+    KID_CUDA(cudaMemcpyAsync(h->colmap, host_column_of, size_t(h->cfg.nc) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    KID_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
 }
 
 int kid_set_steps_per_launch(kid_handle_t* h, int32_t n) {
@@ -850,9 +892,9 @@ int kid_output_enqueue(kid_handle_t* h, double t, int32_t nfields, const int32_t
     if (launch_tile(h, t, 1, 2, -1)) return 1;
     dim3 block(32, 8), grid((h->ncp + 31) / 32, (nfields * nz + 31) / 32);
     if (h->f64)
-        device_to_host_layout<double><<<grid, block, 0, h->stream>>>((const double*)h->out, (double*)h->ostage[b], nc, h->ncp, nfields, nz);
+        device_to_host_layout<double><<<grid, block, 0, h->stream>>>((const double*)h->out, (double*)h->ostage[b], nullptr, nc, h->ncp, nfields, nz);
     else
-        device_to_host_layout<float><<<grid, block, 0, h->stream>>>((const float*)h->out, (float*)h->ostage[b], nc, h->ncp, nfields, nz);
+        device_to_host_layout<float><<<grid, block, 0, h->stream>>>((const float*)h->out, (float*)h->ostage[b], nullptr, nc, h->ncp, nfields, nz);
     KID_CUDA(cudaGetLastError());
     h->launches++;
     KID_CUDA(cudaEventRecord(h->ev_ready[b], h->stream));

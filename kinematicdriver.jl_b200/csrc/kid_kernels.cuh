@@ -674,16 +674,21 @@ __global__ void profile_consts_kernel(const FT* __restrict__ T, FT* __restrict__
 }
 
 // ------------------------------------------------------------ layout transposes
-// host layout [column][var][level] <-> device layout [var][level][column(ncp)]
+// host layout [column][var][level] <-> device layout [var][level][column(ncp)].
+// `perm` (device array, may be null): device column i holds host column perm[i] — callers with members in arbitrary order
+// get the warp-coherent storage order (model.warp_coherent_order) without gathering on the host.
+// The host-layout side may be a device staging buffer or page-locked HOST memory (unified addressing): the kernels then
+// move the state over PCIe themselves, every column's (var, level) record in pieces of 128 B (or 512 B: *_wide).
 template <class FT>
-__global__ void host_to_device_layout(const FT* __restrict__ src, FT* __restrict__ dst, int nc, int ncp, int nv, int nz) {
+__global__ void host_to_device_layout(const FT* __restrict__ src, FT* __restrict__ dst, const int* __restrict__ perm, int nc, int ncp,
+                                      int nv, int nz) {
     __shared__ FT tile[32][33];
     // rows = (v, k) flattened (R = nv*nz), cols = columns
     const int R = nv * nz;
     int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         int cc = c0 + i, r = r0 + threadIdx.x;
-        tile[i][threadIdx.x] = (cc < nc && r < R) ? src[size_t(cc) * R + r] : FT(0);
+        tile[i][threadIdx.x] = (cc < nc && r < R) ? src[size_t(perm ? perm[cc] : cc) * R + r] : FT(0);
     }
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -692,7 +697,8 @@ __global__ void host_to_device_layout(const FT* __restrict__ src, FT* __restrict
     }
 }
 template <class FT>
-__global__ void device_to_host_layout(const FT* __restrict__ src, FT* __restrict__ dst, int nc, int ncp, int nv, int nz) {
+__global__ void device_to_host_layout(const FT* __restrict__ src, FT* __restrict__ dst, const int* __restrict__ perm, int nc, int ncp,
+                                      int nv, int nz) {
     __shared__ FT tile[32][33];
     const int R = nv * nz;
     int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -703,7 +709,38 @@ __global__ void device_to_host_layout(const FT* __restrict__ src, FT* __restrict
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         int cc = c0 + i, r = r0 + threadIdx.x;
-        if (cc < nc && r < R) dst[size_t(cc) * R + r] = tile[threadIdx.x][i];
+        if (cc < nc && r < R) dst[size_t(perm ? perm[cc] : cc) * R + r] = tile[threadIdx.x][i];
+    }
+}
+// Float32, R a multiple of 128: a warp moves 512 contiguous bytes of one column's record (float4 per lane) — the request
+// size that matters when the host-layout side is page-locked host memory reached over PCIe.  Tile: 32 columns x 128 rows.
+static __global__ void __launch_bounds__(256) host_to_device_layout_wide(const float* __restrict__ src, float* __restrict__ dst,
+                                                                  const int* __restrict__ perm, int nc, int ncp, int R) {
+    __shared__ float tile[128][33];
+    const int r0 = blockIdx.y * 128, c0 = blockIdx.x * 32;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i = w; i < 32; i += 8) {
+        const int cc = c0 + i;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cc < nc) v = *reinterpret_cast<const float4*>(src + size_t(perm ? perm[cc] : cc) * R + r0 + 4 * lane);
+        tile[4 * lane][i] = v.x; tile[4 * lane + 1][i] = v.y; tile[4 * lane + 2][i] = v.z; tile[4 * lane + 3][i] = v.w;
+    }
+    __syncthreads();
+    for (int r = w; r < 128; r += 8)
+        if (c0 + lane < ncp) dst[size_t(r0 + r) * ncp + c0 + lane] = tile[r][lane];
+}
+static __global__ void __launch_bounds__(256) device_to_host_layout_wide(const float* __restrict__ src, float* __restrict__ dst,
+                                                                  const int* __restrict__ perm, int nc, int ncp, int R) {
+    __shared__ float tile[128][33];
+    const int r0 = blockIdx.y * 128, c0 = blockIdx.x * 32;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int r = w; r < 128; r += 8) tile[r][lane] = (c0 + lane < ncp) ? src[size_t(r0 + r) * ncp + c0 + lane] : 0.f;
+    __syncthreads();
+    for (int i = w; i < 32; i += 8) {
+        const int cc = c0 + i;
+        if (cc < nc)
+            *reinterpret_cast<float4*>(dst + size_t(perm ? perm[cc] : cc) * R + r0 + 4 * lane) =
+                make_float4(tile[4 * lane][i], tile[4 * lane + 1][i], tile[4 * lane + 2][i], tile[4 * lane + 3][i]);
     }
 }
 

@@ -96,6 +96,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         "kid_set_state": (C.c_int, [H, C.c_void_p]),
         "kid_get_state": (C.c_int, [H, C.c_void_p]),
         "kid_set_state_async": (C.c_int, [H, C.c_void_p]),
+        "kid_set_column_map": (C.c_int, [H, C.POINTER(C.c_int32)]),
         "kid_get_state_async": (C.c_int, [H, C.c_void_p]),
         "kid_init_shipway_hill": (C.c_int, [H, C.POINTER(C.c_double), C.c_void_p, C.c_int32]),
         "kid_get_profiles": (C.c_int, [H, C.c_void_p, C.c_void_p]),
@@ -282,6 +283,15 @@ class Handle:
         """Enqueue the upload only; Y_pinned must be page-locked, C-contiguous FLOAT_TYPE and stay untouched until synchronize()."""
         assert Y_pinned.dtype == self.dtype and Y_pinned.flags.c_contiguous
         self._check(self.lib.kid_set_state_async(self._h, _ptr(Y_pinned)))
+
+    def set_column_map(self, host_column_of: np.ndarray | None):
+        """Device column i <-> host column host_column_of[i] in set_state* / get_state* (page-locked host arrays)."""
+        if host_column_of is None:
+            self._check(self.lib.kid_set_column_map(self._h, None))
+            return
+        m = np.ascontiguousarray(host_column_of, dtype=np.int32)
+        assert m.size == self.cfg.nc
+        self._check(self.lib.kid_set_column_map(self._h, m.ctypes.data_as(C.POINTER(C.c_int32))))
 
     def get_state_async(self, out_pinned: np.ndarray):
         assert out_pinned.dtype == self.dtype and out_pinned.flags.c_contiguous

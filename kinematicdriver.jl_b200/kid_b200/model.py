@@ -473,6 +473,7 @@ def _k1d_ensemble_case_device_ic(FT, c, seed, device, order, options) -> Case:
     w1 = 2.0 * (0.5 + 0.6 * uniform01(seed, c, 0))
     Nd = 10.0 ** (7.0 + 1.5 * uniform01(seed, c, 1))
     p0 = 1e5 * (0.98 + 0.04 * uniform01(seed, c, 2))
+    perm = np.arange(nc)
     if order in ("sorted", "morton"):
         perm = morton_order(w1, np.log10(Nd), p0)
         w1, Nd, p0 = w1[perm], Nd[perm], p0[perm]
@@ -486,7 +487,7 @@ def _k1d_ensemble_case_device_ic(FT, c, seed, device, order, options) -> Case:
     sounding = [o[k] for k in ("z_0", "z_1", "z_2", "rv_0", "rv_1", "rv_2", "tht_0", "tht_1", "tht_2")]
     return Case(cfg=cfg, params=base.params, ρ_dry=None, T=None, Y0=None, var_names=base.var_names,
                 col_scalars={COL_W1: w1.astype(FT), COL_PRESCRIBED_ND: Nd.astype(FT)}, z_centers=base.z_centers,
-                meta=dict(base.meta, seed=seed, order=order, p0=p0),
+                meta=dict(base.meta, seed=seed, order=order, p0=p0, column_perm=perm),  # column i = member c[column_perm[i]]
                 device_ic=dict(sounding=sounding, p0=p0.astype(FT), dry=False,
                                q_surf=float(base.col_scalars[COL_Q_SURF][0])))
 

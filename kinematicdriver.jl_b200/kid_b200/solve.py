@@ -207,9 +207,13 @@ class PipelinedEnsemble:
     """A large ensemble split into column chunks, one handle (and CUDA stream) per chunk: the upload of chunk i+1 and
     the download of chunk i-1 overlap the stepping of chunk i.  Host arrays must be page-locked (pinned)."""
 
-    def __init__(self, case: M.Case, nchunks: int = 4, backend=Handle):
+    def __init__(self, case: M.Case, nchunks: int = 4, backend=Handle, host_column_of: np.ndarray | None = None):
+        """host_column_of: column i of `case` (the device storage order, e.g. model.warp_coherent_order) is row
+        host_column_of[i] of the host arrays handed to `solve` — the caller keeps its own member order, the layout kernels
+        gather / scatter straight from / to the page-locked host array (kid_set_column_map)."""
         import copy
         nc = case.cfg.nc
+        self.host_column_of = None if host_column_of is None else np.ascontiguousarray(host_column_of, dtype=np.int32)
         edges = np.linspace(0, nc, nchunks + 1).astype(int)
         edges = (edges // 32) * 32
         edges[-1] = nc
@@ -217,6 +221,8 @@ class PipelinedEnsemble:
         self.handles = []
         for a, b in self.ranges:
             self.handles.append(M.make_handle(M.slice_columns(case, a, b), backend))
+            if self.host_column_of is not None:
+                self.handles[-1].set_column_map(self.host_column_of[a:b])
 
     def set_steps_per_launch(self, n: int):
         for h in self.handles:
@@ -225,7 +231,7 @@ class PipelinedEnsemble:
     def solve(self, Y_pinned: np.ndarray, t0: float, nsteps: int):
         """In place: Y_pinned[column, variable, level] holds the state at t0 on entry and at t0 + nsteps·dt on return."""
         for (a, b), h in zip(self.ranges, self.handles):
-            view = Y_pinned[a:b]
+            view = Y_pinned if self.host_column_of is not None else Y_pinned[a:b]  # with a map: rows are addressed through it
             h.set_state_async(view)
             h.step(t0, nsteps)
             h.get_state_async(view)
