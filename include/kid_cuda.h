@@ -242,6 +242,14 @@ int kid_k2d_stage_end(kid_handle_t* h, int32_t stage);
  * `left`, ordered on both handles' streams (peer copies over NVLink when the handles sit on different GPUs).
  * With separate processes the caller exchanges the buffers of kid_k2d_edge_buffers itself (NCCL send/recv). */
 int kid_k2d_exchange_local(kid_handle_t* left, kid_handle_t* right);
+/* In-library exchange for one process per GPU (replaces the cross-rank part of CC.Spaces.weighted_dss!,
+ * src/K2DModel/tendency.jl:70,106-108,156-157,206-207, for a host that has no device-side communication of its own):
+ * rank 0 obtains a 128-byte id with kid_nccl_unique_id and distributes it by any means (Julia: Distributed / MPI.jl; the
+ * Python mirror: torch.distributed.broadcast_object_list); every rank of the periodic x-ring then calls kid_k2d_comm_init.
+ * Afterwards kid_step on the decomposed handle runs all SSPRK33 stages itself, with one grouped ncclSend/ncclRecv of the packed
+ * edge columns per stage on the handle's stream.  NCCL is bound at run time (dlopen of libnccl.so.2). */
+int kid_nccl_unique_id(void* id128);
+int kid_k2d_comm_init(kid_handle_t* h, int32_t rank, int32_t world, const void* id128);
 
 /* plumbing */
 int kid_synchronize(kid_handle_t* h);

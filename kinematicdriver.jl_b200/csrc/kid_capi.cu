@@ -2,6 +2,8 @@
 // Host-side plumbing only (device memory, layout conversion, launch geometry); all
 // arithmetic of the hot path lives in kid_kernels.cuh / kid_physics.cuh.  There is no CPU
 // fallback: every entry point that computes fails when no CUDA device is usable.
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -23,6 +25,55 @@ int fail(const std::string& m) { g_err = m; return 1; }
         if (e__ != cudaSuccess)                                                                \
             return fail(std::string(#call) + ": " + cudaGetErrorString(e__) + " (libkid_cuda has no CPU fallback)"); \
     } while (0)
+
+// NCCL is bound at run time (dlopen): libkid_cuda.so has no link-time dependency on it, and inside a process that already
+// loaded a NCCL (PyTorch's bundled libnccl.so.2) the same library instance is reused.  Only the point-to-point subset the
+// K2D edge exchange needs.  ncclUniqueId is 128 bytes, ncclDataType_t: ncclFloat32 = 7, ncclFloat64 = 8.
+struct NcclUniqueIdBytes { char internal[128]; };  // layout of ncclUniqueId (passed BY VALUE to ncclCommInitRank)
+struct NcclApi {
+    typedef struct ncclComm* comm_t;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(comm_t*, int, NcclUniqueIdBytes, int) = nullptr;
+    int (*CommDestroy)(comm_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+const NcclApi& nccl_api() {
+    static NcclApi api = [] {
+        NcclApi a;
+        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) return a;
+        a.GetUniqueId = reinterpret_cast<int (*)(void*)>(dlsym(lib, "ncclGetUniqueId"));
+        a.CommDestroy = reinterpret_cast<int (*)(NcclApi::comm_t)>(dlsym(lib, "ncclCommDestroy"));
+        a.GroupStart = reinterpret_cast<int (*)()>(dlsym(lib, "ncclGroupStart"));
+        a.GroupEnd = reinterpret_cast<int (*)()>(dlsym(lib, "ncclGroupEnd"));
+        a.Send = reinterpret_cast<int (*)(const void*, size_t, int, int, NcclApi::comm_t, cudaStream_t)>(dlsym(lib, "ncclSend"));
+        a.Recv = reinterpret_cast<int (*)(void*, size_t, int, int, NcclApi::comm_t, cudaStream_t)>(dlsym(lib, "ncclRecv"));
+        a.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(lib, "ncclGetErrorString"));
+        a.CommInitRank = reinterpret_cast<int (*)(NcclApi::comm_t*, int, NcclUniqueIdBytes, int)>(dlsym(lib, "ncclCommInitRank"));
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.GroupStart && a.GroupEnd && a.Send && a.Recv;
+        return a;
+    }();
+    return api;
+}
+
+// Every entry point runs on the handle's device and leaves the caller's current device untouched: several handles on
+// different GPUs may be driven from one thread (kid_k2d_exchange_local, k2d.LocalRing).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 int nvars_of(int moisture, int precip) {
     if (moisture != KID_MOIST_EQ && moisture != KID_MOIST_NONEQ) return -1;
@@ -73,7 +124,10 @@ struct kid_handle {
     bool params_set = false, profiles_set = false, state_set = false;
     int C = 32, NW = 1;
     // K2D
-    void *U = nullptr, *S = nullptr, *prev_aux = nullptr, *xc = nullptr, *out2 = nullptr;
+    void *U = nullptr, *Y3 = nullptr, *S = nullptr, *prev_aux = nullptr, *xc = nullptr, *out2 = nullptr;
+    // in-library neighbour exchange of a decomposed domain (kid_k2d_comm_init): NCCL communicator of the x-ring
+    struct ncclComm* comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
     double *zsin = nullptr, *cosx = nullptr, *cosz = nullptr;
     void *send_left = nullptr, *send_right = nullptr, *recv_left = nullptr, *recv_right = nullptr;
     int Nq = 0, nfields = 0;
@@ -95,6 +149,8 @@ struct kid_handle {
     int obs_var[KID_MAX_OBS], obs_per[KID_MAX_OBS], obs_off[KID_MAX_OBS + 1];
     int i_tot = 0, i_liq = -1, i_ice = -1, i_rai = -1, i_sno = -1, i_Nl = -1, i_Nr = -1, i_Na = -1;
 };
+
+#define KID_ON_DEVICE(h) DeviceGuard kid_device_guard__((h) ? (h)->cfg.device : 0)
 
 namespace {
 
@@ -352,13 +408,13 @@ int choose_tile(kid_handle* h) {
     if (s > size_t(max_smem)) return fail("column too tall for one shared-memory tile (nz too large)");
     int maxt = h->f64 ? tile_max_threads<double>() : tile_max_threads<float>();
     int NW = std::max(2, std::min(maxt / C, nz));
-    if (h->cfg.reserved[0] > 0) NW = std::max(1, std::min(NW, int(h->cfg.reserved[0])));  // tuning override
+    if (h->cfg.reserved[0] > 0) NW = std::max(2, std::min(NW, int(h->cfg.reserved[0])));  // tuning override (the round-boundary stash needs NW >= 2)
     h->C = C;
     h->NW = NW;
     return 0;
 }
 
-int launch_tile(kid_handle* h, double t0, int nsteps, int diag_mode, int field, int update_prev = 0) {
+int launch_tile(kid_handle* h, double t0, int nsteps, int diag_mode, int field, int update_prev = 0, void* Y_stage = nullptr) {
     if (diag_mode == 2 && field >= 0) { h->diag_nfields = 1; h->diag_fields[0] = field; }  // field < 0: h->diag_fields preset
     cudaError_t e;
     if (diag_mode == 0 && pair_capable(h) && h->gconst && h->state_map_ok) {
@@ -370,10 +426,12 @@ int launch_tile(kid_handle* h, double t0, int nsteps, int diag_mode, int field, 
     if (h->f64) {
         auto a = make_args<double>(h, t0, nsteps, diag_mode, field);
         a.update_prev = update_prev;
+        if (Y_stage) a.Y = (double*)Y_stage;
         e = h->lt->k1d_d(h->cfg.moisture, diag_mode != 0, a, h->prm_d, h->stream);
     } else {
         auto a = make_args<float>(h, t0, nsteps, diag_mode, field);
         a.update_prev = update_prev;
+        if (Y_stage) a.Y = (float*)Y_stage;
         e = h->lt->k1d_f(h->cfg.moisture, diag_mode != 0, a, h->prm_f, h->stream);
     }
     if (e != cudaSuccess) return fail(std::string("k1d_tile_kernel launch: ") + cudaGetErrorString(e));
@@ -397,7 +455,7 @@ double k2d_stage_time(kid_handle* h, double t_step, int stage) {
     float t = float(t_step), dt = float(h->cfg.dt);
     return double(stage == 0 ? t : (stage == 1 ? t + dt : t + dt / 2.0f));
 }
-int k2d_begin(kid_handle* h, double t_stage) {
+int k2d_begin(kid_handle* h, double t_stage, int /*stage*/) {
     if (ensure_out(h, state_elems(h) * h->fsz)) return 1;
     if (launch_tile(h, t_stage, 1, 1, 0, 1)) return 1;
     dim3 block(64), grid((h->cfg.helem + 63) / 64, h->cfg.nz);
@@ -519,6 +577,8 @@ int obs_launch(kid_handle_t* h, int time_cell) {
 
 extern "C" {
 
+static int k2d_exchange_nccl(kid_handle_t* h);
+
 int kid_nvars(int moisture, int precip) { return nvars_of(moisture, precip); }
 
 int kid_var_names(int moisture, int precip, char* buf, size_t buflen) {
@@ -590,7 +650,8 @@ int kid_create(const kid_config_t* cfg, kid_handle_t** out) {
     if (cfg->precip == KID_PRECIP_2M && cfg->rain_formation != KID_RF_SB2006 && cfg->rain_formation != KID_RF_SB2006NL)
         return fail("invalid rain_formation for Precipitation2M");
     if (kid_device_count() < 1) return fail("no CUDA device visible: libkid_cuda has no CPU fallback");
-    KID_CUDA(cudaSetDevice(cfg->device));
+    if (cfg->device < 0 || cfg->device >= kid_device_count()) return fail("kid_config_t.device out of range");
+    DeviceGuard guard(cfg->device);  // the caller's current device is restored on return
 
     kid_handle* h = new kid_handle();
     h->cfg = *cfg;
@@ -623,8 +684,10 @@ int kid_create(const kid_config_t* cfg, kid_handle_t** out) {
 }
 
 void kid_destroy(kid_handle_t* h) {
+    KID_ON_DEVICE(h);
     if (!h) return;
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && nccl_api().ok) nccl_api().CommDestroy(h->comm);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     for (int b = 0; b < 2; ++b) {
         if (h->ostage[b]) cudaFree(h->ostage[b]);
@@ -632,7 +695,7 @@ void kid_destroy(kid_handle_t* h) {
         if (h->ev_done[b]) cudaEventDestroy(h->ev_done[b]);
     }
     for (void* p : {h->colmap, h->gconst, h->ps_liq, h->ps_mix, h->prm_sets, h->col_to_set, h->Y, h->rho_dry, h->T, h->w1, h->q_surf, h->Nd, h->aux_Naer,
-                    h->out, h->staging, h->U, h->S, h->prev_aux, h->xc, h->out2, h->send_left, h->send_right, h->recv_left,
+                    h->out, h->staging, h->U, h->Y3, h->S, h->prev_aux, h->xc, h->out2, h->send_left, h->send_right, h->recv_left,
                     h->recv_right, (void*)h->obsG, (void*)h->red, (void*)h->zsin, (void*)h->cosx, (void*)h->cosz})
         if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -640,6 +703,7 @@ void kid_destroy(kid_handle_t* h) {
 }
 
 int kid_set_params(kid_handle_t* h, const double* params, int32_t nparams, int32_t nsets, const int32_t* column_to_set) {
+    KID_ON_DEVICE(h);
     if (!h || !params) return fail("null argument");
     if (nparams != KID_NPARAMS) return fail("kid_set_params: nparams != KID_NPARAMS (header/library version skew)");
     if (nsets < 1) return fail("kid_set_params: nsets must be >= 1");
@@ -699,10 +763,12 @@ int kid_set_params(kid_handle_t* h, const double* params, int32_t nparams, int32
 }
 
 int kid_set_profiles(kid_handle_t* h, const void* rho_dry, const void* T, int32_t per_column) {
+    KID_ON_DEVICE(h);
     if (!h || !rho_dry || !T) return fail("null argument");
     const int nz = h->cfg.nz;
     size_t n = per_column ? size_t(nz) * h->ncp : size_t(nz);
     h->consts_dirty = true;
+    h->profiles_set = false;  // until the new profiles are on the device
     for (void** p : {&h->rho_dry, &h->T, &h->ps_liq, &h->ps_mix}) {
         if (*p) cudaFree(*p);
         *p = nullptr;
@@ -724,6 +790,7 @@ int kid_set_profiles(kid_handle_t* h, const void* rho_dry, const void* T, int32_
 }
 
 int kid_set_column_scalar(kid_handle_t* h, int32_t which, const void* values) {
+    KID_ON_DEVICE(h);
     if (!h) return fail("null handle");
     if (!h->params_set) return fail("kid_set_params must be called before kid_set_column_scalar");
     switch (which) {
@@ -735,9 +802,12 @@ int kid_set_column_scalar(kid_handle_t* h, int32_t which, const void* values) {
 }
 
 static int set_state_impl(kid_handle_t* h, const void* Y, bool sync);
-int kid_set_state(kid_handle_t* h, const void* Y) { return set_state_impl(h, Y, true); }
-int kid_set_state_async(kid_handle_t* h, const void* Y) { return set_state_impl(h, Y, false); }
+int kid_set_state(kid_handle_t* h, const void* Y) {
+    KID_ON_DEVICE(h); return set_state_impl(h, Y, true); }
+int kid_set_state_async(kid_handle_t* h, const void* Y) {
+    KID_ON_DEVICE(h); return set_state_impl(h, Y, false); }
 int kid_get_state_async(kid_handle_t* h, void* Y) {
+    KID_ON_DEVICE(h);
     if (!h || !Y) return fail("null argument");
     if (!h->state_set) return fail("kid_set_state has not been called");
     return to_host_layout(h, h->Y, Y, h->nv, false, true);
@@ -771,12 +841,14 @@ static int set_state_impl(kid_handle_t* h, const void* Y, bool sync) {
 }
 
 int kid_get_state(kid_handle_t* h, void* Y) {
+    KID_ON_DEVICE(h);
     if (!h || !Y) return fail("null argument");
     if (!h->state_set) return fail("kid_set_state has not been called");
     return to_host_layout(h, h->Y, Y, h->nv, true, true);
 }
 
 int kid_set_column_map(kid_handle_t* h, const int32_t* host_column_of) {
+    KID_ON_DEVICE(h);
     if (!h) return fail("null handle");
     if (h->colmap) { cudaFree(h->colmap); h->colmap = nullptr; }
     if (!host_column_of) return 0;
@@ -789,6 +861,7 @@ int kid_set_column_map(kid_handle_t* h, const int32_t* host_column_of) {
 }
 
 int kid_set_steps_per_launch(kid_handle_t* h, int32_t n) {
+    KID_ON_DEVICE(h);
     if (!h) return fail("null handle");
     if (n < 0) return fail("steps_per_launch must be >= 0");
     h->steps_per_launch = n;
@@ -796,16 +869,20 @@ int kid_set_steps_per_launch(kid_handle_t* h, int32_t n) {
 }
 
 int kid_step(kid_handle_t* h, double t0, int32_t nsteps) {
+    KID_ON_DEVICE(h);
     if (check_ready(h)) return 1;
     if (nsteps < 0) return fail("nsteps must be >= 0");
     if (h->cfg.model == KID_MODEL_K2D) {
-        if (h->cfg.helem != h->cfg.helem_global)
-            return fail("kid_step on a decomposed K2D handle: drive the stages with kid_k2d_stage_begin/_end and exchange the edges");
+        const bool decomposed = h->cfg.helem != h->cfg.helem_global;
+        if (decomposed && !h->comm)
+            return fail("kid_step on a decomposed K2D handle: call kid_k2d_comm_init first (in-library NCCL edge exchange), or drive the "
+                        "stages with kid_k2d_stage_begin/_end and exchange the edges yourself");
         for (int s = 0; s < nsteps; ++s) {
             double ts = h->f64 ? t0 + double(s) * h->cfg.dt : double(float(t0 + double(s) * h->cfg.dt));
             for (int stage = 0; stage < 3; ++stage) {
-                if (k2d_begin(h, k2d_stage_time(h, ts, stage))) return 1;
-                if (k2d_end(h, stage, 0, 0)) return 1;
+                if (k2d_begin(h, k2d_stage_time(h, ts, stage), stage)) return 1;
+                if (decomposed && k2d_exchange_nccl(h)) return 1;
+                if (k2d_end(h, stage, decomposed ? 1 : 0, 0)) return 1;
             }
         }
         return 0;
@@ -823,13 +900,14 @@ int kid_step(kid_handle_t* h, double t0, int32_t nsteps) {
 }
 
 int kid_rhs(kid_handle_t* h, double t, void* dY_out) {
+    KID_ON_DEVICE(h);
     if (check_ready(h)) return 1;
     if (!dY_out) return fail("null argument");
     if (ensure_out(h, state_elems(h) * h->fsz)) return 1;
     KID_CUDA(cudaMemsetAsync(h->out, 0, state_elems(h) * h->fsz, h->stream));
     if (h->cfg.model == KID_MODEL_K2D) {
         if (h->cfg.helem != h->cfg.helem_global) return fail("kid_rhs is only available on an undecomposed K2D handle");
-        if (k2d_begin(h, t)) return 1;
+        if (k2d_begin(h, t, 0)) return 1;
         if (k2d_end(h, 0, 0, 1)) return 1;
         return to_host_layout(h, h->out2, dY_out, h->nv);
     }
@@ -838,6 +916,7 @@ int kid_rhs(kid_handle_t* h, double t, void* dY_out) {
 }
 
 int kid_get_aux(kid_handle_t* h, double t, int32_t field, void* out) {
+    KID_ON_DEVICE(h);
     if (check_ready(h)) return 1;
     if (!out) return fail("null argument");
     if (field < 0 || field >= KID_NAUX) return fail("invalid aux field id");
@@ -857,6 +936,7 @@ static int set_diag_fields(kid_handle_t* h, int32_t nfields, const int32_t* fiel
 }
 
 int kid_get_aux_many(kid_handle_t* h, double t, int32_t nfields, const int32_t* fields, void* out) {
+    KID_ON_DEVICE(h);
     if (check_ready(h)) return 1;
     if (!out) return fail("null argument");
     if (set_diag_fields(h, nfields, fields)) return 1;
@@ -866,6 +946,7 @@ int kid_get_aux_many(kid_handle_t* h, double t, int32_t nfields, const int32_t* 
 }
 
 int kid_output_enqueue(kid_handle_t* h, double t, int32_t nfields, const int32_t* fields, void* out_pinned) {
+    KID_ON_DEVICE(h);
     if (check_ready(h)) return 1;
     if (!out_pinned) return fail("null argument");
     if (set_diag_fields(h, nfields, fields)) return 1;
@@ -906,12 +987,23 @@ int kid_output_enqueue(kid_handle_t* h, double t, int32_t nfields, const int32_t
 }
 
 int kid_init_shipway_hill(kid_handle_t* h, const double* sounding, const void* p0, int32_t dry) {
+    KID_ON_DEVICE(h);
     if (!h || !sounding) return fail("null argument");
     if (!h->params_set) return fail("kid_set_params must be called before kid_init_shipway_hill");
     if (h->cfg.model != KID_MODEL_K1D && h->cfg.model != KID_MODEL_K1D_COL_SED)
         return fail("kid_init_shipway_hill: K1DModel handles only");
     const int nz = h->cfg.nz, nc = h->cfg.nc;
     const size_t n = size_t(nz) * h->ncp;
+    // arguments are checked before any device state is touched
+    if (!(sounding[2] >= h->cfg.z_max)) return fail("z_max cannot be higher than z_2");
+    if (!(sounding[1] > sounding[0]) || !(sounding[2] > sounding[1])) return fail("kid_init_shipway_hill: the sounding needs z_0 < z_1 < z_2");
+    void* p0_dev = nullptr;
+    KID_CUDA(cudaMalloc(&p0_dev, size_t(h->ncp) * h->fsz));
+    struct FreeOnExit { void* p; ~FreeOnExit() { if (p) cudaFree(p); } } p0_owner{p0_dev};
+    if (upload_columns(h, p0_dev, p0, 100000.0)) return 1;
+    // from here on the previous profiles / state are gone: the handle is not ready until the kernel has been launched
+    h->profiles_set = false;
+    h->state_set = false;
     for (void** p : {&h->rho_dry, &h->T, &h->ps_liq, &h->ps_mix}) {
         if (*p) cudaFree(*p);
         *p = nullptr;
@@ -920,9 +1012,6 @@ int kid_init_shipway_hill(kid_handle_t* h, const double* sounding, const void* p
     }
     h->prof_per_column = 1;
     h->consts_dirty = true;
-    void* p0_dev = nullptr;
-    KID_CUDA(cudaMalloc(&p0_dev, size_t(h->ncp) * h->fsz));
-    if (upload_columns(h, p0_dev, p0, 100000.0)) { cudaFree(p0_dev); return 1; }
     KID_CUDA(cudaMemsetAsync(h->Y, 0, state_elems(h) * h->fsz, h->stream));
     auto fill = [&](auto& a) {
         a.z_0 = sounding[0]; a.z_1 = sounding[1]; a.z_2 = sounding[2];
@@ -934,7 +1023,6 @@ int kid_init_shipway_hill(kid_handle_t* h, const double* sounding, const void* p
         a.nz = nz; a.nc = nc; a.ncp = h->ncp; a.nv = h->nv; a.nsub = 4; a.dry = dry;
         a.i_tot = 0; a.i_Na = na_index(h->cfg.moisture, h->cfg.precip);
     };
-    if (!(sounding[2] >= h->cfg.z_max)) { cudaFree(p0_dev); return fail("z_max cannot be higher than z_2"); }
     if (h->f64) {
         ICArgs<double> a{}; fill(a);
         a.p0 = (const double*)p0_dev; a.Nd = (const double*)h->Nd; a.rho_dry = (double*)h->rho_dry; a.T = (double*)h->T;
@@ -955,13 +1043,13 @@ int kid_init_shipway_hill(kid_handle_t* h, const double* sounding, const void* p
         KID_CUDA(cudaMemcpyAsync(h->aux_Naer, (const char*)h->Y + size_t(na) * plane, plane, cudaMemcpyDeviceToDevice, h->stream));
     }
     KID_CUDA(cudaStreamSynchronize(h->stream));
-    cudaFree(p0_dev);
     h->profiles_set = true;
     h->state_set = true;
     return 0;
 }
 
 int kid_get_profiles(kid_handle_t* h, void* rho_dry, void* T) {
+    KID_ON_DEVICE(h);
     if (!h || !rho_dry || !T) return fail("null argument");
     if (!h->profiles_set) return fail("no profiles on the device yet");
     if (h->prof_per_column) {
@@ -982,12 +1070,14 @@ void* kid_host_alloc(size_t bytes) {
 void kid_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int kid_output_wait(kid_handle_t* h) {
+    KID_ON_DEVICE(h);
     if (!h) return fail("null handle");
     if (h->copy_stream) KID_CUDA(cudaStreamSynchronize(h->copy_stream));
     return 0;
 }
 
 int kid_reduce_max(kid_handle_t* h, double t, int32_t field, double* out) {
+    KID_ON_DEVICE(h);
     if (check_ready(h)) return 1;
     if (!out) return fail("null argument");
     if (field < 0 || field >= KID_NAUX) return fail("invalid aux field id");
@@ -1010,6 +1100,7 @@ int kid_reduce_max(kid_handle_t* h, double t, int32_t field, double* out) {
 
 int kid_obs_configure(kid_handle_t* h, int32_t nvars, const int32_t* var_ids, const int32_t* nz_per_filtered_cell,
                       int32_t nt_filtered, int32_t nt_per_filtered_cell, int64_t* n_out) {
+    KID_ON_DEVICE(h);
     if (!h || !var_ids) return fail("null argument");
     if (h->cfg.model == KID_MODEL_K2D) return fail("kid_obs_*: K1D / Box handles only");
     if (nvars < 1 || nvars > KID_MAX_OBS) return fail("kid_obs_configure: 1..16 observables");
@@ -1050,6 +1141,7 @@ int kid_obs_configure(kid_handle_t* h, int32_t nvars, const int32_t* var_ids, co
 }
 
 int kid_obs_accumulate(kid_handle_t* h, int32_t time_cell) {
+    KID_ON_DEVICE(h);
     if (check_ready(h)) return 1;
     if (!h->obsG) return fail("kid_obs_accumulate: call kid_obs_configure first");
     if (time_cell < 0 || time_cell >= h->obs_nt_filtered) return fail("kid_obs_accumulate: time cell out of range");
@@ -1057,6 +1149,7 @@ int kid_obs_accumulate(kid_handle_t* h, int32_t time_cell) {
 }
 
 int kid_obs_get(kid_handle_t* h, double* G) {
+    KID_ON_DEVICE(h);
     if (!h || !G) return fail("null argument");
     if (!h->obsG) return fail("kid_obs_get: call kid_obs_configure first");
     const size_t bytes = size_t(h->cfg.nc) * h->obs_nt_filtered * h->obs_n_out * sizeof(double);
@@ -1066,14 +1159,16 @@ int kid_obs_get(kid_handle_t* h, double* G) {
 }
 
 int kid_k2d_stage_begin(kid_handle_t* h, double t0, int32_t stage) {
+    KID_ON_DEVICE(h);
     if (check_ready(h)) return 1;
     if (h->cfg.model != KID_MODEL_K2D) return fail("not a K2D handle");
     if (stage < 0 || stage > 2) return fail("stage must be 0, 1 or 2");
     double ts = h->f64 ? t0 : double(float(t0));
-    return k2d_begin(h, k2d_stage_time(h, ts, stage));
+    return k2d_begin(h, k2d_stage_time(h, ts, stage), stage);
 }
 int kid_k2d_edge_buffers(kid_handle_t* h, void** send_left, void** send_right, void** recv_left, void** recv_right,
                          size_t* edge_count) {
+    KID_ON_DEVICE(h);
     if (!h || h->cfg.model != KID_MODEL_K2D) return fail("not a K2D handle");
     if (send_left) *send_left = h->send_left;
     if (send_right) *send_right = h->send_right;
@@ -1083,10 +1178,61 @@ int kid_k2d_edge_buffers(kid_handle_t* h, void** send_left, void** send_right, v
     return 0;
 }
 int kid_k2d_stage_end(kid_handle_t* h, int32_t stage) {
+    KID_ON_DEVICE(h);
     if (check_ready(h)) return 1;
     if (h->cfg.model != KID_MODEL_K2D) return fail("not a K2D handle");
     if (stage < 0 || stage > 2) return fail("stage must be 0, 1 or 2");
     return k2d_end(h, stage, 1, 0);
+}
+
+int kid_nccl_unique_id(void* id128) {
+    if (!id128) return fail("null argument");
+    const NcclApi& n = nccl_api();
+    if (!n.ok) return fail("libnccl.so.2 could not be loaded: the in-library K2D exchange needs NCCL");
+    int rc = n.GetUniqueId(id128);
+    if (rc != 0) return fail(std::string("ncclGetUniqueId: ") + (n.GetErrorString ? n.GetErrorString(rc) : "error"));
+    return 0;
+}
+
+int kid_k2d_comm_init(kid_handle_t* h, int32_t rank, int32_t world, const void* id128) {
+    if (!h || !id128) return fail("null argument");
+    KID_ON_DEVICE(h);
+    if (h->cfg.model != KID_MODEL_K2D) return fail("not a K2D handle");
+    if (world < 1 || rank < 0 || rank >= world) return fail("kid_k2d_comm_init: invalid rank / world");
+    const NcclApi& n = nccl_api();
+    if (!n.ok) return fail("libnccl.so.2 could not be loaded: the in-library K2D exchange needs NCCL");
+    if (h->comm) { n.CommDestroy(h->comm); h->comm = nullptr; }
+    NcclUniqueIdBytes id;
+    std::memcpy(&id, id128, sizeof(id));
+    int rc = n.CommInitRank(&h->comm, world, id, rank);
+    if (rc != 0) { h->comm = nullptr; return fail(std::string("ncclCommInitRank: ") + (n.GetErrorString ? n.GetErrorString(rc) : "error")); }
+    h->comm_rank = rank;
+    h->comm_world = world;
+    return 0;
+}
+
+// periodic ring exchange of the packed rank-edge columns on the handle's stream (after the pack of k2d_begin, before the
+// DSS of k2d_end): recv_left <- left neighbour's send_right, recv_right <- right neighbour's send_left
+static int k2d_exchange_nccl(kid_handle_t* h) {
+    const NcclApi& n = nccl_api();
+    const size_t count = size_t(h->nfields) * h->cfg.nz;
+    const int dtype = h->f64 ? 8 : 7;  // ncclFloat64 : ncclFloat32
+    if (h->comm_world == 1) {
+        KID_CUDA(cudaMemcpyAsync(h->recv_left, h->send_right, count * h->fsz, cudaMemcpyDeviceToDevice, h->stream));
+        KID_CUDA(cudaMemcpyAsync(h->recv_right, h->send_left, count * h->fsz, cudaMemcpyDeviceToDevice, h->stream));
+        return 0;
+    }
+    const int left = (h->comm_rank + h->comm_world - 1) % h->comm_world, right = (h->comm_rank + 1) % h->comm_world;
+    int rc = n.GroupStart();
+    // world == 2: both neighbours are the same peer; NCCL matches sends and receives to a peer in issue order, so the
+    // receive order mirrors the peer's send order (its send_left is my recv_right)
+    if (!rc) rc = n.Send(h->send_left, count, dtype, left, h->comm, h->stream);
+    if (!rc) rc = n.Send(h->send_right, count, dtype, right, h->comm, h->stream);
+    if (!rc) rc = n.Recv(h->recv_right, count, dtype, right, h->comm, h->stream);
+    if (!rc) rc = n.Recv(h->recv_left, count, dtype, left, h->comm, h->stream);
+    int rc2 = n.GroupEnd();
+    if (rc || rc2) return fail(std::string("NCCL edge exchange: ") + (n.GetErrorString ? n.GetErrorString(rc ? rc : rc2) : "error"));
+    return 0;
 }
 
 int kid_k2d_exchange_local(kid_handle_t* left, kid_handle_t* right) {
@@ -1095,29 +1241,46 @@ int kid_k2d_exchange_local(kid_handle_t* left, kid_handle_t* right) {
     if (left->nfields != right->nfields || left->cfg.nz != right->cfg.nz || left->fsz != right->fsz)
         return fail("kid_k2d_exchange_local: handles of different shape");
     size_t bytes = size_t(left->nfields) * left->cfg.nz * left->fsz;
-    cudaEvent_t el, er;
-    KID_CUDA(cudaEventCreateWithFlags(&el, cudaEventDisableTiming));
-    KID_CUDA(cudaEventCreateWithFlags(&er, cudaEventDisableTiming));
-    // each copy runs on the RECEIVER's stream after the sender's pack kernel has finished
-    KID_CUDA(cudaEventRecord(el, left->stream));
-    KID_CUDA(cudaEventRecord(er, right->stream));
-    KID_CUDA(cudaStreamWaitEvent(right->stream, el, 0));
-    KID_CUDA(cudaStreamWaitEvent(left->stream, er, 0));
-    KID_CUDA(cudaMemcpyPeerAsync(right->recv_left, right->cfg.device, left->send_right, left->cfg.device, bytes, right->stream));
-    KID_CUDA(cudaMemcpyPeerAsync(left->recv_right, left->cfg.device, right->send_left, right->cfg.device, bytes, left->stream));
-    KID_CUDA(cudaEventDestroy(el));
-    KID_CUDA(cudaEventDestroy(er));
+    // each copy runs on the RECEIVER's stream after the sender's pack kernel has finished; an event belongs to the device
+    // of the stream it is recorded on
+    cudaEvent_t el = nullptr, er = nullptr;
+    {
+        DeviceGuard g(left->cfg.device);
+        KID_CUDA(cudaEventCreateWithFlags(&el, cudaEventDisableTiming));
+        KID_CUDA(cudaEventRecord(el, left->stream));
+    }
+    {
+        DeviceGuard g(right->cfg.device);
+        KID_CUDA(cudaEventCreateWithFlags(&er, cudaEventDisableTiming));
+        KID_CUDA(cudaEventRecord(er, right->stream));
+        KID_CUDA(cudaStreamWaitEvent(right->stream, el, 0));
+        KID_CUDA(cudaMemcpyPeerAsync(right->recv_left, right->cfg.device, left->send_right, left->cfg.device, bytes, right->stream));
+    }
+    {
+        DeviceGuard g(left->cfg.device);
+        KID_CUDA(cudaStreamWaitEvent(left->stream, er, 0));
+        KID_CUDA(cudaMemcpyPeerAsync(left->recv_right, left->cfg.device, right->send_left, right->cfg.device, bytes, left->stream));
+        KID_CUDA(cudaEventDestroy(el));
+    }
+    {
+        DeviceGuard g(right->cfg.device);
+        KID_CUDA(cudaEventDestroy(er));
+    }
     return 0;
 }
 
 int kid_synchronize(kid_handle_t* h) {
+    KID_ON_DEVICE(h);
     if (!h) return fail("null handle");
     KID_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }
-void* kid_stream(kid_handle_t* h) { return h ? (void*)h->stream : nullptr; }
-void* kid_state_device_ptr(kid_handle_t* h) { return h ? h->Y : nullptr; }
-int64_t kid_launch_count(kid_handle_t* h) { return h ? h->launches : 0; }
+void* kid_stream(kid_handle_t* h) {
+    KID_ON_DEVICE(h); return h ? (void*)h->stream : nullptr; }
+void* kid_state_device_ptr(kid_handle_t* h) {
+    KID_ON_DEVICE(h); return h ? h->Y : nullptr; }
+int64_t kid_launch_count(kid_handle_t* h) {
+    KID_ON_DEVICE(h); return h ? h->launches : 0; }
 const char* kid_last_error(void) { return g_err.c_str(); }
 const char* kid_version(void) { return "libkid_cuda 0.1 (sm_100a)"; }
 

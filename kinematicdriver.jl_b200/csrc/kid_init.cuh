@@ -101,9 +101,13 @@ __global__ void init_shipway_hill_kernel(const ICArgs<FT> A) {
     ICProfile<FT> pr(A);
     const size_t plane = size_t(A.nz) * A.ncp;
     double z = A.z_0, rho = pr.rho_surface(double(A.p0[c]));
-    double qv_s, th_s;
-    pr.sounding(0.0, qv_s, th_s);  // aux.q_surf = init_profile(z = 0).qv (K1DModel/ode_utils.jl:96)
-    A.q_surf[c] = FT(qv_s);
+    // aux.q_surf = init_profile(kid_params, thermo_params, z = 0).qv (K1DModel/ode_utils.jl:96): the reference calls it
+    // WITHOUT the dry flag, so q_surf is the moist sounding's surface humidity also for a dry initial state
+    {
+        const double rv_s = 0.0 < A.z_1 ? A.rv_0 + (A.rv_1 - A.rv_0) / (A.z_1 - A.z_0) * (0.0 - A.z_0)
+                                        : A.rv_1 + (A.rv_2 - A.rv_1) / (A.z_2 - A.z_1) * (0.0 - A.z_1);
+        A.q_surf[c] = FT(rv_s / (1.0 + rv_s));
+    }
     const double Nd = double(A.Nd[c]);
     for (int k = 0; k < A.nz; ++k) {
         const double zc = A.z_min + (k + 0.5) * A.dz;

@@ -5,6 +5,8 @@ src/K2DModel/tendency.jl:70,106-108,156-157,206-207).
 Three ways to run:
   * one handle owning the whole periodic domain: `handle.step(t0, n)` (the wrap is inside the kernel);
   * one PROCESS driving several sub-domain handles (`LocalRing`): kid_k2d_exchange_local peer copies;
+  * one process per GPU, exchange inside the library (`LibraryRing`, kid_k2d_comm_init): kid_step issues one grouped
+    ncclSend/ncclRecv of the packed edge columns per stage on its own stream — what a Julia host would use;
   * one process per GPU (`DistributedRing`): the edge buffers are exchanged with torch.distributed
     send/recv (NCCL over NVLink; gloo in the CPU tests of the plumbing).
 """
@@ -131,6 +133,22 @@ def exchange_edges(dist, send_left, send_right, recv_left, recv_right, rank: int
            dist.P2POp(dist.irecv, recv_right, right), dist.P2POp(dist.irecv, recv_left, left)]
     for req in dist.batch_isend_irecv(ops):
         req.wait()
+
+
+class LibraryRing:
+    """One process per GPU, exchange INSIDE the library (kid_k2d_comm_init): `dist` — any initialised torch.distributed
+    backend — only carries the 128-byte NCCL id from rank 0 to the others; afterwards `step` is one kid_step call."""
+
+    def __init__(self, handle: Handle, dist, rank: int, world: int):
+        from .lib import nccl_unique_id
+        box = [nccl_unique_id(handle.lib) if rank == 0 else None]
+        if world > 1:
+            dist.broadcast_object_list(box, src=0)
+        self.h = handle
+        handle.k2d_comm_init(rank, world, box[0])
+
+    def step(self, t0: float, nsteps: int):
+        self.h.step(t0, nsteps)
 
 
 class DistributedRing:

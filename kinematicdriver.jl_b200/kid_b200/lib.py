@@ -119,6 +119,8 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
                                            C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
         "kid_k2d_stage_end": (C.c_int, [H, C.c_int32]),
         "kid_k2d_exchange_local": (C.c_int, [H, H]),
+        "kid_nccl_unique_id": (C.c_int, [C.c_void_p]),
+        "kid_k2d_comm_init": (C.c_int, [H, C.c_int32, C.c_int32, C.c_void_p]),
         "kid_synchronize": (C.c_int, [H]),
         "kid_stream": (C.c_void_p, [H]),
         "kid_state_device_ptr": (C.c_void_p, [H]),
@@ -188,6 +190,15 @@ def _ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def nccl_unique_id(lib: C.CDLL | None = None) -> bytes:
+    """128-byte ncclUniqueId (kid_nccl_unique_id): rank 0 creates it, every rank passes it to Handle.k2d_comm_init."""
+    lib = lib or load_library()
+    buf = C.create_string_buffer(128)
+    if lib.kid_nccl_unique_id(buf) != 0:
+        raise KidCudaError(lib.kid_last_error().decode())
+    return buf.raw
+
+
 def measure_fp32_peak(device: int = 0, lib: C.CDLL | None = None) -> dict:
     """FFMA micro-benchmark on the device (kid_measure_fp32_peak): the Float32 roofline denominator, measured in the run."""
     lib = lib or load_library()
@@ -241,6 +252,7 @@ class Handle:
         t = np.ascontiguousarray(T, dtype=self.dtype)
         per_column = int(r.ndim == 2)
         self._check(self.lib.kid_set_profiles(self._h, _ptr(r), _ptr(t), per_column))
+        self._profiles_per_column = bool(per_column)
 
     def set_column_scalar(self, which: int, values: np.ndarray | None):
         if values is None:
@@ -259,10 +271,11 @@ class Handle:
             p = np.ascontiguousarray(np.broadcast_to(np.asarray(p0, dtype=self.dtype), (self.cfg.nc,)))
         self._check(self.lib.kid_init_shipway_hill(self._h, snd.ctypes.data_as(C.POINTER(C.c_double)),
                                                    None if p is None else _ptr(p), int(dry)))
+        self._profiles_per_column = True
 
     def get_profiles(self):
         """(ρ_dry, T) as uploaded / built on the device: [nc, nz] each (or [nz] for one shared profile)."""
-        shape = (self.cfg.nc, self.cfg.nz)
+        shape = (self.cfg.nc, self.cfg.nz) if getattr(self, "_profiles_per_column", True) else (self.cfg.nz,)
         r, t = np.empty(shape, dtype=self.dtype), np.empty(shape, dtype=self.dtype)
         self._check(self.lib.kid_get_profiles(self._h, _ptr(r), _ptr(t)))
         return r, t
@@ -386,6 +399,12 @@ class Handle:
 
     def k2d_exchange_local(self, right: "Handle"):
         self._check(self.lib.kid_k2d_exchange_local(self._h, right._h))
+
+    def k2d_comm_init(self, rank: int, world: int, unique_id: bytes):
+        """In-library NCCL ring of a decomposed K2D domain: afterwards step() exchanges the edge columns itself."""
+        assert len(unique_id) == 128
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self.lib.kid_k2d_comm_init(self._h, int(rank), int(world), buf))
 
     def k2d_edge_buffers(self):
         p = [C.c_void_p() for _ in range(4)]

@@ -11,7 +11,7 @@ from kid_b200 import k2d, model as M
 from kid_b200.lib import Handle
 
 ap = argparse.ArgumentParser(); ap.add_argument("--steps", type=int, default=200); ap.add_argument("--weak", action="store_true")
-ap.add_argument("--ft", default="f32"); ap.add_argument("--tile-c", type=int, default=0); ap.add_argument("--nw", type=int, default=0)
+ap.add_argument("--exchange", default="lib", choices=["lib", "torch"]); ap.add_argument("--ft", default="f32"); ap.add_argument("--tile-c", type=int, default=0); ap.add_argument("--nw", type=int, default=0)
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -27,7 +27,7 @@ cs = k2d.k2d_case(FT, rank=rank, world=world, device=local, **kw)
 if a.tile_c: cs.cfg.reserved[1] = a.tile_c
 if a.nw: cs.cfg.reserved[0] = a.nw
 h = M.make_handle(cs, Handle)
-ring = k2d.DistributedRing(h, dist, rank, world) if world > 1 else None
+ring = ((k2d.LibraryRing if a.exchange == "lib" else k2d.DistributedRing)(h, dist, rank, world)) if world > 1 else None
 def step(t0, n):
     if ring: ring.step(t0, n)
     else: h.step(t0, n)
@@ -41,6 +41,6 @@ if dist: dist.all_reduce(tt, op=dist.ReduceOp.MAX)
 Y = h.get_state()
 if rank == 0:
     n_nodes = nx * 4
-    print(json.dumps({"workload": "K2D NonEq+2M", "nodes": n_nodes, "levels": 256, "ft": a.ft, "n_gpus": world, "scaling": "weak" if a.weak else "strong",
+    print(json.dumps({"workload": "K2D NonEq+2M", "nodes": n_nodes, "levels": 256, "ft": a.ft, "n_gpus": world, "exchange": a.exchange if world > 1 else None, "scaling": "weak" if a.weak else "strong",
                       "ms_per_step": 1e3 * tt.item() / a.steps, "gp_steps_per_s": n_nodes * 256 * a.steps / tt.item(), "finite": bool(np.isfinite(Y).all())}))
 if dist: dist.barrier(); dist.destroy_process_group()

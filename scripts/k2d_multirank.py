@@ -16,7 +16,8 @@ kw = dict(nx=16, nz=32, npoly=4, moisture_choice="NonEquilibriumMoisture", preci
           t1=300.0, w1=2.5, domain_height=2400.0, domain_width=4800.0)
 FT = np.float32
 mine = M.make_handle(k2d.k2d_case(FT, rank=rank, world=world, device=local, **kw), Handle)
-ring = k2d.DistributedRing(mine, dist, rank, world)
+exchange = sys.argv[1] if len(sys.argv) > 1 else "lib"
+ring = (k2d.LibraryRing if exchange == "lib" else k2d.DistributedRing)(mine, dist, rank, world)
 ring.step(0.0, 120)
 mine.synchronize()
 Y = mine.get_state()
@@ -25,5 +26,5 @@ whole.step(0.0, 120)
 Yw = whole.get_state()
 off, cnt = k2d.partition_elements(16, world, rank)
 ref = Yw[off * 5:(off + cnt) * 5]
-print(f"rank {rank}/{world}: bitwise_equal={np.array_equal(Y, ref)} max_abs_diff={np.abs(Y - ref).max():.3e} finite={np.isfinite(Y).all()}", flush=True)
+print(f"[{exchange}] rank {rank}/{world}: bitwise_equal={np.array_equal(Y, ref)} max_abs_diff={np.abs(Y - ref).max():.3e} finite={np.isfinite(Y).all()}", flush=True)
 dist.barrier(); dist.destroy_process_group()
