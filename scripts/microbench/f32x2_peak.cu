@@ -65,7 +65,40 @@ void run(const char* name, double flops_per_loop_body, int iters) {
     cudaFree(out);
 }
 
+// dependent-issue latency: ONE warp per SM runs a single dependent chain; cycles per instruction from clock64()
+template <int MODE>
+__global__ void latency_kernel(float* out, long long* cyc, int iters, float a, float b) {
+    float x = threadIdx.x * 1e-3f;
+    u64 p = pk(x, x + 0.5f);
+    const u64 pa = pk(a, a), pb = pk(b, b);
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (MODE == 0) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(x) : "f"(a), "f"(b));
+            if (MODE == 1) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p) : "l"(pa), "l"(pb));
+            if (MODE == 2) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p) : "l"(pb));
+            if (MODE == 3) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x));
+        }
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x + lo(p);
+}
+template <int MODE>
+void latency(const char* name) {
+    float* out; long long* cyc;
+    cudaMalloc(&out, 148 * 32 * sizeof(float)); cudaMalloc(&cyc, 148 * sizeof(long long));
+    const int iters = 20000;
+    latency_kernel<MODE><<<148, 32>>>(out, cyc, iters, 1.0001f, 1e-7f);
+    long long h[148];
+    cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    printf("{\"dependent_chain\": \"%s\", \"cycles_per_instruction\": %.2f}\n", name, double(h[0]) / (double(iters) * 16));
+    cudaFree(out); cudaFree(cyc);
+}
+
 int main() {
+    latency<0>("FFMA"); latency<1>("FFMA2"); latency<2>("FADD2"); latency<3>("MUFU.EX2");
     const int N = 100000;
     run<0>("FFMA", 16, N);
     run<1>("FFMA2", 32, N);
