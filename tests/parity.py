@@ -56,3 +56,35 @@ def rhs_errors(a, b, Y, var_names, dt, FT):
         den = max(float(np.max(np.abs(b[:, i]))), 1000.0 * eps * scale[group_of(v)] / dt, 1e-300)
         out[v] = float(np.max(np.abs(a[:, i] - b[:, i])) / den)
     return out
+
+
+def pointwise_errors(a, b, var_names, floor=1e-3):
+    """Pointwise relative error with an absolute floor: max over grid points of |a - b| / max(|b|, floor * max|b_v|).
+    Unlike `errors` (normalised by the field maximum) a large relative error in a small-valued region shows, down to
+    `floor` of the field maximum."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    out = {}
+    for i, v in enumerate(var_names):
+        m = float(np.max(np.abs(b[:, i])))
+        if m == 0.0:
+            out[v] = float(np.max(np.abs(a[:, i])))
+            continue
+        out[v] = float(np.max(np.abs(a[:, i] - b[:, i]) / np.maximum(np.abs(b[:, i]), floor * m)))
+    return out
+
+
+def column_integrated_number_error(a, b, var_names):
+    """Relative error of Σ_levels (N_liq + N_rai + N_aer) per column (max over columns): insensitive to WHICH level a
+    knife-edge decision (find_cloud_base!) activates on."""
+    idx = [var_names.index(v) for v in ("N_liq", "N_rai", "N_aer") if v in var_names]
+    a = np.asarray(a, dtype=np.float64)[:, idx].sum(axis=(1, 2))
+    b = np.asarray(b, dtype=np.float64)[:, idx].sum(axis=(1, 2))
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+def cloud_base_levels(Y, var_names, threshold=1e6):
+    """Lowest level with N_liq above `threshold` per column (-1: none)."""
+    N = np.asarray(Y)[:, var_names.index("N_liq")]
+    has = N > threshold
+    return np.where(has.any(axis=1), has.argmax(axis=1), -1)
