@@ -46,14 +46,14 @@ def _step_index(t: float, t_ini: float, dt: float) -> int:
     return int(round(n))
 
 
-def solve_gvector(case: M.Case, variables, t_calib, filter: dict | None = None, t_ini: float = 0.0, backend=Handle,
+def solve_gvector(case: M.Case, variables, t_calib, filter: dict | None = None, t_ini: float = 0.0,
                   handle=None) -> np.ndarray:
     """ODE.solve(..., saveat) + ODEsolution2Gvector for every column of `case`; returns [nc, n_out] Float64.
 
     filter["apply"] false (or filter None): the state is observed at the times t_calib (KiDUtils.jl:329-340).
     filter["apply"] true: at filter["saveat_t"], averaged over nt_per_filtered_cell snapshots and blocks of
     nz_per_filtered_cell levels (KiDUtils.jl:342-376)."""
-    h = handle or M.make_handle(case, backend)
+    h = handle or M.make_handle(case)
     dt = float(case.cfg.dt)
     if filter is not None and filter["apply"]:
         times = np.asarray(filter["saveat_t"], dtype=float)
@@ -190,7 +190,7 @@ def col_sed_calibration_case(FT, model_settings: dict, cases: list[dict], u: np.
     return M.with_parameter_sets(base, overrides, column_to_set=np.arange(nc))
 
 
-def run_ensembles(u, u_names, config: dict, n_ensemble: int | None = None, FT=np.float64, backend=Handle) -> list:
+def run_ensembles(u, u_names, config: dict, n_ensemble: int | None = None, FT=np.float64) -> list:
     """calibration/OptimizationUtils.jl:197-211 without the ReferenceStatistics transform (a host-side linear map):
     returns [G(u[:, i]) for i in 1:n_ensemble], each the concatenation over the cases (KiDUtils.jl:45-81)."""
     u = np.atleast_2d(np.asarray(u, dtype=np.float64))
@@ -211,14 +211,14 @@ def run_ensembles(u, u_names, config: dict, n_ensemble: int | None = None, FT=np
         case = col_sed_calibration_case(FT, ms, cases, u[:, :n_ensemble], list(u_names))
     else:
         case = kid_calibration_case(FT, ms, cases, u[:, :n_ensemble], list(u_names))
-    G = solve_gvector(case, variables, t_calib, filt, t_ini=float(ms.get("t_ini", 0.0)), backend=backend)
+    G = solve_gvector(case, variables, t_calib, filt, t_ini=float(ms.get("t_ini", 0.0)))
     n_cases = len(cases)
     return [G[m * n_cases:(m + 1) * n_cases].reshape(-1) for m in range(n_ensemble)]
 
 
-def run_dyn_model(u, u_names, config: dict, FT=np.float64, backend=Handle) -> np.ndarray:
+def run_dyn_model(u, u_names, config: dict, FT=np.float64) -> np.ndarray:
     """calibration/KiDUtils.jl:10-43 with RS = nothing: the G vector of one parameter vector."""
-    return run_ensembles(np.asarray(u, dtype=np.float64).reshape(-1, 1), u_names, config, 1, FT=FT, backend=backend)[0]
+    return run_ensembles(np.asarray(u, dtype=np.float64).reshape(-1, 1), u_names, config, 1, FT=FT)[0]
 
 
 # ------------------------------------------------------------------ G-vector bookkeeping and diagnostics (host, small)

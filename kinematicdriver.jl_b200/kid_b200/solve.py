@@ -64,7 +64,7 @@ def simulation_output(handle, t: float, fields=None) -> dict:
 
 
 def solve(case: M.Case, tspan=None, dt: float | None = None, saveat: float | None = None, callback=None,
-          condition=None, backend=Handle, handle=None) -> ODESolution:
+          condition=None, handle=None) -> ODESolution:
     """ODE.solve(ODEProblem(rhs!, Y, tspan, aux), SSPRK33(); dt, saveat, callback).
 
     saveat: save interval (the state at t0, every multiple of saveat and t_end is returned, as OrdinaryDiffEq does).
@@ -77,7 +77,7 @@ def solve(case: M.Case, tspan=None, dt: float | None = None, saveat: float | Non
         raise ValueError("dt differs from the dt the case was built with (it enters every limiter: TS.dt)")
     t0, t_end = tspan if tspan is not None else (0.0, TS.t_max)
     saveat = float(saveat if saveat is not None else (TS.dt_io if TS else t_end - t0))
-    h = handle or M.make_handle(case, backend)
+    h = handle or M.make_handle(case)
     sol = ODESolution(var_names=case.var_names, handle=h)
     nsteps = int(round((t_end - t0) / dt))
     save_every = max(1, int(round(saveat / dt)))
@@ -143,7 +143,7 @@ class OutputPipeline:
 
 
 # ------------------------------------------------------------------ drivers
-def run_KiD_simulation(FT, opts: dict | None = None, nc: int = 1, output: bool = False, backend=Handle):
+def run_KiD_simulation(FT, opts: dict | None = None, nc: int = 1, output: bool = False):
     """test/experiments/KiD_driver/run_KiD_simulation.jl:13-166 (minus NetCDF/plots): returns (solution, outputs)."""
     opts = dict(opts or {})
     FT = {"Float64": np.float64, "Float32": np.float32}.get(opts.pop("FLOAT_TYPE", None), FT)
@@ -152,7 +152,7 @@ def run_KiD_simulation(FT, opts: dict | None = None, nc: int = 1, output: bool =
     TS = case.meta["TS"]
     outputs = []
     cb = cond = pipe = None
-    h = M.make_handle(case, backend)
+    h = M.make_handle(case)
     if output:
         cond = OutputCadence(TS)
         if hasattr(h, "output_enqueue"):  # asynchronous, double-buffered download of the output fields
@@ -170,7 +170,7 @@ def run_KiD_simulation(FT, opts: dict | None = None, nc: int = 1, output: bool =
     return sol, outputs
 
 
-def run_box_simulation(FT, opts: dict | None = None, nc: int = 1, backend=Handle):
+def run_box_simulation(FT, opts: dict | None = None, nc: int = 1):
     """test/experiments/box_driver/run_box_simulation.jl:12-124 (minus plots)."""
     o = dict(qt=1e-3, Nd=1e8, k=2.0, rhod=1.22, precipitation_choice="Precipitation2M", rain_formation_choice="SB2006",
              dt=1.0, dt_output=30.0, t_ini=0.0, t_end=3600.0, microphys_params={})
@@ -179,10 +179,10 @@ def run_box_simulation(FT, opts: dict | None = None, nc: int = 1, backend=Handle
                       rain_formation_choice=o["rain_formation_choice"], qt=o["qt"], Nd=o["Nd"], k=o["k"], rhod=o["rhod"],
                       dt=o["dt"], dt_output=o["dt_output"], t_ini=o["t_ini"], t_end=o["t_end"],
                       microphys_params=o["microphys_params"])
-    return solve(case, (o["t_ini"], o["t_end"]), dt=o["dt"], saveat=o["dt_output"], backend=backend)
+    return solve(case, (o["t_ini"], o["t_end"]), dt=o["dt"], saveat=o["dt_output"])
 
 
-def run_KiD_col_sed_simulation(FT, opts: dict | None = None, nc: int = 1, backend=Handle):
+def run_KiD_col_sed_simulation(FT, opts: dict | None = None, nc: int = 1):
     """test/experiments/KiD_col_sed_driver/run_KiD_col_sed_simulation.jl:13-146 (minus NetCDF/plots), with the script's
     option names (qt, prescribed_Nd, k, rhod, precipitation_choice, rain_formation_choice, sedimentation_choice, z_min,
     z_max, n_elem, dt, dt_output, t_ini, t_end)."""
@@ -192,22 +192,22 @@ def run_KiD_col_sed_simulation(FT, opts: dict | None = None, nc: int = 1, backen
         raise NotImplementedError("CloudyPrecip is outside the device hot path of libkid_cuda.so and there is no CPU fallback")
     case = M.col_sed_case(FT, nc=nc, **o)
     oo = case.meta["opts"]
-    return solve(case, (oo["t_ini"], oo["t_end"]), dt=oo["dt"], saveat=oo["dt_output"], backend=backend)
+    return solve(case, (oo["t_ini"], oo["t_end"]), dt=oo["dt"], saveat=oo["dt_output"])
 
 
-def run_K2D_simulation(FT, opts: dict | None = None, backend=Handle):
+def run_K2D_simulation(FT, opts: dict | None = None):
     """test/experiments/Ki2D_driver/run_kinematic2d_simulations.jl:15-171 (single-domain, minus NetCDF/plots)."""
     o = dict(opts or {})
     case = K2.k2d_case(FT, **o)
     oo = case.meta["opts"]
-    return solve(case, (oo["t_ini"], oo["t_end"]), dt=oo["dt"], saveat=oo["dt_output"], backend=backend)
+    return solve(case, (oo["t_ini"], oo["t_end"]), dt=oo["dt"], saveat=oo["dt_output"])
 
 
 class PipelinedEnsemble:
     """A large ensemble split into column chunks, one handle (and CUDA stream) per chunk: the upload of chunk i+1 and
     the download of chunk i-1 overlap the stepping of chunk i.  Host arrays must be page-locked (pinned)."""
 
-    def __init__(self, case: M.Case, nchunks: int = 4, backend=Handle, host_column_of: np.ndarray | None = None):
+    def __init__(self, case: M.Case, nchunks: int = 4, host_column_of: np.ndarray | None = None):
         """host_column_of: column i of `case` (the device storage order, e.g. model.warp_coherent_order) is row
         host_column_of[i] of the host arrays handed to `solve` — the caller keeps its own member order, the layout kernels
         gather / scatter straight from / to the page-locked host array (kid_set_column_map)."""
@@ -220,7 +220,7 @@ class PipelinedEnsemble:
         self.ranges = [(int(a), int(b)) for a, b in zip(edges[:-1], edges[1:]) if b > a]
         self.handles = []
         for a, b in self.ranges:
-            self.handles.append(M.make_handle(M.slice_columns(case, a, b), backend))
+            self.handles.append(M.make_handle(M.slice_columns(case, a, b)))
             if self.host_column_of is not None:
                 self.handles[-1].set_column_map(self.host_column_of[a:b])
 

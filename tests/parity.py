@@ -88,3 +88,15 @@ def cloud_base_levels(Y, var_names, threshold=1e6):
     N = np.asarray(Y)[:, var_names.index("N_liq")]
     has = N > threshold
     return np.where(has.any(axis=1), has.argmax(axis=1), -1)
+
+
+def on_backend(handle_type, fn, *args, **kwargs):
+    """Run a product entry point with `handle_type` (the CPU oracle's handle class) in place of the CUDA library's handle:
+    test plumbing only — the product API has no backend switch (kid_b200.model.Handle is patched for the call)."""
+    from kid_b200 import model as M
+    saved = M.Handle
+    M.Handle = handle_type
+    try:
+        return fn(*args, **kwargs)
+    finally:
+        M.Handle = saved

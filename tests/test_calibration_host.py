@@ -3,6 +3,8 @@ driven on the CPU through the oracle backend."""
 import numpy as np
 import pytest
 
+from parity import on_backend
+
 from kid_b200 import calibration as CAL
 from kid_b200 import model as M
 from oracle import diagnostics as OD
@@ -35,7 +37,7 @@ def test_filtered_gvector_with_unit_cells_is_the_unfiltered_one():
 def test_save_times_off_the_step_grid_are_refused():
     case = M.k1d_case(np.float64, nc=1, n_elem=8, moisture_choice="NonEquilibriumMoisture", precipitation_choice="Precipitation1M", dt=2.0)
     with pytest.raises(NotImplementedError):
-        CAL.solve_gvector(case, ["qt"], [3.0], backend=OracleEnsembleHandle)
+        on_backend(OracleEnsembleHandle, CAL.solve_gvector, case, ["qt"], [3.0])
 
 
 def test_run_ensembles_on_the_oracle_backend():
@@ -48,14 +50,14 @@ def test_run_ensembles_on_the_oracle_backend():
     }
     u_names = ["rain_terminal_velocity_size_relation_coefficient_chiv", "rain_cross_section_size_relation_coefficient_chia"]
     u = np.array([[1.0, 0.6], [1.0, 2.0]])
-    G = CAL.run_ensembles(u, u_names, config, 2, backend=OracleEnsembleHandle)
+    G = on_backend(OracleEnsembleHandle, CAL.run_ensembles, u, u_names, config, 2)
     assert len(G) == 2 and G[0].shape == (2 * 2 * (6 + 4),) and np.isfinite(np.stack(G)).all()
     case = CAL.kid_calibration_case(np.float64, config["model"], config["observations"]["cases"], u, u_names)
     assert list(case.meta["col_member"]) == [0, 0, 1, 1] and list(case.meta["col_case"]) == [0, 1, 0, 1]
     assert case.params.shape[0] == 2 and case.ρ_dry.shape == (4, 12)
     assert not np.allclose(case.ρ_dry[0], case.ρ_dry[1])  # p0 enters the hydrostatic profile
     # member 0 / case 0 is the plain single-column run
-    single = CAL.run_dyn_model(u[:, 0], u_names, config, backend=OracleEnsembleHandle)
+    single = on_backend(OracleEnsembleHandle, CAL.run_dyn_model, u[:, 0], u_names, config)
     assert np.array_equal(single, G[0])
 
 
@@ -70,7 +72,7 @@ BOX_NAMES = ["SB2006_collection_kernel_coeff_kcc", "SB2006_collection_kernel_coe
 
 def test_box_calibration_ensemble_on_the_oracle_backend():
     u = np.array([[4.44e9, 6e9], [5.25, 4.0]])
-    G = CAL.run_ensembles(u, BOX_NAMES, BOX_CONFIG, 2, backend=OracleEnsembleHandle)
+    G = on_backend(OracleEnsembleHandle, CAL.run_ensembles, u, BOX_NAMES, BOX_CONFIG, 2)
     assert len(G) == 2 and G[0].shape == (2 * 3 * 4,) and np.isfinite(np.stack(G)).all()
     case = CAL.box_calibration_case(np.float64, BOX_CONFIG["model"], BOX_CONFIG["observations"]["cases"], u, BOX_NAMES)
     # every (member, case) pair has its own parameter set: the case's k is SB2006's cloud ν
@@ -78,7 +80,7 @@ def test_box_calibration_ensemble_on_the_oracle_backend():
     from kid_b200.parameters import param_names
     nu = case.params[:, param_names().index("sb_nu_c")]
     assert list(nu) == [2.0, 4.0, 2.0, 4.0]
-    single = CAL.run_dyn_model(u[:, 1], BOX_NAMES, BOX_CONFIG, backend=OracleEnsembleHandle)
+    single = on_backend(OracleEnsembleHandle, CAL.run_dyn_model, u[:, 1], BOX_NAMES, BOX_CONFIG)
     assert np.array_equal(single, G[1])
     # rain forms from cloud water: ql decreases, qr increases over the run in every member/case
     g = G[0].reshape(2, 3, 4)   # [case][time][variable]
@@ -90,8 +92,7 @@ def test_col_sed_driver_and_calibration_on_the_oracle_backend():
     calibration/KiDUtils.jl:155-236)."""
     from kid_b200.solve import run_KiD_col_sed_simulation
     from oracle.oracle import OracleHandle
-    sol = run_KiD_col_sed_simulation(np.float64, dict(n_elem=12, z_max=1200.0, t_end=120.0, dt=2.0, dt_output=60.0),
-                                     backend=OracleHandle)
+    sol = on_backend(OracleHandle, run_KiD_col_sed_simulation, np.float64, dict(n_elem=12, z_max=1200.0, t_end=120.0, dt=2.0, dt_output=60.0))
     assert sol.t == [0.0, 60.0, 120.0]
     l0, r1 = sol.variable("ρq_liq")[0, 0], sol.variable("ρq_rai")[-1, 0]
     assert np.allclose(l0, l0[0]) and l0[0] > 0              # the same gamma-distribution state at every level
@@ -103,7 +104,7 @@ def test_col_sed_driver_and_calibration_on_the_oracle_backend():
         "observations": dict(data_names=["qr", "Nr"], cases=[dict(qt=1e-3, Nd=1e8, k=2.0), dict(qt=2e-3, Nd=2e8, k=3.0)]),
     }
     u = np.array([[4.44e9, 6e9]])
-    G = CAL.run_ensembles(u, ["SB2006_collection_kernel_coeff_kcc"], config, 2, backend=OracleEnsembleHandle)
+    G = on_backend(OracleEnsembleHandle, CAL.run_ensembles, u, ["SB2006_collection_kernel_coeff_kcc"], config, 2)
     assert len(G) == 2 and G[0].shape == (2 * 3 * 2 * 12,) and np.isfinite(np.stack(G)).all()
     case = CAL.col_sed_calibration_case(np.float64, config["model"], config["observations"]["cases"], u,
                                         ["SB2006_collection_kernel_coeff_kcc"])
@@ -137,16 +138,16 @@ def test_reference_run_kid_and_gvector_shapes():
     u, u_names = np.array([1e-4]), ["cloud_liquid_water_specific_humidity_autoconversion_threshold"]
     n_elem, n_times, n_cases = 10, 5, 2
     one = dict(cfg, observations=dict(cfg["observations"], cases=cfg["observations"]["cases"][:1], data_names=["rlr", "rv"]))
-    G = CAL.run_dyn_model(u, u_names, one, backend=OracleEnsembleHandle)
+    G = on_backend(OracleEnsembleHandle, CAL.run_dyn_model, u, u_names, one)
     assert G.shape == (2 * n_elem * n_times,)                       # length(G) == sum(n_heights) * n_times
     filt = dict(apply=True, nz_unfiltered=[n_elem, n_elem], nz_per_filtered_cell=[2, 5], nt_per_filtered_cell=5)
     onef = dict(one, model=dict(one["model"], filter=filt))
-    Gf = CAL.run_dyn_model(u, u_names, onef, backend=OracleEnsembleHandle)
+    Gf = on_backend(OracleEnsembleHandle, CAL.run_dyn_model, u, u_names, onef)
     assert Gf.shape == ((5 + 2) * (n_times - 1),)                    # sum(nz_filtered) * (n_times - 1)
-    G_all = CAL.run_dyn_model(u, u_names, cfg, backend=OracleEnsembleHandle)
+    G_all = on_backend(OracleEnsembleHandle, CAL.run_dyn_model, u, u_names, cfg)
     assert G_all.shape == (n_elem * n_times * 2 * n_cases,)         # n_heights * n_times * n_vars * n_cases
     first = dict(cfg, observations=dict(cfg["observations"], cases=cfg["observations"]["cases"][:1]))
-    G_1 = CAL.run_dyn_model(u, u_names, first, backend=OracleEnsembleHandle)
+    G_1 = on_backend(OracleEnsembleHandle, CAL.run_dyn_model, u, u_names, first)
     assert np.array_equal(G_all[:G_1.size], G_1) and np.isfinite(G_all).all()
 
 

@@ -3,6 +3,8 @@ get_variable_data_from_ODE / ODEsolution2Gvector applied to downloaded states.""
 import numpy as np
 import pytest
 
+from parity import on_backend
+
 from kid_b200 import calibration as CAL
 from kid_b200 import model as M
 from kid_b200.lib import Handle, KidCudaError
@@ -161,7 +163,7 @@ def test_box_calibration_ensemble_matches_the_oracle_backend():
     from test_calibration_host import BOX_CONFIG, BOX_NAMES
     u = np.array([[4.44e9, 6e9, 3e9], [5.25, 4.0, 6.5]])
     Gd = np.stack(CAL.run_ensembles(u, BOX_NAMES, BOX_CONFIG, 3, FT=np.float64))
-    Go = np.stack(CAL.run_ensembles(u, BOX_NAMES, BOX_CONFIG, 3, FT=np.float64, backend=OracleEnsembleHandle))
+    Go = np.stack(on_backend(OracleEnsembleHandle, CAL.run_ensembles, u, BOX_NAMES, BOX_CONFIG, 3, FT=np.float64))
     g, o = Gd.reshape(3, 2, 3, 4), Go.reshape(3, 2, 3, 4)  # [member][case][time][variable]
     for v in range(4):
         assert np.abs(g[..., v] - o[..., v]).max() <= 1e-7 * np.abs(o[..., v]).max(), v
@@ -172,7 +174,7 @@ def test_col_sed_driver_and_calibration_match_the_oracle_backend():
     from oracle.oracle import OracleEnsembleHandle, OracleHandle
     opts = dict(n_elem=24, z_max=2400.0, t_end=300.0, dt=2.0, dt_output=150.0, sedimentation_choice="Chen2022")
     a = run_KiD_col_sed_simulation(np.float64, opts, nc=2)
-    b = run_KiD_col_sed_simulation(np.float64, opts, nc=2, backend=OracleHandle)
+    b = on_backend(OracleHandle, run_KiD_col_sed_simulation, np.float64, opts, nc=2)
     for ua, ub in zip(a.u, b.u):
         assert np.abs(ua - ub).max() <= 1e-7 * np.abs(ub).max()
     config = {
@@ -184,7 +186,7 @@ def test_col_sed_driver_and_calibration_match_the_oracle_backend():
     u = np.array([[4.44e9, 6e9]])
     names = ["SB2006_collection_kernel_coeff_kcc"]
     Gd = np.stack(CAL.run_ensembles(u, names, config, 2))
-    Go = np.stack(CAL.run_ensembles(u, names, config, 2, backend=OracleEnsembleHandle))
+    Go = np.stack(on_backend(OracleEnsembleHandle, CAL.run_ensembles, u, names, config, 2))
     g, o = Gd.reshape(2, 2, 3, 2, 12), Go.reshape(2, 2, 3, 2, 12)  # [member][case][time][variable][level]
     for v in range(2):
         assert np.abs(g[:, :, :, v] - o[:, :, :, v]).max() <= 1e-6 * np.abs(o[:, :, :, v]).max(), v
