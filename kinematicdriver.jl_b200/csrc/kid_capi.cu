@@ -643,8 +643,8 @@ int kid_create(const kid_config_t* cfg, kid_handle_t** out) {
     if ((cfg->model == KID_MODEL_K1D || cfg->model == KID_MODEL_K1D_COL_SED || cfg->model == KID_MODEL_K2D) && cfg->nz < 3)
         return fail("K1DModel needs at least 3 levels (Extrapolate boundary stencils)");
     if (!(cfg->dt > 0)) return fail("dt must be positive");
-    if (cfg->sedimentation == KID_SED_CHEN2022 && cfg->precip != KID_PRECIP_2M)
-        return fail("sedimentation Chen2022 is implemented for Precipitation2M (rain) only: the Chen2022 snow velocity of Precipitation1M is not on the device path");
+    if (cfg->sedimentation == KID_SED_CHEN2022 && cfg->precip != KID_PRECIP_2M && cfg->precip != KID_PRECIP_1M)
+        return fail("sedimentation Chen2022 needs Precipitation1M or Precipitation2M");
     if (cfg->precip == KID_PRECIP_1M && (cfg->rain_formation < KID_RF_CLIMA_1M || cfg->rain_formation > KID_RF_VARTIMESCALE))
         return fail("invalid rain_formation for Precipitation1M");
     if (cfg->precip == KID_PRECIP_2M && cfg->rain_formation != KID_RF_SB2006 && cfg->rain_formation != KID_RF_SB2006NL)

@@ -109,8 +109,9 @@ def get_precipitation_type(precipitation_choice: str, toml_dict=None, *, rain_fo
         if sedimentation_choice in ("CliMA_1M", None):
             st = "CliMA_1M"
         elif sedimentation_choice == "Chen2022":
-            raise NotImplementedError("sedimentation_choice=Chen2022 with Precipitation1M (Chen2022 snow velocity) is not "
-                                      "implemented on the device path; it is available with Precipitation2M")
+            # CMP.Chen2022VelType (helper_functions.jl:36-37): rain by Chen et al. (2022) Table B1; the snow / ice tables
+            # are not part of the parameter table — snow, where present, gets a NaN velocity (the run fails loudly)
+            st = "Chen2022"
         else:
             raise ValueError(f"Invalid sedimentation choice: {sedimentation_choice}")
         rf = "CliMA_1M" if rain_formation_choice is None else rain_formation_choice

@@ -158,7 +158,7 @@ struct Model {
     // src/Common/tendency.jl:179-210
     void precompute_aux_precip(const FT* Yc, ColAux<FT>& a) {
         if (sw.precip == KID_PRECIP_1M) {
-            CM1<FT> cm1(P);
+            CM1<FT> cm1(P, sw.sedimentation == KID_SED_CHEN2022);
             for (int k = 0; k < nz; ++k) a.q_rai[k] = q_(var(Yc, L.rai)[k], a.rho[k]);
             for (int k = 0; k < nz; ++k) a.q_sno[k] = q_(var(Yc, L.sno)[k], a.rho[k]);
             for (int k = 0; k < nz; ++k) a.vt_rai[k] = cm1.terminal_velocity(cm1.rain(), a.rho[k], a.q_rai[k]);
@@ -257,7 +257,7 @@ struct Model {
     // src/Common/tendency.jl:405-580
     void precompute_aux_precip_sources_1m(ColAux<FT>& a) {
         Thermo<FT> td(P);
-        CM1<FT> cm1(P);
+        CM1<FT> cm1(P, sw.sedimentation == KID_SED_CHEN2022);
         const FT T_fr = P.td_T_freeze;
         const FT c_vl = P.td_cp_l;  // TD.Parameters.cv_l == cp_l
         const int rf = sw.rain_formation;

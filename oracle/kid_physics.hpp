@@ -263,7 +263,8 @@ template <class FT>
 struct CM1 {
     const Prm<FT>& P;
     Thermo<FT> td;
-    explicit CM1(const Prm<FT>& p) : P(p), td(p) {}
+    bool chen2022 = false;  // sedimentation_choice = "Chen2022": CMP.Chen2022VelType (helper_functions.jl:36-37)
+    explicit CM1(const Prm<FT>& p, bool chen = false) : P(p), td(p), chen2022(chen) {}
     Species1M<FT> rain() const {
         return {P.rain_r0, P.rain_m0, P.rain_me, P.rain_dm, P.rain_chim, P.rain_a0, P.rain_ae, P.rain_da,
                 P.rain_chia, P.rain_a_vent, P.rain_b_vent, P.rain_chiv, P.rain_ve, P.rain_dv, false};
@@ -298,12 +299,37 @@ struct CM1 {
     }
     // CM1.terminal_velocity(precip, vel, ρ, q) (Common/tendency.jl:191-192)
     FT terminal_velocity(const Species1M<FT>& s, FT rho, FT q) const {
+        if (chen2022) return s.is_snow ? terminal_velocity_chen2022_snow(q) : terminal_velocity_chen2022_rain(rho, q);
         if (q > FT(0)) {
             FT li = lambda_inverse(s, q, rho);
             return s.chiv * v0(s, rho) * kidm::pow(li / s.r0, s.ve + s.dv) *
                    sf_gamma(s.me + s.ve + s.dm + s.dv + FT(1)) / sf_gamma(s.me + s.dm + FT(1));
         }
         return FT(0);
+    }
+    // CM1.terminal_velocity(rain, vel::Chen2022VelTypeRain, ρ, q): Chen et al. (2022) eq. 20, mass-weighted (k = 3), over the
+    // 1-moment Marshall-Palmer distribution: Σ_i a_i λ^4 Γ(b_i+4) / (λ+c_i)^(b_i+4) / Γ(4) with λ = 1/lambda_inverse(rain) and
+    // the Table B1 coefficients as in rain_terminal_velocity_chen2022 below (the fit is applied to the distribution's own
+    // size variable, as the upstream call does).
+    FT terminal_velocity_chen2022_rain(FT rho, FT q) const {
+        if (!(q > FT(0))) return FT(0);
+        FT lam = FT(1) / lambda_inverse(rain(), q, rho);
+        FT qf = kidm::exp(P.ch_rho0 * rho);
+        FT ai[3] = {P.ch_a1 * qf, P.ch_a2 * qf, P.ch_a3 * qf * kidm::pow(rho, P.ch_a3_pow)};
+        FT bi[3] = {P.ch_b1 - P.ch_b_rho * rho, P.ch_b2 - P.ch_b_rho * rho, P.ch_b3 - P.ch_b_rho * rho};
+        FT ci[3] = {P.ch_c1 * FT(1000), P.ch_c2 * FT(1000), P.ch_c3 * FT(1000)};
+        FT s3 = FT(0);
+        for (int i = 0; i < 3; ++i) {
+            FT aiu = ai[i] * kidm::pow(FT(1000), bi[i]);
+            s3 = s3 + aiu * kidm::pow(lam, FT(4)) * FT(std::tgamma(double(bi[i] + FT(4)))) / kidm::pow(lam + ci[i], bi[i] + FT(4)) / FT(6);
+        }
+        return kidm::max(FT(0), s3);
+    }
+    // Chen2022VelTypeSnowIce needs the Table B2-B4 constants of Chen et al. (2022), which cannot be reproduced here (the
+    // parameter table does not carry them): where snow is present the velocity is NaN, so a cold run fails loudly instead
+    // of sedimenting snow with another law; without snow (q_sno = 0) CM1.terminal_velocity is 0 for every scheme.
+    FT terminal_velocity_chen2022_snow(FT q) const {
+        return (q > FT(0)) ? FT(std::numeric_limits<double>::quiet_NaN()) : FT(0);
     }
     // CM1.conv_q_lcl_to_q_rai(acnv1M, q_liq, smooth_transition = true) (Common/tendency.jl:430)
     FT conv_q_lcl_to_q_rai(FT q_liq) const {

@@ -320,7 +320,7 @@ def test_error_behaviour():
     with pytest.raises(lib.KidCudaError, match="at least 3 levels"):
         Handle(bad.cfg)
     bad.cfg.nz = 8
-    bad.cfg.sedimentation = 2
+    bad.cfg.precip, bad.cfg.sedimentation = 1, 2   # Chen2022 sedimentation without a precipitating species (0M)
     with pytest.raises(lib.KidCudaError, match="Chen2022"):
         Handle(bad.cfg)
     with pytest.raises(lib.KidCudaError, match="KID_NPARAMS"):
@@ -485,6 +485,28 @@ def test_chen2022_rain_sedimentation_parity(FT):
     e = errors(g2.get_state(), o2.get_state(), cs.var_names)
     tol = 1e-6 if FT is np.float64 else 5e-2
     assert max(e.values()) < tol, e
+
+
+@pytest.mark.parametrize("FT", [np.float64, np.float32])
+def test_chen2022_sedimentation_with_precipitation1m(FT):
+    """sedimentation_choice = "Chen2022" with Precipitation1M (CMP.Chen2022VelType, helper_functions.jl:36-37): the rain
+    velocity is Chen et al. (2022) eq. 20 over the Marshall-Palmer distribution; warm columns carry no snow."""
+    kw = dict(nc=8, n_profiles=2, n_elem=32, moisture_choice="NonEquilibriumMoisture", precipitation_choice="Precipitation1M")
+    cs = M.k1d_ensemble_case(FT, sedimentation_scheme_choice="Chen2022", **kw)
+    g, o = M.make_handle(cs, Handle), M.make_handle(cs, OracleHandle)
+    g.step(0.0, 900)
+    o.set_state(g.get_state())
+    a, b = g.get_aux(900.0, "term_vel_rai"), o.get_aux(900.0, "term_vel_rai")
+    assert b.max() > 0.5 and np.abs(a - b).max() <= (1e-9 if FT is np.float64 else 2e-4) * b.max()
+    blk = M.make_handle(M.k1d_ensemble_case(FT, **kw), Handle)
+    blk.set_state(g.get_state())
+    assert np.abs(blk.get_aux(900.0, "term_vel_rai") - a).max() > 0.05   # not the Blk1M law
+    g2, o2 = M.make_handle(cs, Handle), M.make_handle(cs, OracleHandle)
+    g2.step(0.0, 300)
+    o2.step(0.0, 300)
+    e = errors(g2.get_state(), o2.get_state(), cs.var_names)
+    assert np.isfinite(g2.get_state()).all()
+    assert max(e.values()) < (1e-6 if FT is np.float64 else 5e-3), e
 
 
 def test_checkpoint_restart_is_bitwise():

@@ -151,8 +151,9 @@ def test_morton_order_keeps_neighbours_close_in_every_key():
     assert max(spread_lex(b), spread_lex(c)) > 0.8          # a lexicographic sort only helps the first key
 
 
-def test_chen2022_is_a_2m_sedimentation_choice_only():
-    p = ET.get_precipitation_type("Precipitation2M", PR.override_toml_dict(), sedimentation_choice="Chen2022")
-    assert p.sedimentation == 2 and p.sedimentation_name == "Chen2022"
-    with pytest.raises(NotImplementedError):
-        ET.get_precipitation_type("Precipitation1M", PR.override_toml_dict(), sedimentation_choice="Chen2022")
+def test_chen2022_sedimentation_choice():
+    for ps in ("Precipitation2M", "Precipitation1M"):
+        p = ET.get_precipitation_type(ps, PR.override_toml_dict(), sedimentation_choice="Chen2022")
+        assert p.sedimentation == 2 and p.sedimentation_name == "Chen2022"
+    with pytest.raises(ValueError):
+        ET.get_precipitation_type("Precipitation1M", PR.override_toml_dict(), sedimentation_choice="SB2006")

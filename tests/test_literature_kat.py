@@ -85,6 +85,36 @@ def test_sb2006_bulk_fall_speeds_are_size_distribution_averages(rhoq_rai, N_rai)
     assert got_q > got_N > 0
 
 
+def test_chen2022_bulk_rain_velocity_of_the_1m_scheme_is_the_marshall_palmer_average():
+    """CM1.terminal_velocity(rain, Chen2022VelTypeRain, ρ, q): mass-weighted mean of the Table B1 single-drop law over
+    n(x) ~ exp(-λ x), λ = 1/lambda_inverse(rain) (the fit is applied to the distribution's own size variable x)."""
+    rho, q_rai = 1.1, 1e-3
+    ip = dict(ρ=rho, ρ_dry=rho * (1 - 12e-3), T=288.0, ρq_tot=12e-3 * rho, ρq_liq=5e-4 * rho, ρq_ice=0.0, ρq_rai=q_rai * rho, ρq_sno=0.0)
+    cs = M.custom_case(np.float64, MODEL_BOX, "NonEquilibriumMoisture", "Precipitation1M", ip, sedimentation_choice="Chen2022")
+    td = cs.meta["toml"]
+    g = lambda k: td["Chen2022_table_B1_" + k + "_coeff"]  # noqa: E731
+    qf = math.exp(g("q") * rho)
+    a = [g("a1") * qf, g("a2") * qf, g("a3") * qf * rho ** g("a3_pow")]
+    b = [g(k) - g("b_rho") * rho for k in ("b1", "b2", "b3")]
+    c = [g("c1") * 1e3, g("c2") * 1e3, g("c3") * 1e3]
+    a = [ai * 1e3 ** bi for ai, bi in zip(a, b)]  # mm -> m
+    # Marshall-Palmer λ of the 1-moment scheme: ρ q = χm m0 n0 Γ(me+Δm+1) λ^-(me+Δm+1) / r0^(me+Δm)
+    r0, m0 = td["rain_drop_radius"] if "rain_drop_radius" in td else 1e-3, None
+    h = M.make_handle(cs, OracleHandle)
+    v_code = h.get_aux(0.0, "term_vel_rai")[0, 0]
+    # λ from the Blk1M law of the same distribution: v_blk = χv v0 (λ r0)^-(ve+Δv) Γ(me+ve+Δm+Δv+1)/Γ(me+Δm+1)
+    blk = M.make_handle(M.custom_case(np.float64, MODEL_BOX, "NonEquilibriumMoisture", "Precipitation1M", ip), OracleHandle)
+    v_blk = blk.get_aux(0.0, "term_vel_rai")[0, 0]
+    me, ve, r0 = 3.0, 0.5, 1e-3
+    v0 = math.sqrt(8.0 / 3.0 / 0.55 * (1000.0 / rho - 1.0) * td["gravitational_acceleration"] * r0)
+    lam = (v0 * special.gamma(me + ve + 1) / special.gamma(me + 1) / v_blk) ** (1.0 / ve) / r0
+    v = lambda x: sum(ai * x ** bi * math.exp(-ci * x) for ai, bi, ci in zip(a, b, c))  # noqa: E731
+    num = integrate.quad(lambda x: v(x) * x ** 3 * math.exp(-lam * x), 0, 60 / lam, epsabs=0, epsrel=1e-11, limit=400)[0]
+    den = integrate.quad(lambda x: x ** 3 * math.exp(-lam * x), 0, 60 / lam, epsabs=0, epsrel=1e-11, limit=400)[0]
+    assert v_code == pytest.approx(num / den, rel=1e-6)
+    assert 1.0 < v_code < 10.0
+
+
 def test_sb2006_autoconversion_at_a_hand_evaluated_point():
     """SB2006 eq. 4: dL_r/dt = k_cc/(20 x*) (ν+2)(ν+4)/(ν+1)^2 L_c^2 x_c^2 [1 + Φ_au(τ)/(1-τ)^2] ρ0/ρ with k_cc = 4.44e9,
     x* = 2.6e-10 kg, ν = 2: at L_c = 1 g/m3, N_c = 100 cm^-3, no rain (τ = 0, Φ_au = 0), ρ = ρ0:
