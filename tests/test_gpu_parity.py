@@ -490,7 +490,8 @@ def test_chen2022_rain_sedimentation_parity(FT):
 @pytest.mark.parametrize("FT", [np.float64, np.float32])
 def test_chen2022_sedimentation_with_precipitation1m(FT):
     """sedimentation_choice = "Chen2022" with Precipitation1M (CMP.Chen2022VelType, helper_functions.jl:36-37): the rain
-    velocity is Chen et al. (2022) eq. 20 over the Marshall-Palmer distribution; warm columns carry no snow."""
+    velocity is Chen et al. (2022) eq. 20 over the Marshall-Palmer distribution (snow keeps the Blk1M law; warm columns
+    carry none)."""
     kw = dict(nc=8, n_profiles=2, n_elem=32, moisture_choice="NonEquilibriumMoisture", precipitation_choice="Precipitation1M")
     cs = M.k1d_ensemble_case(FT, sedimentation_scheme_choice="Chen2022", **kw)
     g, o = M.make_handle(cs, Handle), M.make_handle(cs, OracleHandle)
