@@ -85,6 +85,7 @@ enum kid_obs_var {
     KID_OBS_QT = 0, KID_OBS_QL, KID_OBS_QR, KID_OBS_QV, KID_OBS_QLR,
     KID_OBS_RT, KID_OBS_RL, KID_OBS_RR, KID_OBS_RV, KID_OBS_RLR,
     KID_OBS_NL, KID_OBS_NR, KID_OBS_NA, KID_OBS_RHO, KID_OBS_RAIN_VT, KID_OBS_RAINRATE,
+    KID_OBS_Z_TOP, /* radar reflectivity of the rain below cloud top: ONE value per column (Precipitation1M only) */
     KID_NOBS
 };
 #define KID_MAX_OBS_VARS 16
@@ -175,6 +176,13 @@ int kid_set_column_map(kid_handle_t* h, const int32_t* host_column_of);
  * solve.  Needs kid_set_params (and kid_set_column_scalar(PRESCRIBED_ND) if members differ in Nd) first; afterwards
  * the handle is ready to step (profiles, q_surf and state are set).  K1DModel handles only. */
 int kid_init_shipway_hill(kid_handle_t* h, const double* sounding, const void* p0, int32_t dry);
+/* replaces: initial_condition_0d + initialise_state for BoxModel and the col_sed column (src/Common/initial_condition.jl:
+ * 237-308; run_box_simulation.jl:60-76, run_KiD_col_sed_simulation.jl:80-103): the gamma-distribution state (liquid / rain
+ * split at a 40 um radius) of every column from its total water qt, number Nd, shape k and dry density, built on the device
+ * (T = 300 K, every level alike) — calibration ensembles with per-case (qt, Nd, k) need no host loop over members.
+ * Each array: nc values of FLOAT_TYPE. */
+int kid_init_gamma_0d(kid_handle_t* h, const void* qt, const void* Nd, const void* k, const void* rho_dry);
+
 /* download the time-invariant profiles (the layout kid_set_profiles takes: nc x nz, or nz if one profile is shared) */
 int kid_get_profiles(kid_handle_t* h, void* rho_dry, void* T);
 

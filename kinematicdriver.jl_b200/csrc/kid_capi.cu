@@ -564,6 +564,7 @@ int obs_launch(kid_handle_t* h, int time_cell) {
     for (int j = 0; j < h->obs_nvars; ++j) { a.var_id[j] = h->obs_var[j]; a.nz_per_cell[j] = h->obs_per[j]; a.out_offset[j] = h->obs_off[j]; }
     a.out_offset[h->obs_nvars] = h->obs_off[h->obs_nvars];
     a.weight = 1.0 / double(h->obs_nt_per);
+    a.z_span = h->cfg.z_max - h->cfg.z_min;
     a.sw = h->sw;
     cudaError_t e;
     if constexpr (sizeof(FT) == 8) e = h->lt->obs_d(h->cfg.moisture, a, h->prm_d, h->stream);
@@ -1048,6 +1049,67 @@ int kid_init_shipway_hill(kid_handle_t* h, const double* sounding, const void* p
     return 0;
 }
 
+int kid_init_gamma_0d(kid_handle_t* h, const void* qt, const void* Nd, const void* k, const void* rho_dry) {
+    KID_ON_DEVICE(h);
+    if (!h || !qt || !Nd || !k || !rho_dry) return fail("null argument");
+    if (!h->params_set) return fail("kid_set_params must be called before kid_init_gamma_0d");
+    if (h->cfg.model != KID_MODEL_BOX && h->cfg.model != KID_MODEL_K1D_COL_SED)
+        return fail("kid_init_gamma_0d: BoxModel / K1D col_sed handles only");
+    if (h->cfg.moisture != KID_MOIST_NONEQ) return fail("kid_init_gamma_0d: the box initial condition has ρq_liq (NonEquilibriumMoisture)");
+    const int nz = h->cfg.nz, nc = h->cfg.nc;
+    const size_t n = size_t(nz) * h->ncp, colb = size_t(h->ncp) * h->fsz;
+    void* in[4] = {nullptr, nullptr, nullptr, nullptr};
+    struct FreeAll { void** p; ~FreeAll() { for (int i = 0; i < 4; ++i) if (p[i]) cudaFree(p[i]); } } owner{in};
+    const void* src[4] = {qt, Nd, k, rho_dry};
+    for (int i = 0; i < 4; ++i) {
+        KID_CUDA(cudaMalloc(&in[i], colb));
+        if (upload_columns(h, in[i], src[i], 0.0)) return 1;
+    }
+    h->profiles_set = false;
+    h->state_set = false;
+    for (void** p : {&h->rho_dry, &h->T, &h->ps_liq, &h->ps_mix}) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+        KID_CUDA(cudaMalloc(p, n * h->fsz));
+        KID_CUDA(cudaMemsetAsync(*p, 0, n * h->fsz, h->stream));
+    }
+    h->prof_per_column = 1;
+    h->consts_dirty = true;
+    KID_CUDA(cudaMemsetAsync(h->Y, 0, state_elems(h) * h->fsz, h->stream));
+    int idx = 1, i_liq = idx++, i_ice = idx++;
+    (void)i_ice;
+    int i_rai = -1, i_Nl = -1, i_Nr = -1;
+    if (h->cfg.precip >= KID_PRECIP_1M) { i_rai = idx; idx += 2; }
+    if (h->cfg.precip == KID_PRECIP_2M) { i_Nl = idx++; i_Nr = idx++; }
+    auto fill = [&](auto& a) {
+        a.nz = nz; a.nc = nc; a.ncp = h->ncp;
+        a.i_tot = 0; a.i_liq = i_liq; a.i_rai = i_rai; a.i_Nl = i_Nl; a.i_Nr = i_Nr;
+    };
+    if (h->f64) {
+        IC0dArgs<double> a{}; fill(a);
+        a.qt = (const double*)in[0]; a.Nd = (const double*)in[1]; a.k = (const double*)in[2]; a.rho_dry = (const double*)in[3];
+        a.rho_dry_out = (double*)h->rho_dry; a.T_out = (double*)h->T; a.Y = (double*)h->Y;
+        init_gamma_0d_kernel<double><<<(nc + 63) / 64, 64, 0, h->stream>>>(a);
+    } else {
+        IC0dArgs<float> a{}; fill(a);
+        a.qt = (const float*)in[0]; a.Nd = (const float*)in[1]; a.k = (const float*)in[2]; a.rho_dry = (const float*)in[3];
+        a.rho_dry_out = (float*)h->rho_dry; a.T_out = (float*)h->T; a.Y = (float*)h->Y;
+        init_gamma_0d_kernel<float><<<(nc + 63) / 64, 64, 0, h->stream>>>(a);
+    }
+    KID_CUDA(cudaGetLastError());
+    h->launches++;
+    const int na = na_index(h->cfg.moisture, h->cfg.precip);
+    if (na >= 0) {  // aux N_aer snapshot (= 0), as in kid_set_state
+        const size_t plane = n * h->fsz;
+        if (!h->aux_Naer) KID_CUDA(cudaMalloc(&h->aux_Naer, plane));
+        KID_CUDA(cudaMemcpyAsync(h->aux_Naer, (const char*)h->Y + size_t(na) * plane, plane, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    KID_CUDA(cudaStreamSynchronize(h->stream));
+    h->profiles_set = true;
+    h->state_set = true;
+    return 0;
+}
+
 int kid_get_profiles(kid_handle_t* h, void* rho_dry, void* T) {
     KID_ON_DEVICE(h);
     if (!h || !rho_dry || !T) return fail("null argument");
@@ -1103,7 +1165,7 @@ int kid_obs_configure(kid_handle_t* h, int32_t nvars, const int32_t* var_ids, co
     KID_ON_DEVICE(h);
     if (!h || !var_ids) return fail("null argument");
     if (h->cfg.model == KID_MODEL_K2D) return fail("kid_obs_*: K1D / Box handles only");
-    if (nvars < 1 || nvars > KID_MAX_OBS) return fail("kid_obs_configure: 1..16 observables");
+    if (nvars < 1 || nvars > KID_MAX_OBS) return fail("kid_obs_configure: 1..17 observables");
     if (nt_filtered < 1 || nt_per_filtered_cell < 1) return fail("kid_obs_configure: nt_filtered, nt_per_filtered_cell >= 1");
     const int nz = h->cfg.nz;
     const bool neq = h->cfg.moisture == KID_MOIST_NONEQ;
@@ -1121,10 +1183,12 @@ int kid_obs_configure(kid_handle_t* h, int32_t nvars, const int32_t* var_ids, co
         if (needs_liq && !neq) return fail("observable needs ρq_liq: NonEquilibriumMoisture only");
         if (needs_rai && !has_pr) return fail("observable needs ρq_rai: Precipitation1M / Precipitation2M only");
         if (needs_N && !is2m) return fail("observable needs N_liq/N_rai/N_aer: Precipitation2M only");
+        if (v == KID_OBS_Z_TOP && !(neq && h->cfg.precip == KID_PRECIP_1M))
+            return fail("Computing radar reflectivity for the given precipitation style is invalid!! (Z_top: NonEquilibriumMoisture + Precipitation1M)");
         h->obs_var[j] = v;
-        h->obs_per[j] = per;
+        h->obs_per[j] = v == KID_OBS_Z_TOP ? nz : per;  // Z_top: one value per column
         h->obs_off[j] = off;
-        off += nz / per;
+        off += v == KID_OBS_Z_TOP ? 1 : nz / per;
     }
     h->obs_off[nvars] = off;
     h->obs_nvars = nvars;

@@ -10,7 +10,7 @@
 
 namespace kid {
 
-constexpr int KID_MAX_OBS = 16;
+constexpr int KID_MAX_OBS = 17;
 
 template <class FT>
 struct ObsArgs {
@@ -25,6 +25,7 @@ struct ObsArgs {
     int nz_per_cell[KID_MAX_OBS]; // levels averaged into one filtered cell
     int out_offset[KID_MAX_OBS + 1];  // prefix sum of nz / nz_per_cell over the variables
     double weight;                // 1 / nt_per_filtered_cell
+    double z_span;                // z_max - z_min (Z_top: the 500 m averaging depth in levels)
     DevSwitches sw;
 };
 
@@ -73,6 +74,46 @@ KID_DEV FT obs_value(const PRM& P, const DevSwitches& sw, int var, const FT* y, 
     return FT(0);
 }
 
+// "Z_top" of get_variable_data_from_ODE (src/Common/helper_functions.jl:164-185): cloud top = highest level with
+// q_liq + q_rai >= 1e-3 (level 1 if none), q_rai and ρ averaged over the `steps` levels below it — steps =
+// round(500 m / dz) with dz = (z_max - z_min) / (nz + 1), the reference divides by the number of FACES — then
+// CMD.radar_reflectivity_1M(rain, q_rai, ρ) = 10 log10(720 n0 λ⁻⁷ / 1e-18 m³) of the Marshall-Palmer distribution, with the
+// reference's replacements -Inf -> -300, Inf -> 300, NaN -> 0.
+template <class FT, int MOIST, int PRECIP, class PRM>
+KID_DEV double obs_z_top(const PRM& P, const ObsArgs<FT>& A, int c) {
+    using L = Lay<MOIST, PRECIP>;
+    if constexpr (L::neq && PRECIP == KID_PRECIP_1M) {
+        const size_t plane = size_t(A.nz) * A.ncp;
+        auto rho_at = [&](int k) { return A.rho_dry[A.prof_per_column ? size_t(k) * A.ncp + c : size_t(k)] + A.Y[L::tot * plane + size_t(k) * A.ncp + c]; };
+        int z_top = A.nz - 1;  // 0-based
+        while (z_top > 0) {
+            const FT rho = rho_at(z_top);
+            const FT qlr = A.Y[L::liq * plane + size_t(z_top) * A.ncp + c] / rho + A.Y[L::rai * plane + size_t(z_top) * A.ncp + c] / rho;
+            if (!(qlr < FT(1e-3))) break;
+            --z_top;
+        }
+        const double dz = A.z_span / double(A.nz + 1);
+        const int steps = int(rint(500.0 / dz));
+        const int lo = max(z_top - steps + 1, 0);
+        FT qr = FT(0), rho_m = FT(0);
+        for (int k = lo; k <= z_top; ++k) {
+            const FT rho = rho_at(k);
+            qr += A.Y[L::rai * plane + size_t(k) * A.ncp + c] / rho;
+            rho_m += rho;
+        }
+        qr /= FT(z_top - lo + 1);
+        rho_m /= FT(z_top - lo + 1);
+        CM1<FT, PRM> cm1(P);
+        const double li = double(cm1.lambda_inverse(P.rain_n0, P.rain_r0_pow, P.rain_m0, P.rain_li_exp, P.rain_chim, P.rain_gam_m, qr, rho_m));
+        double Z = 10.0 * (log10(720.0 * double(P.rain_n0)) + 7.0 * log10(li) + 18.0);
+        if (Z != Z) Z = 0.0;
+        else if (Z == -INFINITY) Z = -300.0;
+        else if (Z == INFINITY) Z = 300.0;
+        return Z;
+    }
+    return 0.0;
+}
+
 // one thread per (column, filtered output cell): mean over the cell's levels, added to the time cell with weight
 // 1 / nt_per_filtered_cell (the Float64 accumulation of ODEsolution2Gvector)
 template <class FT, int MOIST, int PRECIP>
@@ -86,6 +127,10 @@ __global__ void obs_accumulate_kernel(const ObsArgs<FT> A, const __grid_constant
     const int cell = o - A.out_offset[j], per = A.nz_per_cell[j];
     const DevParams<FT>& P = A.prm_sets ? A.prm_sets[A.col_to_set[c]] : Pshared;
     const size_t plane = size_t(A.nz) * A.ncp;
+    if (A.var_id[j] == KID_OBS_Z_TOP) {  // one value per column
+        A.G[(size_t(c) * A.nt_filtered + A.time_cell) * A.n_out + o] += obs_z_top<FT, MOIST, PRECIP>(P, A, c) * A.weight;
+        return;
+    }
     double sum = 0.0;
     for (int l = 0; l < per; ++l) {
         const int k = cell * per + l;

@@ -127,4 +127,74 @@ __global__ void init_shipway_hill_kernel(const ICArgs<FT> A) {
     }
 }
 
+// ------------------------------------------------------------------ initial_condition_0d (Box, col_sed)
+// Regularised upper incomplete gamma function Q(a, x), a > 0, x >= 0 (series for x < a + 1, continued fraction otherwise),
+// in double: SpecialFunctions.gamma_inc(a, x)[2] of src/Common/initial_condition.jl:257,275.
+__device__ inline double gamma_inc_Q(double a, double x) {
+    if (!(x > 0.0)) return 1.0;
+    const double gln = lgamma(a);
+    if (x < a + 1.0) {
+        double ap = a, del = 1.0 / a, sum = del;
+        for (int n = 0; n < 2000; ++n) {
+            ap += 1.0;
+            del *= x / ap;
+            sum += del;
+            if (fabs(del) < fabs(sum) * 1e-17) break;
+        }
+        return 1.0 - sum * exp(-x + a * log(x) - gln);
+    }
+    double b = x + 1.0 - a, c = 1e300, d = 1.0 / b, h = d;
+    for (int i = 1; i < 2000; ++i) {
+        const double an = -double(i) * (double(i) - a);
+        b += 2.0;
+        d = an * d + b;
+        if (fabs(d) < 1e-300) d = 1e-300;
+        c = b + an / c;
+        if (fabs(c) < 1e-300) c = 1e-300;
+        d = 1.0 / d;
+        const double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < 1e-17) break;
+    }
+    return exp(-x + a * log(x) - gln) * h;
+}
+
+template <class FT>
+struct IC0dArgs {
+    const FT *qt, *Nd, *k, *rho_dry;  // [ncp] per column: total water (cloud + rain), number, gamma shape, dry density
+    FT* rho_dry_out;                  // [nz][ncp]
+    FT* T_out;                        // [nz][ncp]
+    FT* Y;                            // [nv][nz][ncp] (zero-filled by the caller)
+    int nz, nc, ncp;
+    int i_tot, i_liq, i_rai, i_Nl, i_Nr;  // state indices (-1: absent)
+};
+// initial_condition_0d (src/Common/initial_condition.jl:237-308): the box model's gamma-distribution state — liquid and
+// rain split at a fixed 40 um radius — per column, copied to every level (run_KiD_col_sed_simulation.jl:80-103).
+// The arithmetic follows the reference's FT roundings; the incomplete gamma function is evaluated in double.
+template <class FT>
+__global__ void init_gamma_0d_kernel(const IC0dArgs<FT> A) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= A.nc) return;
+    const FT qt = A.qt[c], Nd = A.Nd[c], k = A.k[c], rho_dry = A.rho_dry[c];
+    const FT Lt = rho_dry * qt / (FT(1) - qt);
+    const FT rhow = FT(1000), radius_th = FT(40 * 1e-6);
+    const FT thr = FT(4.0 / 3.0) * FT(M_PI) * (radius_th * radius_th * radius_th) * rhow / (Lt / Nd / k);
+    // gamma_inc(thrshld, k + 1)[2]: a = thrshld, x = k + 1, as the reference writes it
+    const FT mass_ratio = FT(gamma_inc_Q(double(thr), double(k) + 1.0));
+    const FT rq_liq = mass_ratio * Lt, rq_rai = Lt - rq_liq;
+    const FT num_ratio = FT(gamma_inc_Q(double(thr), double(k)));
+    const FT N_liq = num_ratio * Nd, N_rai = Nd - N_liq;
+    const size_t plane = size_t(A.nz) * A.ncp;
+    for (int l = 0; l < A.nz; ++l) {
+        const size_t pi = size_t(l) * A.ncp + c;
+        A.rho_dry_out[pi] = rho_dry;
+        A.T_out[pi] = FT(300);
+        A.Y[size_t(A.i_tot) * plane + pi] = Lt;
+        if (A.i_liq >= 0) A.Y[size_t(A.i_liq) * plane + pi] = rq_liq;
+        if (A.i_rai >= 0) A.Y[size_t(A.i_rai) * plane + pi] = rq_rai;
+        if (A.i_Nl >= 0) A.Y[size_t(A.i_Nl) * plane + pi] = N_liq;
+        if (A.i_Nr >= 0) A.Y[size_t(A.i_Nr) * plane + pi] = N_rai;
+    }
+}
+
 }  // namespace kid

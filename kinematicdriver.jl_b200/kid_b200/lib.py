@@ -33,7 +33,7 @@ AUX_FIELDS = [
 AUX_ID = {n: i for i, n in enumerate(AUX_FIELDS)}
 # enum kid_obs_var: the names get_variable_data_from_ODE accepts (src/Common/helper_functions.jl:98-191)
 OBS_VARS = ["qt", "ql", "qr", "qv", "qlr", "rt", "rl", "rr", "rv", "rlr", "Nl", "Nr", "Na", "rho",
-            "rain averaged terminal velocity", "rainrate"]
+            "rain averaged terminal velocity", "rainrate", "Z_top"]
 OBS_ID = {n: i for i, n in enumerate(OBS_VARS)}
 
 
@@ -100,6 +100,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         "kid_get_state_async": (C.c_int, [H, C.c_void_p]),
         "kid_init_shipway_hill": (C.c_int, [H, C.POINTER(C.c_double), C.c_void_p, C.c_int32]),
         "kid_get_profiles": (C.c_int, [H, C.c_void_p, C.c_void_p]),
+        "kid_init_gamma_0d": (C.c_int, [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
         "kid_step": (C.c_int, [H, C.c_double, C.c_int32]),
         "kid_set_steps_per_launch": (C.c_int, [H, C.c_int32]),
         "kid_rhs": (C.c_int, [H, C.c_double, C.c_void_p]),
@@ -271,6 +272,12 @@ class Handle:
             p = np.ascontiguousarray(np.broadcast_to(np.asarray(p0, dtype=self.dtype), (self.cfg.nc,)))
         self._check(self.lib.kid_init_shipway_hill(self._h, snd.ctypes.data_as(C.POINTER(C.c_double)),
                                                    None if p is None else _ptr(p), int(dry)))
+        self._profiles_per_column = True
+
+    def init_gamma_0d(self, qt, Nd, k, rho_dry):
+        """Box / col_sed initial condition built on the device (initial_condition_0d per column; scalars broadcast)."""
+        arrs = [np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=self.dtype), (self.cfg.nc,))) for x in (qt, Nd, k, rho_dry)]
+        self._check(self.lib.kid_init_gamma_0d(self._h, *[_ptr(a) for a in arrs]))
         self._profiles_per_column = True
 
     def get_profiles(self):

@@ -149,8 +149,9 @@ def k1d_case(FT=np.float64, nc: int = 1, model: int = MODEL_K1D, device: int = 0
 
 def box_case(FT=np.float64, nc: int = 1, device: int = 0, precipitation_choice="Precipitation2M",
              rain_formation_choice="SB2006", qt=1e-3, Nd=1e8, k=2.0, rhod=1.22, dt=1.0, dt_output=30.0,
-             t_ini=0.0, t_end=3600.0, microphys_params=None, precip_sinks=0) -> Case:
-    """run_box_simulation.jl:12-81 for nc boxes.  qt, Nd may be arrays of length nc (ensemble)."""
+             t_ini=0.0, t_end=3600.0, microphys_params=None, precip_sinks=0, ic: str = "host") -> Case:
+    """run_box_simulation.jl:12-81 for nc boxes.  qt, Nd may be arrays of length nc (ensemble).
+    ic="device": initial_condition_0d of every box is evaluated on the device (kid_init_gamma_0d)."""
     FT = np.dtype(FT).type
     qt_a = np.broadcast_to(np.asarray(qt, dtype=np.float64), (nc,))
     Nd_a = np.broadcast_to(np.asarray(Nd, dtype=np.float64), (nc,))
@@ -164,17 +165,21 @@ def box_case(FT=np.float64, nc: int = 1, device: int = 0, precipitation_choice="
     moisture = ET.get_moisture_type("NonEquilibriumMoisture", td)
     precip = ET.get_precipitation_type(precipitation_choice, td, rain_formation_choice=rain_formation_choice)
     names = ET.state_variable_names(moisture, precip)
-    Y0 = np.zeros((nc, len(names), 1), dtype=FT)
-    ρ_dry = np.zeros((nc, 1), dtype=FT)
-    T = np.zeros((nc, 1), dtype=FT)
-    cache = {}
-    for c in range(nc):
-        key = (qt_a[c], Nd_a[c])
-        if key not in cache:
-            cache[key] = IC.initial_condition_0d(FT, thermo_params, qt_a[c], Nd_a[c], k, rhod)
-        ip = cache[key]
-        Y0[c, :, 0] = [ip[n] for n in names]
-        ρ_dry[c, 0], T[c, 0] = ip["ρ_dry"], ip["T"]
+    Y0 = ρ_dry = T = None
+    if ic == "host":
+        Y0 = np.zeros((nc, len(names), 1), dtype=FT)
+        ρ_dry = np.zeros((nc, 1), dtype=FT)
+        T = np.zeros((nc, 1), dtype=FT)
+        cache = {}
+        for c in range(nc):
+            key = (qt_a[c], Nd_a[c])
+            if key not in cache:
+                cache[key] = IC.initial_condition_0d(FT, thermo_params, qt_a[c], Nd_a[c], k, rhod)
+            ip = cache[key]
+            Y0[c, :, 0] = [ip[n] for n in names]
+            ρ_dry[c, 0], T[c, 0] = ip["ρ_dry"], ip["T"]
+    elif ic != "device":
+        raise ValueError("ic must be 'host' or 'device'")
     cfg = make_config(
         model=MODEL_BOX, moisture=moisture.kid_enum, precip=precip.kid_enum, rain_formation=precip.rain_formation,
         sedimentation=precip.sedimentation, float_type=float_enum(FT), nz=1, nc=nc,
@@ -184,7 +189,9 @@ def box_case(FT=np.float64, nc: int = 1, device: int = 0, precipitation_choice="
     table = PR.flatten_params(td, precip.rain_formation)
     return Case(cfg=cfg, params=table, ρ_dry=ρ_dry, T=T, Y0=Y0, var_names=names,
                 col_scalars={COL_PRESCRIBED_ND: Nd_a.astype(FT)}, z_centers=np.array([0.5], dtype=FT),
-                meta=dict(toml=td, moisture=moisture, precip=precip, TS=TimeStepping(dt, dt_output, t_end)))
+                meta=dict(toml=td, moisture=moisture, precip=precip, TS=TimeStepping(dt, dt_output, t_end)),
+                device_ic=(dict(kind="gamma0d", qt=qt_a.astype(FT), Nd=Nd_a.astype(FT), k=np.full(nc, k, dtype=FT),
+                                rhod=np.full(nc, rhod, dtype=FT)) if ic == "device" else None))
 
 
 def col_sed_case(FT=np.float64, nc: int = 1, device: int = 0, precipitation_choice="Precipitation2M",
@@ -250,6 +257,10 @@ def apply_case(handle, case: Case):
             raise RuntimeError("this case builds its initial condition on the device: materialise(case) it first")
         for which, values in case.col_scalars.items():
             handle.set_column_scalar(which, values)
+        if case.device_ic.get("kind") == "gamma0d":
+            d = case.device_ic
+            handle.init_gamma_0d(d["qt"], d["Nd"], d["k"], d["rhod"])
+            return handle
         handle.init_shipway_hill(case.device_ic["sounding"], case.device_ic["p0"], case.device_ic.get("dry", False))
         return handle
     handle.set_profiles(case.ρ_dry, case.T)
@@ -273,9 +284,9 @@ def slice_columns(case: Case, a: int, b: int) -> Case:
     scal = {k: np.asarray(v)[a:b] for k, v in case.col_scalars.items()}
     c2s = None if case.column_to_set is None else case.column_to_set[a:b]
     if case.device_ic is not None and case.Y0 is None:
+        per_col = {k: np.asarray(v)[a:b] for k, v in case.device_ic.items() if k in ("p0", "qt", "Nd", "k", "rhod")}
         return Case(cfg=cfg, params=case.params, ρ_dry=None, T=None, Y0=None, var_names=case.var_names, col_scalars=scal,
-                    column_to_set=c2s, z_centers=case.z_centers, meta=case.meta,
-                    device_ic=dict(case.device_ic, p0=np.asarray(case.device_ic["p0"])[a:b]))
+                    column_to_set=c2s, z_centers=case.z_centers, meta=case.meta, device_ic=dict(case.device_ic, **per_col))
     pc = np.ndim(case.ρ_dry) == 2
     return Case(cfg=cfg, params=case.params, ρ_dry=case.ρ_dry[a:b] if pc else case.ρ_dry, T=case.T[a:b] if pc else case.T,
                 Y0=case.Y0[a:b], var_names=case.var_names, col_scalars=scal, column_to_set=c2s, z_centers=case.z_centers,
@@ -341,7 +352,8 @@ def materialise(case: Case, handle=None) -> Case:
     out.ρ_dry, out.T = h.get_profiles()
     out.Y0 = h.get_state()
     out.col_scalars = dict(case.col_scalars)
-    out.col_scalars[COL_Q_SURF] = np.full(case.cfg.nc, case.device_ic["q_surf"], dtype=case.dtype)
+    if "q_surf" in case.device_ic:
+        out.col_scalars[COL_Q_SURF] = np.full(case.cfg.nc, case.device_ic["q_surf"], dtype=case.dtype)
     return out
 
 

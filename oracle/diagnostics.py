@@ -48,6 +48,35 @@ def get_variable_data_from_ODE(u: dict, rho_dry: np.ndarray, var: str, vt: np.nd
     raise ValueError(f'Data name "{var}" not recognized!!')
 
 
+def z_top(u: dict, rho_dry: np.ndarray, z_span: float, rain: dict) -> float:
+    """"Z_top" (helper_functions.jl:164-185) of one column.  rain: n0, r0, m0, me, Δm, χm of CMP.Rain (Marshall-Palmer);
+    CMD.radar_reflectivity_1M restated as 10 log10(720 n0 λ^-7 / 1e-18) [UPSTREAM, recollected]."""
+    import math
+    rho = rho_dry + u["ρq_tot"]
+    qliq, qrai = u["ρq_liq"] / rho, u["ρq_rai"] / rho
+    qlr = qliq + qrai
+    nz = qlr.size
+    zt = nz  # 1-based
+    while qlr[zt - 1] < 1e-3 and zt > 1:
+        zt -= 1
+    dz = z_span / (nz + 1)  # the reference takes length(z) of the FACE field
+    steps = int(round(500.0 / dz))
+    ind = max(zt - steps + 1, 1)
+    qr = float(np.mean(qrai[ind - 1:zt]))
+    rh = float(np.mean(rho[ind - 1:zt]))
+    me = rain["me"] + rain["Δm"]
+    if qr > 0 and rh > 0:
+        li = (rh * qr * rain["r0"] ** me / (rain["χm"] * rain["m0"] * rain["n0"] * math.gamma(me + 1.0))) ** (1.0 / (me + 1.0))
+    else:
+        li = 0.0
+    if li <= 0.0:
+        return -300.0
+    Z = 10.0 * (math.log10(720.0 * rain["n0"]) + 7.0 * math.log10(li) + 18.0)
+    if Z != Z:
+        return 0.0
+    return Z
+
+
 def gvector_unfiltered(states: list, rho_dry, variables, vts=None) -> np.ndarray:
     """states: one {name: [nz]} dict per saved time (KiDUtils.jl:329-340)."""
     out = []

@@ -190,3 +190,38 @@ def test_col_sed_driver_and_calibration_match_the_oracle_backend():
     g, o = Gd.reshape(2, 2, 3, 2, 12), Go.reshape(2, 2, 3, 2, 12)  # [member][case][time][variable][level]
     for v in range(2):
         assert np.abs(g[:, :, :, v] - o[:, :, :, v]).max() <= 1e-6 * np.abs(o[:, :, :, v]).max(), v
+
+
+@pytest.mark.parametrize("FT,tol", [(np.float64, 1e-9), (np.float32, 2e-3)])
+def test_z_top_radar_reflectivity_observable(FT, tol):
+    """"Z_top" (helper_functions.jl:164-185): one value per column and save time, Precipitation1M only; against the numpy
+    restatement applied to the downloaded state (absolute tolerance in dBZ)."""
+    case = M.k1d_ensemble_case(FT, nc=6, n_profiles=2, n_elem=64, moisture_choice="NonEquilibriumMoisture",
+                               precipitation_choice="Precipitation1M")
+    times = [600.0, 1200.0, 1800.0]
+    G = CAL.solve_gvector(case, ["Z_top", "qr"], times)
+    assert G.shape == (6, len(times) * (1 + 64))
+    td = case.meta["toml"]
+    rain = dict(n0=td["rain_drop_size_distribution_coefficient_n0"], r0=td["rain_drop_length_scale"] if "rain_drop_length_scale" in td else 1e-3,
+                m0=None, me=td["rain_mass_size_relation_coefficient_me"], Δm=td["rain_mass_size_relation_coefficient_delm"],
+                χm=td["rain_mass_size_relation_coefficient_chim"])
+    rain["m0"] = 4.0 / 3.0 * np.pi * td["density_liquid_water"] * rain["r0"] ** 3
+    h = M.make_handle(case, Handle)
+    done, saw_rain = 0, False
+    for i, t in enumerate(times):
+        h.step(float(done), int(t) - done)
+        done = int(t)
+        Y = h.get_state()
+        for c in range(6):
+            u = {n: Y[c, j].astype(np.float64) for j, n in enumerate(case.var_names)}
+            rd = (case.ρ_dry[c] if case.ρ_dry.ndim == 2 else case.ρ_dry).astype(np.float64)
+            ref = OD.z_top(u, rd, float(case.cfg.z_max - case.cfg.z_min), rain)
+            if FT is np.float32 and ref < -300.0:
+                ref = -300.0  # rain so thin that λ⁻¹ underflows in Float32: log10(0) = -Inf -> -300 (the reference's replace!)
+            got = G[c].reshape(len(times), 65)[i, 0]
+            assert abs(got - ref) <= tol * max(1.0, abs(ref)) * 50, (c, t, got, ref)
+            saw_rain |= ref > -100.0
+    assert saw_rain
+    with pytest.raises(KidCudaError, match="radar reflectivity"):
+        CAL.solve_gvector(M.k1d_ensemble_case(FT, nc=2, n_profiles=1, n_elem=16, moisture_choice="NonEquilibriumMoisture",
+                                              precipitation_choice="Precipitation2M"), ["Z_top"], [10.0])

@@ -61,3 +61,30 @@ def test_device_ic_ensemble_steps_like_the_oracle():
     o.step(0.0, 120)
     e = errors(h.get_state(), o.get_state(), case.var_names)
     assert max(e.values()) < 1e-6, e
+
+
+@pytest.mark.parametrize("FT,rtol", [(np.float64, 1e-12), (np.float32, 2e-6)])
+def test_box_initial_condition_on_the_device(FT, rtol):
+    """kid_init_gamma_0d against the host restatement of initial_condition_0d (src/Common/initial_condition.jl:237-308),
+    per-box qt and Nd, both precipitation styles; then a few steps from either initial condition agree."""
+    nc = 48
+    rng = np.random.default_rng(5)
+    qt = 1e-3 * (0.5 + 1.5 * rng.random(nc))
+    Nd = 10.0 ** (7.5 + rng.random(nc))
+    for ps, rf in (("Precipitation2M", "SB2006"), ("Precipitation1M", "CliMA_1M")):
+        host = M.box_case(FT, nc=nc, precipitation_choice=ps, rain_formation_choice=rf, qt=qt, Nd=Nd)
+        dev = M.box_case(FT, nc=nc, precipitation_choice=ps, rain_formation_choice=rf, qt=qt, Nd=Nd, ic="device")
+        assert dev.Y0 is None
+        hd, hh = M.make_handle(dev, Handle), M.make_handle(host, Handle)
+        Yd, Yh = hd.get_state(), hh.get_state()
+        # the rain part is the small difference Lt - ρq_liq (Nd - N_liq): measured against the scale of its kind
+        scale_of = lambda Y, v: max(np.abs(Y[:, j]).max() for j, w in enumerate(host.var_names) if w.startswith("N_") == v.startswith("N_"))  # noqa: E731
+        for i, v in enumerate(host.var_names):
+            assert np.abs(Yd[:, i] - Yh[:, i]).max() <= rtol * max(scale_of(Yh, v), 1e-300), (ps, v)
+        rd, Td = hd.get_profiles()
+        assert np.array_equal(rd, host.ρ_dry) and np.all(Td == 300)
+        hd.step(0.0, 50)
+        hh.step(0.0, 50)
+        a, b = hd.get_state(), hh.get_state()
+        for i, v in enumerate(host.var_names):
+            assert np.abs(a[:, i] - b[:, i]).max() <= (1e-9 if FT is np.float64 else 2e-3) * max(scale_of(b, v), 1e-300), (ps, v)
