@@ -108,6 +108,7 @@ struct kid_handle {
     void *prm_sets = nullptr, *col_to_set = nullptr;  // per-column parameter sets (calibration ensembles)
     void* colmap = nullptr;                            // kid_set_column_map: host column of every device column
     void *ps_liq = nullptr, *ps_mix = nullptr;        // p_sat(T) per grid point (profile constants)
+    float* gconst_G = nullptr;                         // G(T) per grid point (inside the gconst allocation)
     void* gconst = nullptr;                            // float4 per grid point: constants of the packed 2M kernel (kid_pair_kernel.cuh)
     CUtensorMap state_map{};                           // TMA descriptor of the device state [var][level][column] (box 32 x 32 x nv)
     bool state_map_ok = false;
@@ -375,9 +376,11 @@ int check_ready(kid_handle* h) {
             const size_t n = h->prof_per_column ? size_t(h->cfg.nz) * h->ncp : size_t(h->cfg.nz);
             if (h->gconst) cudaFree(h->gconst);
             h->gconst = nullptr;
-            KID_CUDA(cudaMalloc(&h->gconst, n * sizeof(float4)));
-            KID_CUDA(cudaMemsetAsync(h->gconst, 0, n * sizeof(float4), h->stream));
-            e = h->lt->gconsts_f(make_args<float>(h, 0.0, 0, 0, 0), h->prm_f, (float4*)h->gconst, h->stream);
+            // float4 (ps_mix, 1/ps_liq, λ, T) per grid point, followed by the G(T) array
+            KID_CUDA(cudaMalloc(&h->gconst, n * (sizeof(float4) + sizeof(float))));
+            KID_CUDA(cudaMemsetAsync(h->gconst, 0, n * (sizeof(float4) + sizeof(float)), h->stream));
+            h->gconst_G = (float*)((float4*)h->gconst + n);
+            e = h->lt->gconsts_f(make_args<float>(h, 0.0, 0, 0, 0), h->prm_f, (float4*)h->gconst, h->gconst_G, h->stream);
             if (e != cudaSuccess) return fail(std::string("grid_consts_kernel launch: ") + cudaGetErrorString(e));
             h->launches++;
         }
@@ -418,7 +421,7 @@ int launch_tile(kid_handle* h, double t0, int nsteps, int diag_mode, int field, 
     if (diag_mode == 2 && field >= 0) { h->diag_nfields = 1; h->diag_fields[0] = field; }  // field < 0: h->diag_fields preset
     cudaError_t e;
     if (diag_mode == 0 && pair_capable(h) && h->gconst && h->state_map_ok) {
-        e = h->lt->pair_f(h->cfg.moisture, make_args<float>(h, t0, nsteps, 0, 0), (const float4*)h->gconst, h->state_map, h->prm_f, h->stream);
+        e = h->lt->pair_f(h->cfg.moisture, make_args<float>(h, t0, nsteps, 0, 0), (const float4*)h->gconst, h->gconst_G, h->state_map, h->prm_f, h->stream);
         if (e != cudaSuccess) return fail(std::string("k1d_pair_kernel launch: ") + cudaGetErrorString(e));
         h->launches++;
         return 0;

@@ -84,22 +84,22 @@ size_t smem_bytes(int moisture, int nz, int C, bool pcp) {
 
 #if KID_PRECIP == 3
 template <int MOIST>
-cudaError_t pair_m(const KArgs<float>& a, const float4* gconst, const CUtensorMap& tmY, const DevParams<float>& P, cudaStream_t s) {
+cudaError_t pair_m(const KArgs<float>& a, const float4* gconst, const float* gG, const CUtensorMap& tmY, const DevParams<float>& P, cudaStream_t s) {
     auto kern = k1d_pair_kernel<MOIST>;
     const size_t smem = k1d_pair_smem_bytes<MOIST>();
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     dim3 block(PAIR_C, PAIR_TJ), grid((a.nc + PAIR_C - 1) / PAIR_C);
-    kern<<<grid, block, smem, s>>>(a, gconst, tmY, P);
+    kern<<<grid, block, smem, s>>>(a, gconst, gG, tmY, P);
     return cudaGetLastError();
 }
-cudaError_t pair(int moisture, const KArgs<float>& a, const float4* gconst, const CUtensorMap& tmY, const DevParams<float>& P, cudaStream_t s) {
-    return moisture == KID_MOIST_EQ ? pair_m<KID_MOIST_EQ>(a, gconst, tmY, P, s) : pair_m<KID_MOIST_NONEQ>(a, gconst, tmY, P, s);
+cudaError_t pair(int moisture, const KArgs<float>& a, const float4* gconst, const float* gG, const CUtensorMap& tmY, const DevParams<float>& P, cudaStream_t s) {
+    return moisture == KID_MOIST_EQ ? pair_m<KID_MOIST_EQ>(a, gconst, gG, tmY, P, s) : pair_m<KID_MOIST_NONEQ>(a, gconst, gG, tmY, P, s);
 }
-cudaError_t gconsts(const KArgs<float>& a, const DevParams<float>& P, float4* out, cudaStream_t s) {
+cudaError_t gconsts(const KArgs<float>& a, const DevParams<float>& P, float4* out, float* outG, cudaStream_t s) {
     const int ncol = a.prof_per_column ? a.nc : 1;
     dim3 block(128), grid((ncol + 127) / 128, a.nz);
-    grid_consts_kernel<ConstPrm<float>><<<grid, block, 0, s>>>(a.T, out, a.nz, a.nc, a.ncp, a.prof_per_column, P);
+    grid_consts_kernel<ConstPrm<float>><<<grid, block, 0, s>>>(a.T, a.ps_liq, a.ps_mix, out, outG, a.nz, a.nc, a.ncp, a.prof_per_column, P);
     return cudaGetLastError();
 }
 #define KID_PAIR_ENTRIES pair, gconsts

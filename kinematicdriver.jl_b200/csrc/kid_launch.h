@@ -12,7 +12,16 @@ namespace kid {
 
 // tile of k1d_pair_kernel (kid_pair_kernel.cuh): 128 levels x 16 columns, 16 level-pair rows (256 threads, 128 registers):
 // two tiles are resident per SM, so the barrier waits of one overlap with the work of the other
-constexpr int PAIR_NZ = 128, PAIR_C = 16, PAIR_TJ = 16, PAIR_CTAS_PER_SM = 2;
+#ifndef KID_PAIR_C
+#define KID_PAIR_C 16
+#endif
+#ifndef KID_PAIR_TJ
+#define KID_PAIR_TJ 16
+#endif
+#ifndef KID_PAIR_CTAS
+#define KID_PAIR_CTAS 2
+#endif
+constexpr int PAIR_NZ = 128, PAIR_C = KID_PAIR_C, PAIR_TJ = KID_PAIR_TJ, PAIR_CTAS_PER_SM = KID_PAIR_CTAS;
 
 struct LaunchTable {
     // K1D / col_sed / (diag of) Box: tile kernel.  diag = false: step; true: rhs / aux mode.
@@ -29,8 +38,8 @@ struct LaunchTable {
     size_t (*k1d_smem_d)(int moisture, int nz, int C, bool per_column_params);
     // Precipitation2M, Float32, 128 levels, shared parameter set: the packed two-levels-per-thread step kernel
     // (kid_pair_kernel.cuh) and its per-grid-point constants; null for the other precipitation styles
-    cudaError_t (*pair_f)(int moisture, const KArgs<float>&, const float4* gconst, const CUtensorMap& state_map, const DevParams<float>&, cudaStream_t);
-    cudaError_t (*gconsts_f)(const KArgs<float>&, const DevParams<float>&, float4* out, cudaStream_t);
+    cudaError_t (*pair_f)(int moisture, const KArgs<float>&, const float4* gconst, const float* gG, const CUtensorMap& state_map, const DevParams<float>&, cudaStream_t);
+    cudaError_t (*gconsts_f)(const KArgs<float>&, const DevParams<float>&, float4* out, float* outG, cudaStream_t);
 };
 
 const LaunchTable* launch_table_precip0();

@@ -22,8 +22,8 @@
 //    the next rhs! call from the same state).  The terminal velocities are two more planes of the shared-memory tile
 //    with their own round-boundary stash row.  A launch starts with a pseudo-stage that only does this evaluation.
 //
-// Time-invariant functions of T per grid point (q_vs ρ, λ(T), R_v T / p_sat, G(T)) come from a float4 array filled at
-// upload (grid_consts_kernel), so T itself is only read by the rare ARG evaluation.
+// Time-invariant values per grid point (p_sat,mixed(T), 1 / p_sat,liq(T), λ(T), T; G(T) in an array of its own) come from
+// arrays filled at upload (grid_consts_kernel).
 #pragma once
 #include <cuda.h>  // CUtensorMap
 
@@ -94,25 +94,27 @@ __device__ __noinline__ float pair_activation_rate(const DevParams<float>& P, co
     return aerosol_activation_rate<float>(P, sw, q_tot, q_liq + q_rai, q_ice, N_liq + N_rai, N_aer, T, ps_l, p, rho, rw, dt);
 }
 
-// per-grid-point constants (see GridConst2): computed in double from the Float32 temperature
+// per-grid-point constants (see GridConst2) from the profile constants of the scalar kernels (profile_consts_kernel: the
+// same p_sat values), λ(T) as TD<float> evaluates it, and G(T) in double
 template <class PRMSRC>
-__global__ void grid_consts_kernel(const float* __restrict__ T, float4* __restrict__ out, int nz, int nc, int ncp, int per_column,
+__global__ void grid_consts_kernel(const float* __restrict__ T, const float* __restrict__ ps_liq, const float* __restrict__ ps_mix,
+                                   float4* __restrict__ out, float* __restrict__ outG, int nz, int nc, int ncp, int per_column,
                                    const __grid_constant__ DevParams<float> P) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y;
     if (c >= (per_column ? nc : 1)) return;
-    TD<double, DevParams<float>> td(P);
     const size_t i = per_column ? size_t(k) * ncp + c : size_t(k);
-    const double t = double(T[i]);
-    const double lam = td.liquid_fraction_T(t);
-    const double ps_l = td.psat_liquid(t), ps_m = td.psat_mixed(t, lam);
-    const double RvT = double(P.td_R_v) * t;
-    out[i] = make_float4(float(ps_m / RvT), float(RvT / ps_l), float(lam), float(td.G_func(t, td.latent_heat_vapor(t), ps_l)));  // (qvs_rho, S_fac, lam, G)
+    const float t = T[i];
+    TD<float, DevParams<float>> tdf(P);
+    TD<double, DevParams<float>> td(P);
+    out[i] = make_float4(ps_mix[i], rcp1(ps_liq[i]), t, tdf.liquid_fraction_T(t));  // (ps_mix, inv_psl, T, lam); lam is not staged
+    const double td_ = double(t);
+    outG[i] = float(td.G_func(td_, td.latent_heat_vapor(td_), td.psat_liquid(td_)));
 }
 
 template <int MOIST>
 __global__ void __launch_bounds__(PAIR_C * PAIR_TJ, PAIR_CTAS_PER_SM)
-k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const __grid_constant__ CUtensorMap tmY,
+k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const float* __restrict__ gG, const __grid_constant__ CUtensorMap tmY,
                 const __grid_constant__ DevParams<float> P) {
     using L = Lay<MOIST, KID_PRECIP_2M>;
     using namespace pairasync;
@@ -123,7 +125,10 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const _
     constexpr int HO = (NZ / 2) * C;  // a plane stores its even levels first, then the odd ones: offset of level k0 + 1 from level k0
     constexpr int NADV = adv_count<MOIST, KID_PRECIP_2M>();
     constexpr unsigned UN_BYTES = NV * LPR * C * sizeof(float);
-    static_assert(R >= 3, "the stage loop relies on two barriers between a block's WRITE phase and its next readers");
+    static_assert(R >= 2 && NZ % LPR == 0, "a stage is R >= 2 whole rounds");
+    // R >= 3: a block's WRITE phase and its next readers (the READ phase of the block below, one stage later) are always
+    // separated by a round barrier; with R = 2 the last block is read right at the start of the next stage: extra barrier
+    constexpr bool STAGE_BARRIER = R < 3;
     const int c = threadIdx.x, j = threadIdx.y;
     const int tid = j * C + c;
     const int gc0 = blockIdx.x * C, gc = gc0 + c;
@@ -135,8 +140,8 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const _
     float* Ys = reinterpret_cast<float*>(smem_raw);    // [NP][NR][C]; rows NZ, NZ+1: old values of the level below a block (2 parities)
     float* rds = Ys + NP * sV;                         // [NZ][C] ρ_dry
     float* uns = rds + NZ * C;                         // [NV][LPR][C] u^n of this round's levels (bulk copies)
-    float2* gca = reinterpret_cast<float2*>(uns + NV * LPR * C);  // [LPR][C] (q_vs ρ, S_fac) of this round's levels (cp.async)
-    float* gcb = reinterpret_cast<float*>(gca + LPR * C);        // [LPR][C] λ(T)
+    float2* gca = reinterpret_cast<float2*>(uns + NV * LPR * C);  // [LPR][C] (ps_mix, 1/ps_liq) of this round's levels (cp.async)
+    float* gcb = reinterpret_cast<float*>(gca + LPR * C);        // [LPR][C] T
     int* cb = reinterpret_cast<int*>(gcb + LPR * C);   // [2][C] cloud-base level (lowest activating level), two stages in flight
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(cb + 2 * C);
 
@@ -295,23 +300,24 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const _
             {
                 cp_async_wait_all();
                 const float2 a0 = gca[(2 * j) * C + c], a1 = gca[(2 * j + 1) * C + c];
-                g.qvs_rho = f2(a0.x, a1.x); g.S_fac = f2(a0.y, a1.y);
-                g.lam = f2(gcb[(2 * j) * C + c], gcb[(2 * j + 1) * C + c]);
+                g.ps_mix = f2(a0.x, a1.x); g.inv_psl = f2(a0.y, a1.y);
+                g.T = f2(gcb[(2 * j) * C + c], gcb[(2 * j + 1) * C + c]);
+                g.lam = liquid_fraction_x2(P, g.T);
                 // G(T): only rain evaporation reads it; straight from global memory inside that branch
                 const size_t i0 = A.prof_per_column ? size_t(k0) * ncp + gc : size_t(k0);
-                g.G0 = &gconst[i0].w;
-                g.G1 = &gconst[i0 + (A.prof_per_column ? size_t(ncp) : size_t(1))].w;
+                g.G0 = gG + i0;
+                g.G1 = gG + i0 + (A.prof_per_column ? size_t(ncp) : size_t(1));
             }
             if (real) {
                 PointX2 a;
-                thermo_point_x2<MOIST>(y, rd, g, a);
+                thermo_point_x2<MOIST>(P.td_R_v, y, rd, g, a);
                 if (stale_Naer) a.N_aer = f2(A.aux_Naer[size_t(k0) * ncp + gc], A.aux_Naer[size_t(k0 + 1) * ncp + gc]);
                 // activation source: the rate at the cloud-base level found one stage ago (or at every level, local_activation);
                 // re-evaluated here from the same state instead of being stored per level
                 F2 act = f2(0.f);
                 if (k1d) {
                     if (loc) {
-                        const F2 S = fma2((a.q_tot - (a.q_liq + a.q_rai)) - a.q_ice, a.rho * g.S_fac, -1.f);
+                        const F2 S = supersaturation_x2(P.td_R_v, a.rho, a.q_tot, a.q_liq + a.q_rai, a.q_ice, g);
                         if (!(S.x < S_SCREEN) && !(a.N_aer.x < 1.1920929e-07f)) act.x = arg_rate(a, 0, k0, rw);
                         if (!(S.y < S_SCREEN) && !(a.N_aer.y < 1.1920929e-07f)) act.y = arg_rate(a, 1, k0 + 1, rw);
                     } else if ((cbk >> 1) == (k0 >> 1)) {
@@ -324,7 +330,7 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const _
                 if constexpr (L::neq) {
                     if (k1d) {
                         F2 cs_liq, cs_ice;
-                        cloud_sources_x2(P.inv_tau_relax_liq, P.inv_tau_relax_ice, a, g, cs_liq, cs_ice);
+                        cloud_sources_x2(P.td_R_v, P.inv_tau_relax_liq, P.inv_tau_relax_ice, a, g, cs_liq, cs_ice);
                         tend[L::liq] = a.rho * cs_liq;
                         tend[L::ice] = a.rho * cs_ice;
                     }
@@ -362,7 +368,7 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const _
                 // aux of the state just formed, as the next rhs! call starts with (precompute_aux_thermo!,
                 // precompute_aux_precip!, precompute_aux_activation!: K1DModel/ode_utils.jl:33-38)
                 PointX2 a;
-                thermo_point_x2<MOIST>(y, rd, g, a);
+                thermo_point_x2<MOIST>(P.td_R_v, y, rd, g, a);
                 F2 vq, vN;
                 terminal_velocities_x2(P, sw, a, vq, vN);
                 pa[VT1 * sV] = vq.x; pa[VT1 * sV + HO] = vq.y;
@@ -372,7 +378,7 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const _
                     // accumulator starts at level 1 and is replaced only while its S is 0 and the candidate's S is > 0 (so a
                     // NEGATIVE rate at level 1 sticks).  Once this thread has a candidate its higher levels are skipped.
                     if (first == INT_MAX) {
-                        const F2 S = fma2((a.q_tot - (a.q_liq + a.q_rai)) - a.q_ice, a.rho * g.S_fac, -1.f);
+                        const F2 S = supersaturation_x2(P.td_R_v, a.rho, a.q_tot, a.q_liq + a.q_rai, a.q_ice, g);
                         if (!(S.x < S_SCREEN) && !(a.N_aer.x < 1.1920929e-07f)) {
                             const float S_Nl = arg_rate(a, 0, k0, rw_n);
                             if ((k0 == 0) ? (S_Nl != 0.f) : (S_Nl > 0.f)) first = k0;
@@ -391,6 +397,7 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const _
         // the slot just consumed serves the stage after next: every thread read it after this stage's first barrier and
         // has passed at least two more barriers; the next writers (atomicMin above, next stage) come after the next barrier
         if (j == 0) cb[par * C + c] = INT_MAX;
+        if constexpr (STAGE_BARRIER) __syncthreads();
     }
 }
 

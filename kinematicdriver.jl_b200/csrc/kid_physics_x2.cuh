@@ -14,20 +14,38 @@ namespace kid {
 struct PointX2 {
     F2 rho, inv_rho, q_tot, q_liq, q_ice, q_rai, q_sno, N_liq, N_rai, N_aer;
 };
-// Time-invariant functions of T (and p_sat(T)) per grid point, evaluated once per upload in double
-// (grid_consts_kernel): T never changes (src/Common/tendency.jl:34-135 only read it).
-//   qvs_rho = p_sat,mixed(T) / (R_v T)       q_vap_saturation(T, ρ) = qvs_rho / ρ
-//   lam     = liquid_fraction(T)             condensate_partition
-//   S_fac   = R_v T / p_sat,liq(T)           supersaturation_over_liquid + 1 = q_vap ρ S_fac
-//   G       = G_func_liquid(T)               CM2.rain_evaporation (read from global memory inside that branch)
+// Time-invariant values per grid point, staged per round (grid_consts_kernel): T never changes
+// (src/Common/tendency.jl:34-135 only read it).
+//   T, ps_mix = p_sat,mixed(T)   q_vap_saturation(T, ρ) = ps_mix / (ρ R_v T)      (the scalar kernel's values and operation
+//   inv_psl = 1 / p_sat,liq(T)   supersaturation = p_v / p_sat,liq - 1             order: q_tot - q_vs and S cancel, so the
+//   lam     = liquid_fraction(T) condensate_partition                              two kernels must round alike)
+//   G       = G_func_liquid(T)   CM2.rain_evaporation (read from global memory inside that branch)
 struct GridConst2 {
-    F2 qvs_rho, lam, S_fac;
+    F2 T, ps_mix, inv_psl, lam;  // lam is not staged: liquid_fraction_x2(T) (1 wherever T > T_freeze)
     const float *G0, *G1;  // G(T) of the two points: read from global memory where rain evaporates
 };
+// TD<float>::liquid_fraction_T for the pair; one warp-uniform branch in a warm run
+template <class PRM>
+KID_DEV F2 liquid_fraction_x2(const PRM& P, F2 T) {
+    F2 lam = f2(1.f);
+    if (any(!(T > P.td_T_freeze))) {
+        TD<float, PRM> td(P);
+        lam = f2(td.liquid_fraction_T(T.x), td.liquid_fraction_T(T.y));
+    }
+    return lam;
+}
+// ρ R_v T as TD<float>::condensate_partition / supersaturation form it: (ρ R_v) T
+KID_DEV F2 rho_RvT_x2(float R_v, F2 rho, const GridConst2& g) { return (rho * R_v) * g.T; }
+// TD.q_vap_saturation: ps_mix / (ρ R_v T)
+KID_DEV F2 q_vs_x2(float R_v, F2 rho, const GridConst2& g) { return g.ps_mix / rho_RvT_x2(R_v, rho, g); }
+// TD.supersaturation over liquid: (q_tot - q_liq - q_ice) (ρ R_v T) / p_sat,liq - 1, with q_liq, q_ice the condensate totals
+KID_DEV F2 supersaturation_x2(float R_v, F2 rho, F2 q_tot, F2 q_l, F2 q_i, const GridConst2& g) {
+    return fma2(((q_tot - q_l) - q_i) * rho_RvT_x2(R_v, rho, g), g.inv_psl, -1.f);  // p_v / p_vs - 1 contracts to one FFMA in the scalar build
+}
 
 // precompute_aux_thermo! + the q/N part of precompute_aux_precip! (src/Common/tendency.jl:34-73, :104-135, :203-206)
 template <int MOIST>
-KID_DEV void thermo_point_x2(const F2* y, F2 rho_dry, const GridConst2& g, PointX2& a) {
+KID_DEV void thermo_point_x2(float R_v, const F2* y, F2 rho_dry, const GridConst2& g, PointX2& a) {
     using L = Lay<MOIST, KID_PRECIP_2M>;
     a.rho = rho_dry + y[L::tot];
     a.inv_rho = vrcp(a.rho);
@@ -41,7 +59,7 @@ KID_DEV void thermo_point_x2(const F2* y, F2 rho_dry, const GridConst2& g, Point
         a.q_liq = vmax(y[L::liq] * a.inv_rho, 0.f);
         a.q_ice = vmax(y[L::ice] * a.inv_rho, 0.f);
     } else {
-        const F2 q_c = vmax(a.q_tot - g.qvs_rho * a.inv_rho, 0.f);
+        const F2 q_c = vmax(a.q_tot - q_vs_x2(R_v, a.rho, g), 0.f);
         const F2 ql_eq = g.lam * q_c;
         a.q_liq = ql_eq - a.q_rai;            // src/Common/tendency.jl:64-65: unclamped
         a.q_ice = (q_c - ql_eq) - a.q_sno;    // (1 - λ) q_c
@@ -133,8 +151,8 @@ KID_DEV F2 gamma_upper_neg_x2(float a, float gam_a1, const float* gser, F2 x) {
 }
 
 // precompute_aux_moisture_sources! (src/Common/tendency.jl:310-376), NonEquilibriumMoisture + 2M
-KID_DEV void cloud_sources_x2(float inv_tau_liq, float inv_tau_ice, const PointX2& a, const GridConst2& g, F2& cs_liq, F2& cs_ice) {
-    const F2 q_c = vmax(a.q_tot - g.qvs_rho * a.inv_rho, 0.f);
+KID_DEV void cloud_sources_x2(float R_v, float inv_tau_liq, float inv_tau_ice, const PointX2& a, const GridConst2& g, F2& cs_liq, F2& cs_ice) {
+    const F2 q_c = vmax(a.q_tot - q_vs_x2(R_v, a.rho, g), 0.f);
     const F2 ql_eq = g.lam * q_c;
     const F2 ql = ql_eq - a.q_rai, qi = (q_c - ql_eq) - a.q_sno;
     const F2 S_liq = (ql - a.q_liq) * inv_tau_liq;
@@ -232,7 +250,7 @@ KID_DEV void precip_sources_2m_x2(const PRM& P, const DevSwitches& sw, const Poi
         // CM2.rain_evaporation -> (evap_rate_0 -> N_rai, evap_rate_1 -> q_rai)
         const B2 m_q = q_rai > eps;
         if (any(m_q)) {
-            const F2 S = fma2((a.q_tot - (q_liq + q_rai)) - (a.q_ice + a.q_sno), rho * g.S_fac, -1.f);
+            const F2 S = supersaturation_x2(P.td_R_v, rho, a.q_tot, q_liq + q_rai, a.q_ice + a.q_sno, g);
             const B2 m_ev = m_q && (S < 0.f);
             if (any(m_ev)) {
                 const F2 xr = x_r;
