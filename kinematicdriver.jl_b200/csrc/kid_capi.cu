@@ -336,7 +336,7 @@ bool pair_capable(const kid_handle* h) {
 }
 
 // TMA descriptor of the device state for k1d_pair_kernel: 3-D tensor (columns, levels, variables), Float32, box = one
-// round of one tile (32 columns x 32 levels x all variables).  cuTensorMapEncodeTiled is a driver entry point: fetched
+// warp's share of a round of one tile (PAIR_C columns x 2·32/PAIR_C levels x all variables).  cuTensorMapEncodeTiled is a driver entry point: fetched
 // through the runtime so that the library keeps linking against the static cudart only.
 int make_state_map(kid_handle* h) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -348,7 +348,7 @@ int make_state_map(kid_handle* h) {
     if (!fn || q != cudaDriverEntryPointSuccess) return fail("cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t gdim[3] = {cuuint64_t(h->ncp), cuuint64_t(h->cfg.nz), cuuint64_t(h->nv)};
     const cuuint64_t gstride[2] = {cuuint64_t(h->ncp) * 4, cuuint64_t(h->ncp) * h->cfg.nz * 4};
-    const cuuint32_t box[3] = {cuuint32_t(PAIR_C), 2 * cuuint32_t(PAIR_TJ), cuuint32_t(h->nv)};
+    const cuuint32_t box[3] = {cuuint32_t(PAIR_C), 2 * cuuint32_t(32 / PAIR_C), cuuint32_t(h->nv)};  // one warp's levels of a round
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = reinterpret_cast<EncodeFn>(fn)(&h->state_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, h->Y, gdim, gstride, box, estr,
                                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,

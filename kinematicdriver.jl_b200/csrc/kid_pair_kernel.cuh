@@ -41,7 +41,8 @@ template <int MOIST>
 inline size_t k1d_pair_smem_bytes() {
     using L = Lay<MOIST, KID_PRECIP_2M>;
     return (size_t(L::NV + 2) * (PAIR_NZ + 2) * PAIR_C + size_t(PAIR_NZ) * PAIR_C + size_t(L::NV) * PAIR_LPR * PAIR_C) * sizeof(float) +
-           size_t(PAIR_LPR) * PAIR_C * (sizeof(float2) + sizeof(float)) + size_t(2) * PAIR_C * sizeof(int) + 16;
+           size_t(PAIR_LPR) * PAIR_C * (sizeof(float2) + sizeof(float)) + size_t(2) * PAIR_C * sizeof(int) +
+           size_t(1 + PAIR_C * PAIR_TJ / 32) * sizeof(unsigned long long);
 }
 
 // ---- sm_90+/sm_100 asynchronous-copy plumbing (PTX): mbarrier, bulk copy global -> shared (UBLKCP), cp.async (LDGSTS)
@@ -53,6 +54,9 @@ KID_DEV void mbar_init(void* bar, unsigned count) {
 }
 KID_DEV void mbar_arrive_expect_tx(void* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+KID_DEV void mbar_arrive(void* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 KID_DEV void mbar_wait(void* bar, unsigned parity) {
     asm volatile(
@@ -124,13 +128,16 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
     constexpr int sV = NR * C;
     constexpr int HO = (NZ / 2) * C;  // a plane stores its even levels first, then the odd ones: offset of level k0 + 1 from level k0
     constexpr int NADV = adv_count<MOIST, KID_PRECIP_2M>();
-    constexpr unsigned UN_BYTES = NV * LPR * C * sizeof(float);
+    constexpr int NWARP = C * TJ / 32, WROWS = 32 / C, LW = 2 * WROWS;  // warps per tile; pair-rows and levels of one warp per round
+    constexpr unsigned UN_BYTES = NV * LW * C * sizeof(float);           // u^n box of one warp
+    static_assert(32 % C == 0 && TJ % WROWS == 0, "a warp is a whole number of pair-rows");
     static_assert(R >= 2 && NZ % LPR == 0, "a stage is R >= 2 whole rounds");
     // R >= 3: a block's WRITE phase and its next readers (the READ phase of the block below, one stage later) are always
     // separated by a round barrier; with R = 2 the last block is read right at the start of the next stage: extra barrier
     constexpr bool STAGE_BARRIER = R < 3;
     const int c = threadIdx.x, j = threadIdx.y;
     const int tid = j * C + c;
+    const int lane = tid & 31, warp = tid >> 5, jj = j % WROWS;  // jj: this thread's pair-row inside its warp
     const int gc0 = blockIdx.x * C, gc = gc0 + c;
     const bool active = gc < A.nc;
     const int ncp = A.ncp;
@@ -139,11 +146,12 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* Ys = reinterpret_cast<float*>(smem_raw);    // [NP][NR][C]; rows NZ, NZ+1: old values of the level below a block (2 parities)
     float* rds = Ys + NP * sV;                         // [NZ][C] ρ_dry
-    float* uns = rds + NZ * C;                         // [NV][LPR][C] u^n of this round's levels (bulk copies)
-    float2* gca = reinterpret_cast<float2*>(uns + NV * LPR * C);  // [LPR][C] (ps_mix, 1/ps_liq) of this round's levels (cp.async)
+    float* uns = rds + NZ * C + warp * (NV * LW * C);  // [NWARP][NV][LW][C] u^n of this round's levels: one TMA box per warp
+    float2* gca = reinterpret_cast<float2*>(rds + NZ * C + NV * LPR * C);  // [LPR][C] (ps_mix, 1/ps_liq) of this round's levels (cp.async)
     float* gcb = reinterpret_cast<float*>(gca + LPR * C);        // [LPR][C] T
     int* cb = reinterpret_cast<int*>(gcb + LPR * C);   // [2][C] cloud-base level (lowest activating level), two stages in flight
-    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(cb + 2 * C);
+    unsigned long long* mbar_round = reinterpret_cast<unsigned long long*>(cb + 2 * C);  // round barrier: one arrival per warp
+    unsigned long long* mbar = mbar_round + 1 + warp;                                     // completion of this warp's u^n box
 
     // row of level k inside a plane: even levels first, then the odd ones.  The pair rows (k0, k0 + 1) of consecutive
     // threadIdx.y are then contiguous, so a warp that spans two pair-rows (C = 16) still reads conflict-free.
@@ -158,7 +166,10 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
         w1c = A.w1[gc]; qsurf = A.q_surf[gc]; Ndc = A.Nd[gc];
     }
     if (j == 0) { cb[c] = INT_MAX; cb[C + c] = INT_MAX; }
-    if (tid == 0) mbar_init(mbar, 1);
+    if (tid == 0) {
+        mbar_init(mbar_round, NWARP);
+        for (int w = 0; w < NWARP; ++w) mbar_init(mbar_round + 1 + w, 1);
+    }
     __syncthreads();
 
     const DevSwitches sw = A.sw;
@@ -174,7 +185,8 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
     constexpr float S_SCREEN = -1e-4f;
     const int nst = 3 * A.nsteps;
     int first = INT_MAX;      // lowest activation candidate among this thread's levels, for the stage being prepared
-    unsigned un_phase = 0;    // parity of the mbarrier phase the next u^n fetch completes
+    unsigned un_phase = 0;    // parity of the mbarrier phase this warp's next u^n fetch completes
+    unsigned round_phase = 0; // parity of the round barrier's current phase
 
     // ARG rate of component e of the pair (scalar, rare)
     auto arg_rate = [&](const PointX2& a, int e, int k, float rwx) -> float {
@@ -278,26 +290,21 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
                     }
                 }
             }
-            __syncthreads();  // every thread of the tile has read its old neighbours (and last round's u^n staging rows)
-            if (fetch_un) {
-                // u^n of this round's block — a (32 columns x 32 levels x NV variables) box of the device state — straight
-                // into shared memory with ONE TMA instruction; it lands while the sources are evaluated and is waited for just
-                // before the stage combine
-                if (tid == 0) {
-                    mbar_arrive_expect_tx(mbar, UN_BYTES);
-                    tma_load_3d(uns, &tmY, gc0, r * LPR, 0, mbar);
-                }
-            }
-            if (r == 0) cbk = cb[par * C + c];  // complete: its last atomicMin precedes the barrier above
-            if (!active) continue;
+            // Split round barrier.  No thread may overwrite its rows before every thread of the tile has read its old
+            // neighbours — but the rows are only written at the END of the WRITE phase, after the sources.  So a warp ARRIVES
+            // here (non-blocking) and WAITS just before its stores: by then the other warps have long arrived, and nobody idles
+            // at a barrier while the slowest warp of the round finishes.
+            __syncwarp();
+            if (lane == 0) mbar_arrive(mbar_round);
 
             // ---- WRITE phase: sources + SSPRK33 stage combine in place, then the aux fields of the next stage
             F2 y[NV];
-#pragma unroll
-            for (int v = 0; v < NV; ++v) y[v] = f2(pa[v * sV], pa[v * sV + HO]);
-            const F2 rd = f2(rda[0], rda[HO]);
+            F2 rd = f2(1.f);
             GridConst2 g;
-            {
+            if (active) {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) y[v] = f2(pa[v * sV], pa[v * sV + HO]);
+                rd = f2(rda[0], rda[HO]);
                 cp_async_wait_all();
                 const float2 a0 = gca[(2 * j) * C + c], a1 = gca[(2 * j + 1) * C + c];
                 g.ps_mix = f2(a0.x, a1.x); g.inv_psl = f2(a0.y, a1.y);
@@ -308,10 +315,24 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
                 g.G0 = gG + i0;
                 g.G1 = gG + i0 + (A.prof_per_column ? size_t(ncp) : size_t(1));
             }
-            if (real) {
-                PointX2 a;
+            PointX2 a;
+            Src2M s;
+            F2 cs_liq = f2(0.f), cs_ice = f2(0.f);
+            if (real && active) {
                 thermo_point_x2<MOIST>(P.td_R_v, y, rd, g, a);
                 if (stale_Naer) a.N_aer = f2(A.aux_Naer[size_t(k0) * ncp + gc], A.aux_Naer[size_t(k0 + 1) * ncp + gc]);
+                if constexpr (L::neq) {
+                    if (k1d) cloud_sources_x2(P.td_R_v, P.inv_tau_relax_liq, P.inv_tau_relax_ice, a, g, cs_liq, cs_ice);
+                }
+                precip_sources_2m_x2(P, sw, a, g, inv_dt, s);
+            }
+            // every warp of the tile has read its old neighbours (arrived above): the rows may be overwritten now
+#ifndef KID_EXP_NOWAIT  // experiment: upper bound of what relaxing the round barrier can give (results are then wrong)
+            mbar_wait(mbar_round, round_phase);
+#endif
+            round_phase ^= 1u;
+            if (r == 0) cbk = cb[par * C + c];  // complete: its last atomicMin precedes the owner's arrival at this round's barrier
+            if (real && active) {
                 // activation source: the rate at the cloud-base level found one stage ago (or at every level, local_activation);
                 // re-evaluated here from the same state instead of being stored per level
                 F2 act = f2(0.f);
@@ -329,14 +350,10 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
                 for (int v = 0; v < NV; ++v) tend[v] = f2(0.f);
                 if constexpr (L::neq) {
                     if (k1d) {
-                        F2 cs_liq, cs_ice;
-                        cloud_sources_x2(P.td_R_v, P.inv_tau_relax_liq, P.inv_tau_relax_ice, a, g, cs_liq, cs_ice);
                         tend[L::liq] = a.rho * cs_liq;
                         tend[L::ice] = a.rho * cs_ice;
                     }
                 }
-                Src2M s;
-                precip_sources_2m_x2(P, sw, a, g, inv_dt, s);
                 // precip_sources_tendency! (src/Common/tendency.jl:787-805)
                 tend[L::rai] = a.rho * s.s_rai;
                 tend[L::Na] = fma2(act, closed, s.s_Na);
@@ -350,24 +367,40 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
                     if (e.to_tot) tend[L::tot] += adv[i];  // precipitation also moves ρq_tot (K1DModel/tendency.jl:431-432)
                 });
                 // SSPRK33 as a convex combination  u_new = a·u^n + b·(y + dt·f(y))
-                if (fetch_un) { mbar_wait(mbar, un_phase); un_phase ^= 1u; }  // one mbarrier phase per round
+                if (fetch_un) { mbar_wait(mbar, un_phase); un_phase ^= 1u; }  // one phase of the warp's mbarrier per fetched box
                 float* gY = A.Y + size_t(k0) * ncp + gc;
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
                     const F2 yb = fma2(y[v], rk_b, tend[v] * rk_c);
                     if (stage == 0) y[v] = yb;
-                    else y[v] = fma2(f2(uns[(v * LPR + 2 * j) * C + c], uns[(v * LPR + 2 * j + 1) * C + c]), rk_a, yb);
+                    else y[v] = fma2(f2(uns[(v * LW + 2 * jj) * C + c], uns[(v * LW + 2 * jj + 1) * C + c]), rk_a, yb);
                     pa[v * sV] = y[v].x;
                     pa[v * sV + HO] = y[v].y;
                     if (stage == 2) { gY[v * plane] = y[v].x; gY[v * plane + ncp] = y[v].y; }
                 }
                 // the stored state is the u^n the TMA loads of the next step read: one proxy fence per thread and step
                 if (stage == 2 && r == R - 1) fence_proxy_async();
+            } else if (fetch_un) {
+                un_phase ^= 1u;  // columns beyond the ensemble: keep the phase count of the warp's fetches
             }
-            if (do_post) {
+            // u^n of this warp's levels in the NEXT round that combines with it (stages 2 and 3 of a step) — a (C columns x LW
+            // levels x NV variables) box of the device state — straight into the warp's staging rows with ONE TMA instruction:
+            // it lands while the next round's stencil and sources are evaluated.  The box is private to the warp, so the only
+            // ordering needed is that all its lanes are done with the previous box.
+            {
+                const bool last = (r + 1 == R);
+                const bool next_fetch = last ? (do_post && stage_n != 0) : fetch_un;
+                if (next_fetch) {
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(mbar, UN_BYTES);
+                        tma_load_3d(uns, &tmY, gc0, (last ? 0 : r + 1) * LPR + warp * LW, 0, mbar);
+                    }
+                }
+            }
+            if (do_post && active) {
                 // aux of the state just formed, as the next rhs! call starts with (precompute_aux_thermo!,
                 // precompute_aux_precip!, precompute_aux_activation!: K1DModel/ode_utils.jl:33-38)
-                PointX2 a;
                 thermo_point_x2<MOIST>(P.td_R_v, y, rd, g, a);
                 F2 vq, vN;
                 terminal_velocities_x2(P, sw, a, vq, vN);
@@ -394,8 +427,9 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
                 }
             }
         }
-        // the slot just consumed serves the stage after next: every thread read it after this stage's first barrier and
-        // has passed at least two more barriers; the next writers (atomicMin above, next stage) come after the next barrier
+        // the slot just consumed serves the stage after next: every thread read it after the wait of this stage's first
+        // round, i.e. before it arrived at the last round's barrier, whose wait this thread has passed; the next writers
+        // (atomicMin above, next stage's last round) come after that round's wait, for which this warp must have arrived
         if (j == 0) cb[par * C + c] = INT_MAX;
         if constexpr (STAGE_BARRIER) __syncthreads();
     }
