@@ -116,8 +116,8 @@ def total_columns(args, world: int) -> int:
 
 def global_case(args, world: int, device: int = 0):
     """The whole SURVEY §8(d) ensemble (numpy only: member c has w1, Nd, p0 from the counter hash; hydrostatic profile and
-    initial state are built on the device).  Member order: "sorted" stores the members along a Z-order curve through
-    (w1, log Nd, p0), so that neighbouring columns — the 32 lanes of a warp — follow the same microphysics branches;
+    initial state are built on the device).  Member order: "sorted" stores the members in nested quantile bins of p0, w1 and
+    Nd (model.nested_bin_order), so that neighbouring columns — the 32 lanes of a warp — follow the same microphysics branches;
     "hash" keeps the member-index order of §8(d)."""
     from kid_b200 import model as M
     return M.k1d_ensemble_case(np.float32, nc=total_columns(args, world), ic="device", order=args.order, device=device, n_elem=NZ,
@@ -136,7 +136,7 @@ def workload_config(args, world: int) -> dict:
     return {"workload": WORKLOAD, "columns": total, "levels": NZ,
             "window_model_time_s": [args.t_start + args.warmup, args.t_start + args.warmup + args.steps],
             "member_order": ("hash (SURVEY 8d counter hash)" if args.order == "hash"
-                             else "sorted along a Z-order curve through (w1, log Nd, p0)"),
+                             else "sorted into nested quantile bins (p0, then w1, then Nd): model.nested_bin_order"),
             "initial_condition": "every member its own p0 (SURVEY 8d), hydrostatic profile + initial state per column",
             "parallelism": f"columns sharded x{world}, contiguous blocks, no collective"}
 
@@ -315,6 +315,7 @@ def run_ours(args):
         # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # WARN still prints the version line: not on stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     total = total_columns(args, world)
@@ -410,19 +411,21 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = gp_steps_total / (float(te.item()) * 1e-3)
-    # The same call for a caller whose host arrays are in MEMBER-INDEX order (SURVEY 8d hash order) while the device keeps the
-    # warp-coherent storage order: the layout kernels gather / scatter through the column map (kid_set_column_map), no host gather.
+    # The same call for a caller whose host arrays are in MEMBER-INDEX order (SURVEY 8d hash order): every pipeline chunk is a
+    # contiguous block of the caller's rows, stored on the device in the chunk's own warp-coherent order; the block travels
+    # through the copy engine and the layout kernel permutes on the device (block-local kid_set_column_map): no host gather.
     e2e_user = None
     if args.order == "sorted":
         del pipe
         members = np.asarray(gcase.meta["column_perm"])[ca:cb]      # member index of every device column of this rank
-        host_row = np.argsort(np.argsort(members)).astype(np.int32)  # its row in the rank's member-ordered host array
-        pipe = PipelinedEnsemble(case, nchunks=args.e2e_chunks, host_column_of=host_row)
+        by_member = np.argsort(members)                              # this rank's columns in member-index order
+        case_m = M.reorder_columns(case, by_member)
+        pipe = PipelinedEnsemble.for_member_order(case_m, nchunks=args.e2e_chunks)
         pipe.set_steps_per_launch(spl)
         Yu = torch.empty(state_shape, dtype=torch.float32).pin_memory().numpy()
-        Yu[host_row] = Yn
+        Yu[...] = Yn[by_member]
         pipe.solve(Yu, t, spl)  # warm-up
-        Yu[host_row] = Yn
+        Yu[...] = Yn[by_member]
         barrier()
         w0 = time.perf_counter()
         pipe.solve(Yu, t + e2e_steps, e2e_steps)
@@ -482,7 +485,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": world * state_bytes / e2e_steps,
                     "d2h_bytes_per_step": world * state_bytes / e2e_steps, "resident_fraction": e2e_value / value,
                     "member_index_order_host_arrays": ({"value": e2e_user, "of_sorted_host_arrays": e2e_user / e2e_value,
-                                                        "how": "kid_set_column_map: the layout kernels gather/scatter the page-locked host array"}
+                                                        "how": "every pipeline chunk = a contiguous block of the caller's rows stored in its own warp-coherent order "
+                                                               "(block-local kid_set_column_map: copy engine + permutation on the device)"}
                                                        if e2e_user else None),
                     "call": f"PipelinedEnsemble.solve: {args.e2e_chunks} column chunks x [set_state_async(pinned) + step({e2e_steps}) + get_state_async(pinned)], per rank"},
             "gpu_launches": int(launches),

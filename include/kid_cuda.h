@@ -163,9 +163,10 @@ int kid_get_state_async(kid_handle_t* h, void* Y_pinned);
  * members share a warp: with a map the caller keeps its own order in the host arrays of kid_set_state* / kid_get_state*
  * while the device stores similar members next to each other (kid_b200.model.warp_coherent_order).  Host entries may point
  * anywhere into a larger page-locked array (column chunks of a pipelined ensemble).  Profiles, per-column scalars and aux
- * output stay in device column order.  Needs page-locked host buffers (kid_host_alloc, cudaHostAlloc, cudaHostRegister): the
- * layout kernels then gather / scatter the host rows in place over PCIe (plain transfers use the copy engine + staging,
- * which is faster for contiguous arrays; cfg.reserved[4] = 2 forces in-place access). */
+ * output stay in device column order.  A map that permutes ONE contiguous block of host rows (a chunk of the caller's array
+ * stored in its own warp-coherent order) moves the block with the copy engine and permutes on the device — as fast as an
+ * unmapped transfer.  A scattered map needs page-locked host buffers (kid_host_alloc, cudaHostAlloc, cudaHostRegister): the
+ * layout kernels then gather / scatter the host rows in place over PCIe (slower; cfg.reserved[4] = 2 forces in-place access). */
 int kid_set_column_map(kid_handle_t* h, const int32_t* host_column_of);
 
 /* replaces: ρ_ivp + initial_condition_1d + initialise_state and the ρ_dry, T, q_surf fields of initialise_aux

@@ -107,6 +107,10 @@ struct kid_handle {
     void *aux_Naer = nullptr, *out = nullptr, *staging = nullptr;
     void *prm_sets = nullptr, *col_to_set = nullptr;  // per-column parameter sets (calibration ensembles)
     void* colmap = nullptr;                            // kid_set_column_map: host column of every device column
+    // the map is a permutation of ONE contiguous block of host rows [colmap_base, colmap_base + nc): the block travels through
+    // the copy engine + staging and the layout kernel permutes on the device (colmap_local = map - base); -1: scattered rows
+    void* colmap_local = nullptr;
+    long long colmap_base = -1;
     void *ps_liq = nullptr, *ps_mix = nullptr;        // p_sat(T) per grid point (profile constants)
     float* gconst_G = nullptr;                         // G(T) per grid point (inside the gconst allocation)
     void* gconst = nullptr;                            // float4 per grid point: constants of the packed 2M kernel (kid_pair_kernel.cuh)
@@ -234,9 +238,16 @@ int launch_layout(kid_handle* h, const void* hostside, void* devside, int nv, co
 int to_device_layout(kid_handle* h, const void* host, void* dev, int nv, bool use_map = false) {
     const int nc = h->cfg.nc, nz = h->cfg.nz;
     const int* perm = use_map ? (const int*)h->colmap : nullptr;
-    if (const void* hv = device_view_of_pinned(h, host, perm != nullptr)) return launch_layout<true>(h, hv, dev, nv, perm);
-    if (perm) return fail("a column map (kid_set_column_map) needs page-locked host buffers: allocate them with kid_host_alloc");
     size_t bytes = size_t(nc) * nv * nz * h->fsz;
+    if (perm && h->colmap_base >= 0 && h->cfg.reserved[4] != 2) {
+        // block-local map: the contiguous block of host rows goes through the copy engine, the permutation happens on the device
+        if (ensure_staging(h, bytes)) return 1;
+        const char* src = static_cast<const char*>(host) + size_t(h->colmap_base) * nv * nz * h->fsz;
+        KID_CUDA(cudaMemcpyAsync(h->staging, src, bytes, cudaMemcpyHostToDevice, h->stream));
+        return launch_layout<true>(h, h->staging, dev, nv, (const int*)h->colmap_local);
+    }
+    if (const void* hv = device_view_of_pinned(h, host, perm != nullptr)) return launch_layout<true>(h, hv, dev, nv, perm);
+    if (perm) return fail("a scattered column map (kid_set_column_map) needs page-locked host buffers: allocate them with kid_host_alloc");
     if (ensure_staging(h, bytes)) return 1;
     KID_CUDA(cudaMemcpyAsync(h->staging, host, bytes, cudaMemcpyHostToDevice, h->stream));
     return launch_layout<true>(h, h->staging, dev, nv, nullptr);
@@ -245,13 +256,21 @@ int to_device_layout(kid_handle* h, const void* host, void* dev, int nv, bool us
 int to_host_layout(kid_handle* h, const void* dev, void* host, int nv, bool sync = true, bool use_map = false) {
     const int nc = h->cfg.nc, nz = h->cfg.nz;
     const int* perm = use_map ? (const int*)h->colmap : nullptr;
+    size_t bytes = size_t(nc) * nv * nz * h->fsz;
+    if (perm && h->colmap_base >= 0 && h->cfg.reserved[4] != 2) {
+        if (ensure_staging(h, bytes)) return 1;
+        if (launch_layout<false>(h, h->staging, const_cast<void*>(dev), nv, (const int*)h->colmap_local)) return 1;
+        char* dst = static_cast<char*>(host) + size_t(h->colmap_base) * nv * nz * h->fsz;
+        KID_CUDA(cudaMemcpyAsync(dst, h->staging, bytes, cudaMemcpyDeviceToHost, h->stream));
+        if (sync) KID_CUDA(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
     if (const void* hv = device_view_of_pinned(h, host, perm != nullptr)) {
         if (launch_layout<false>(h, hv, const_cast<void*>(dev), nv, perm)) return 1;
         if (sync) KID_CUDA(cudaStreamSynchronize(h->stream));
         return 0;
     }
-    if (perm) return fail("a column map (kid_set_column_map) needs page-locked host buffers: allocate them with kid_host_alloc");
-    size_t bytes = size_t(nc) * nv * nz * h->fsz;
+    if (perm) return fail("a scattered column map (kid_set_column_map) needs page-locked host buffers: allocate them with kid_host_alloc");
     if (ensure_staging(h, bytes)) return 1;
     if (launch_layout<false>(h, h->staging, const_cast<void*>(dev), nv, nullptr)) return 1;
     KID_CUDA(cudaMemcpyAsync(host, h->staging, bytes, cudaMemcpyDeviceToHost, h->stream));
@@ -698,7 +717,7 @@ void kid_destroy(kid_handle_t* h) {
         if (h->ev_ready[b]) cudaEventDestroy(h->ev_ready[b]);
         if (h->ev_done[b]) cudaEventDestroy(h->ev_done[b]);
     }
-    for (void* p : {h->colmap, h->gconst, h->ps_liq, h->ps_mix, h->prm_sets, h->col_to_set, h->Y, h->rho_dry, h->T, h->w1, h->q_surf, h->Nd, h->aux_Naer,
+    for (void* p : {h->colmap, h->colmap_local, h->gconst, h->ps_liq, h->ps_mix, h->prm_sets, h->col_to_set, h->Y, h->rho_dry, h->T, h->w1, h->q_surf, h->Nd, h->aux_Naer,
                     h->out, h->staging, h->U, h->Y3, h->S, h->prev_aux, h->xc, h->out2, h->send_left, h->send_right, h->recv_left,
                     h->recv_right, (void*)h->obsG, (void*)h->red, (void*)h->zsin, (void*)h->cosx, (void*)h->cosz})
         if (p) cudaFree(p);
@@ -855,11 +874,34 @@ int kid_set_column_map(kid_handle_t* h, const int32_t* host_column_of) {
     KID_ON_DEVICE(h);
     if (!h) return fail("null handle");
     if (h->colmap) { cudaFree(h->colmap); h->colmap = nullptr; }
+    if (h->colmap_local) { cudaFree(h->colmap_local); h->colmap_local = nullptr; }
+    h->colmap_base = -1;
     if (!host_column_of) return 0;
-    for (int c = 0; c < h->cfg.nc; ++c)
+    const int nc = h->cfg.nc;
+    int lo = INT_MAX, hi = -1;
+    for (int c = 0; c < nc; ++c) {
         if (host_column_of[c] < 0) return fail("kid_set_column_map: negative host column");
-    KID_CUDA(cudaMalloc(&h->colmap, size_t(h->cfg.nc) * sizeof(int)));
-    KID_CUDA(cudaMemcpyAsync(h->colmap, host_column_of, size_t(h->cfg.nc) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        lo = std::min(lo, host_column_of[c]);
+        hi = std::max(hi, host_column_of[c]);
+    }
+    KID_CUDA(cudaMalloc(&h->colmap, size_t(nc) * sizeof(int)));
+    KID_CUDA(cudaMemcpyAsync(h->colmap, host_column_of, size_t(nc) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    // a permutation of one contiguous block of host rows?  (max - min + 1 == nc and every row hit once)
+    if (hi - lo + 1 == nc) {
+        std::vector<int> local(nc);
+        std::vector<char> seen(nc, 0);
+        bool perm_ok = true;
+        for (int c = 0; c < nc && perm_ok; ++c) {
+            local[c] = host_column_of[c] - lo;
+            perm_ok = !seen[local[c]];
+            seen[local[c]] = 1;
+        }
+        if (perm_ok) {
+            KID_CUDA(cudaMalloc(&h->colmap_local, size_t(nc) * sizeof(int)));
+            KID_CUDA(cudaMemcpy(h->colmap_local, local.data(), size_t(nc) * sizeof(int), cudaMemcpyHostToDevice));
+            h->colmap_base = lo;
+        }
+    }
     KID_CUDA(cudaStreamSynchronize(h->stream));
     return 0;
 }

@@ -224,6 +224,28 @@ class PipelinedEnsemble:
             if self.host_column_of is not None:
                 self.handles[-1].set_column_map(self.host_column_of[a:b])
 
+    @classmethod
+    def for_member_order(cls, case: M.Case, nchunks: int = 4):
+        """`case` and the host arrays handed to `solve` are in the CALLER's member order (any order).  Every chunk is a
+        contiguous block of host rows whose members are stored on the device in their own warp-coherent order
+        (model.warp_coherent_order of the chunk): the block travels through the copy engine and the layout kernel permutes on
+        the device (block-local column map), so an unordered caller pays neither a host gather nor scattered PCIe reads."""
+        self = cls.__new__(cls)
+        nc = case.cfg.nc
+        edges = (np.linspace(0, nc, nchunks + 1).astype(int) // 32) * 32
+        edges[-1] = nc
+        self.ranges = [(int(a), int(b)) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+        self.handles, maps = [], []
+        for a, b in self.ranges:
+            sub = M.slice_columns(case, a, b)
+            perm = M.warp_coherent_order(sub)
+            h = M.make_handle(M.reorder_columns(sub, perm))
+            h.set_column_map(a + perm)
+            self.handles.append(h)
+            maps.append(a + perm)
+        self.host_column_of = np.concatenate(maps).astype(np.int32)
+        return self
+
     def set_steps_per_launch(self, n: int):
         for h in self.handles:
             h.set_steps_per_launch(n)

@@ -53,9 +53,45 @@ def test_column_map_gathers_and_scatters_through_the_host_order():
     h.set_state(host2)
     h.set_column_map(None)
     assert np.array_equal(h.get_state(), Y[::-1])
+    # a permutation of one contiguous block of host rows travels through the copy engine: pageable arrays work too
     h.set_column_map(perm)
-    with pytest.raises(KidCudaError):   # a map needs page-locked host memory (no host-side gather fallback)
-        h.get_state(np.empty_like(Y))
+    pageable = np.empty_like(Y)
+    h.get_state(pageable)
+    assert np.array_equal(pageable[perm], Y[::-1])
+
+
+def test_scattered_and_block_local_column_maps():
+    """Scattered map: device column i <-> an arbitrary row of a LARGER page-locked array (gathered in place over PCIe; pageable
+    memory is refused: no host-side gather fallback).  Block-local map: a permutation of rows [base, base + nc) of a larger
+    array (copy engine + permutation on the device)."""
+    nc = 64
+    cs = case(nc)
+    h = M.make_handle(cs, Handle)
+    h.step(0.0, 3)
+    Y = h.get_state()
+    rng = np.random.default_rng(3)
+    big = pinned_empty((3 * nc,) + Y.shape[1:], np.float32); big[...] = -1.0
+    rows = rng.permutation(3 * nc)[:nc].astype(np.int32)               # scattered
+    def get(dst):
+        h.get_state_async(dst); h.synchronize()
+    def put(src):
+        h.set_state_async(src); h.synchronize()
+    h.set_column_map(rows)
+    get(big)
+    assert np.array_equal(big[rows], Y)
+    untouched = np.setdiff1d(np.arange(3 * nc), rows)
+    assert np.all(big[untouched] == -1.0)
+    with pytest.raises(KidCudaError):
+        get(np.empty_like(big))
+    big[...] = -1.0
+    local = (nc + rng.permutation(nc)).astype(np.int32)                # block-local: rows [nc, 2 nc)
+    h.set_column_map(local)
+    get(big)
+    assert np.array_equal(big[local], Y) and np.all(big[:nc] == -1.0) and np.all(big[2 * nc:] == -1.0)
+    big[local] = Y[::-1]
+    put(big)
+    h.set_column_map(None)
+    assert np.array_equal(h.get_state(), Y[::-1])
 
 
 def test_pipelined_ensemble_in_member_order_equals_storage_order():
@@ -73,3 +109,8 @@ def test_pipelined_ensemble_in_member_order_equals_storage_order():
     assert np.array_equal(b[host_row], a)
     g.step(30.0, 10)
     assert np.array_equal(a, g.get_state())
+    # the caller's arrays in member order, every chunk stored in its own warp-coherent order (block-local maps)
+    by_member = np.argsort(members)
+    c = pinned_empty(Y0.shape, np.float32); c[...] = Y0[by_member]
+    PipelinedEnsemble.for_member_order(M.reorder_columns(cs, by_member), nchunks=4).solve(c, 30.0, 10)
+    assert np.array_equal(c, a[by_member])
