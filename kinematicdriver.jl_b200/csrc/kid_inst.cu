@@ -102,6 +102,17 @@ cudaError_t gconsts(const KArgs<float>& a, const DevParams<float>& P, float4* ou
     grid_consts_kernel<ConstPrm<float>><<<grid, block, 0, s>>>(a.T, a.ps_liq, a.ps_mix, out, outG, a.nz, a.nc, a.ncp, a.prof_per_column, P);
     return cudaGetLastError();
 }
+#ifdef KID_EXP_TIMING
+}  // namespace
+}  // namespace kid
+extern "C" int kid_exp_pair_cycles(unsigned long long* out, int reset) {
+    if (cudaMemcpyFromSymbol(out, kid::g_pair_cycles, sizeof(kid::g_pair_cycles)) != cudaSuccess) return 1;
+    if (reset) { unsigned long long z[8][8] = {}; cudaMemcpyToSymbol(kid::g_pair_cycles, z, sizeof(z)); }
+    return 0;
+}
+namespace kid {
+namespace {
+#endif
 #define KID_PAIR_ENTRIES pair, gconsts
 #else
 #define KID_PAIR_ENTRIES nullptr, nullptr

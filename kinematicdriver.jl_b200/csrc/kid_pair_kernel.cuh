@@ -83,8 +83,17 @@ KID_DEV void cp_async4(void* dst_smem, const void* src) {
 }
 KID_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 KID_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-// generic-proxy writes to global memory (the stage-3 state store) before later bulk copies (async proxy) read them
-KID_DEV void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// TMA store: one 3-D box shared -> global (bulk async-group completion)
+KID_DEV void tma_store_3d(const CUtensorMap* map, int c0, int c1, int c2, const void* src_smem) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(src_smem)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+KID_DEV void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+KID_DEV void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }  // sources may be reused
+KID_DEV void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }            // stores are complete
+// generic-proxy writes to SHARED memory before a bulk copy (async proxy) reads them
+KID_DEV void fence_proxy_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 }  // namespace pairasync
 
 // ARG activation rate of one grid point (get_aerosol_activation_rate, K1DModel/tendency.jl:35-96).  Rare (cloud-base
@@ -116,6 +125,11 @@ __global__ void grid_consts_kernel(const float* __restrict__ T, const float* __r
     outG[i] = float(td.G_func(td_, td.latent_heat_vapor(td_), td.psat_liquid(td_)));
 }
 
+#ifdef KID_EXP_TIMING
+// experiment build (scripts/build_variant.sh timing -DKID_EXP_TIMING): cycles the warps spend between phases, per round
+__device__ unsigned long long g_pair_cycles[8][8];  // [barrier wait | READ | sources | act + tendencies | u^n wait | combine + stores | prefetch issue | post][round]
+#endif
+
 template <int MOIST>
 __global__ void __launch_bounds__(PAIR_C * PAIR_TJ, PAIR_CTAS_PER_SM)
 k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const float* __restrict__ gG, const __grid_constant__ CUtensorMap tmY,
@@ -141,7 +155,7 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
     const int gc0 = blockIdx.x * C, gc = gc0 + c;
     const bool active = gc < A.nc;
     const int ncp = A.ncp;
-    const size_t plane = size_t(NZ) * ncp;
+    const size_t plane = size_t(NZ) * ncp;  // (tile load)
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* Ys = reinterpret_cast<float*>(smem_raw);    // [NP][NR][C]; rows NZ, NZ+1: old values of the level below a block (2 parities)
@@ -223,6 +237,9 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
             float* pa = Ys + (k0 >> 1) * C + c;  // level k0 (even); level k0 + 1 at + HO; + plane · sV
             const float* rda = rds + (k0 >> 1) * C + c;
             F2 adv[NADV];
+#ifdef KID_EXP_TIMING
+            const long long tc0 = clock64();
+#endif
             if (active) {
                 {   // grid-point constants of this thread's pair -> its own two staging slots (consumed after the barrier)
                     const size_t i0 = A.prof_per_column ? size_t(k0) * ncp + gc : size_t(k0);
@@ -296,6 +313,9 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
             // at a barrier while the slowest warp of the round finishes.
             __syncwarp();
             if (lane == 0) mbar_arrive(mbar_round);
+#ifdef KID_EXP_TIMING
+            const long long tc1 = clock64();
+#endif
 
             // ---- WRITE phase: sources + SSPRK33 stage combine in place, then the aux fields of the next stage
             F2 y[NV];
@@ -327,8 +347,13 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
                 precip_sources_2m_x2(P, sw, a, g, inv_dt, s);
             }
             // every warp of the tile has read its old neighbours (arrived above): the rows may be overwritten now
-#ifndef KID_EXP_NOWAIT  // experiment: upper bound of what relaxing the round barrier can give (results are then wrong)
+#ifdef KID_EXP_TIMING
+            const long long tc2 = clock64();
+#endif
             mbar_wait(mbar_round, round_phase);
+#ifdef KID_EXP_TIMING
+            const long long tc3 = clock64();
+            long long tcA = tc3, tcB = tc3, tcC = tc3, tcD = tc3;
 #endif
             round_phase ^= 1u;
             if (r == 0) cbk = cb[par * C + c];  // complete: its last atomicMin precedes the owner's arrival at this round's barrier
@@ -367,22 +392,46 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
                     if (e.to_tot) tend[L::tot] += adv[i];  // precipitation also moves ρq_tot (K1DModel/tendency.jl:431-432)
                 });
                 // SSPRK33 as a convex combination  u_new = a·u^n + b·(y + dt·f(y))
+#ifdef KID_EXP_TIMING
+                tcA = clock64();
+#endif
                 if (fetch_un) { mbar_wait(mbar, un_phase); un_phase ^= 1u; }  // one phase of the warp's mbarrier per fetched box
-                float* gY = A.Y + size_t(k0) * ncp + gc;
+#ifdef KID_EXP_TIMING
+                tcB = clock64();
+#endif
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
+                    float* un0 = uns + (v * LW + 2 * jj) * C + c;  // this thread's two slots of the warp's box
                     const F2 yb = fma2(y[v], rk_b, tend[v] * rk_c);
                     if (stage == 0) y[v] = yb;
-                    else y[v] = fma2(f2(uns[(v * LW + 2 * jj) * C + c], uns[(v * LW + 2 * jj + 1) * C + c]), rk_a, yb);
+                    else y[v] = fma2(f2(un0[0], un0[C]), rk_a, yb);
                     pa[v * sV] = y[v].x;
                     pa[v * sV + HO] = y[v].y;
-                    if (stage == 2) { gY[v * plane] = y[v].x; gY[v * plane + ncp] = y[v].y; }
+                    // end of a step: the new state leaves through the same box (TMA store below)
+                    if (stage == 2) { un0[0] = y[v].x; un0[C] = y[v].y; }
                 }
-                // the stored state is the u^n the TMA loads of the next step read: one proxy fence per thread and step
-                if (stage == 2 && r == R - 1) fence_proxy_async();
             } else if (fetch_un) {
                 un_phase ^= 1u;  // columns beyond the ensemble: keep the phase count of the warp's fetches
+                if (stage == 2) {
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) { uns[(v * LW + 2 * jj) * C + c] = 0.f; uns[(v * LW + 2 * jj + 1) * C + c] = 0.f; }
+                }
             }
+            // End of a step: the warp's (C columns x LW levels x NV variables) box of the new state -> device state with ONE TMA
+            // store.  State stores and u^n loads both go through the async proxy, so no generic <-> async proxy fence on global
+            // memory is needed (fence.proxy.async after the stores cost 10 % of the kernel); only the shared-memory writes
+            // above are fenced for the bulk copy.
+            if (real && stage == 2) {
+                fence_proxy_async_shared();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_3d(&tmY, gc0, r * LPR + warp * LW, 0, uns);
+                    bulk_commit();
+                }
+            }
+#ifdef KID_EXP_TIMING
+            tcC = clock64();
+#endif
             // u^n of this warp's levels in the NEXT round that combines with it (stages 2 and 3 of a step) — a (C columns x LW
             // levels x NV variables) box of the device state — straight into the warp's staging rows with ONE TMA instruction:
             // it lands while the next round's stencil and sources are evaluated.  The box is private to the warp, so the only
@@ -393,11 +442,18 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
                 if (next_fetch) {
                     __syncwarp();
                     if (lane == 0) {
+                        // the box is the source of this round's store (stage 3): wait until the store has read it; the
+                        // step's first u^n box waits for the previous step's stores of this warp to be complete
+                        if (stage == 2) bulk_wait_read_all();
+                        if (last && stage_n == 1) bulk_wait_all();
                         mbar_arrive_expect_tx(mbar, UN_BYTES);
                         tma_load_3d(uns, &tmY, gc0, (last ? 0 : r + 1) * LPR + warp * LW, 0, mbar);
                     }
                 }
             }
+#ifdef KID_EXP_TIMING
+            tcD = clock64();
+#endif
             if (do_post && active) {
                 // aux of the state just formed, as the next rhs! call starts with (precompute_aux_thermo!,
                 // precompute_aux_precip!, precompute_aux_activation!: K1DModel/ode_utils.jl:33-38)
@@ -426,6 +482,19 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
                     }
                 }
             }
+#ifdef KID_EXP_TIMING
+            if (lane == 0 && real) {
+                const long long tc4 = clock64();
+                atomicAdd(&g_pair_cycles[0][r], (unsigned long long)(tc3 - tc2));
+                atomicAdd(&g_pair_cycles[1][r], (unsigned long long)(tc1 - tc0));
+                atomicAdd(&g_pair_cycles[2][r], (unsigned long long)(tc2 - tc1));
+                atomicAdd(&g_pair_cycles[3][r], (unsigned long long)(tcA - tc3));
+                atomicAdd(&g_pair_cycles[4][r], (unsigned long long)(tcB - tcA));
+                atomicAdd(&g_pair_cycles[5][r], (unsigned long long)(tcC - tcB));
+                atomicAdd(&g_pair_cycles[6][r], (unsigned long long)(tcD - tcC));
+                atomicAdd(&g_pair_cycles[7][r], (unsigned long long)(tc4 - tcD));
+            }
+#endif
         }
         // the slot just consumed serves the stage after next: every thread read it after the wait of this stage's first
         // round, i.e. before it arrived at the last round's barrier, whose wait this thread has passed; the next writers
@@ -433,6 +502,7 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
         if (j == 0) cb[par * C + c] = INT_MAX;
         if constexpr (STAGE_BARRIER) __syncthreads();
     }
+    if (lane == 0) bulk_wait_all();  // the last step's stores read this CTA's shared memory
 }
 
 }  // namespace kid

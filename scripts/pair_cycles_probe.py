@@ -1,0 +1,21 @@
+"""Experiment build (-DKID_EXP_TIMING): where do the warps of k1d_pair_kernel spend their cycles, per round of a stage?"""
+import ctypes as C, os, sys
+from pathlib import Path
+import numpy as np
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "kinematicdriver.jl_b200")); sys.path.insert(0, str(ROOT))
+from kid_b200 import model as M
+from kid_b200 import lib as KL
+from kid_b200.lib import Handle
+cs = M.k1d_ensemble_case(np.float32, nc=262144, n_elem=128, ic="device", order="sorted", moisture_choice="NonEquilibriumMoisture", precipitation_choice="Precipitation2M")
+h = M.make_handle(cs, Handle)
+h.step(0.0, 480); h.synchronize()
+lib = KL.load_library()
+buf = (C.c_ulonglong * 64)()
+lib.kid_exp_pair_cycles(buf, 1)
+h.set_steps_per_launch(10); h.step(480.0, 10); h.synchronize()
+lib.kid_exp_pair_cycles(buf, 0)
+a = np.array(list(buf), dtype=np.float64).reshape(8, 8)[:, :4]
+tot = a.sum()
+for name, row in zip(("wait at round barrier", "READ (stencil)", "sources", "activation + tendencies", "wait for the u^n box", "combine + stores", "u^n prefetch issue", "post (vt, cloud base)"), a):
+    print(f"{name:24s}", " ".join(f"r{r}: {100*v/tot:5.1f}%" for r, v in enumerate(row)), f" | {100*row.sum()/tot:5.1f}%")
