@@ -357,6 +357,11 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
 #endif
             round_phase ^= 1u;
             if (r == 0) cbk = cb[par * C + c];  // complete: its last atomicMin precedes the owner's arrival at this round's barrier
+            // The slot just consumed serves the NEXT stage's candidates: every thread read it after the wait of round 0, i.e.
+            // before it arrived at round 1's barrier, whose wait this thread has passed; the next writers (atomicMin in the
+            // next stage) have passed the wait of this stage's LAST round, for which this warp must have arrived (R >= 3;
+            // R = 2: the stage barrier)
+            if (r == 1 && j == 0) cb[par * C + c] = INT_MAX;
             if (real && active) {
                 // activation source: the rate at the cloud-base level found one stage ago (or at every level, local_activation);
                 // re-evaluated here from the same state instead of being stored per level
@@ -466,7 +471,11 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
                     // find_cloud_base! (K1DModel/tendency.jl:21-32): the lowest level with a positive ARG rate; the
                     // accumulator starts at level 1 and is replaced only while its S is 0 and the candidate's S is > 0 (so a
                     // NEGATIVE rate at level 1 sticks).  Once this thread has a candidate its higher levels are skipped.
-                    if (first == INT_MAX) {
+                    // A candidate is published at once, and a level above an already published candidate of the column (any
+                    // thread's; the rounds climb) can never be the lowest: its ARG evaluation is skipped.  A stale read of the
+                    // slot only costs an evaluation.
+                    const int cb_seen = *reinterpret_cast<volatile int*>(&cb[parn * C + c]);
+                    if (first == INT_MAX && k0 < cb_seen) {
                         const F2 S = supersaturation_x2(P.td_R_v, a.rho, a.q_tot, a.q_liq + a.q_rai, a.q_ice, g);
                         if (!(S.x < S_SCREEN) && !(a.N_aer.x < 1.1920929e-07f)) {
                             const float S_Nl = arg_rate(a, 0, k0, rw_n);
@@ -475,11 +484,9 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
                         if (first == INT_MAX && !(S.y < S_SCREEN) && !(a.N_aer.y < 1.1920929e-07f)) {
                             if (arg_rate(a, 1, k0 + 1, rw_n) > 0.f) first = k0 + 1;
                         }
-                    }
-                    if (r == R - 1) {
                         if (first != INT_MAX) atomicMin(&cb[parn * C + c], first);
-                        first = INT_MAX;
                     }
+                    if (r == R - 1) first = INT_MAX;
                 }
             }
 #ifdef KID_EXP_TIMING
@@ -496,10 +503,6 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
             }
 #endif
         }
-        // the slot just consumed serves the stage after next: every thread read it after the wait of this stage's first
-        // round, i.e. before it arrived at the last round's barrier, whose wait this thread has passed; the next writers
-        // (atomicMin above, next stage's last round) come after that round's wait, for which this warp must have arrived
-        if (j == 0) cb[par * C + c] = INT_MAX;
         if constexpr (STAGE_BARRIER) __syncthreads();
     }
     if (lane == 0) bulk_wait_all();  // the last step's stores read this CTA's shared memory
