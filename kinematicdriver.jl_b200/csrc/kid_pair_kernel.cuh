@@ -41,7 +41,7 @@ template <int MOIST>
 inline size_t k1d_pair_smem_bytes() {
     using L = Lay<MOIST, KID_PRECIP_2M>;
     return (size_t(L::NV + 2) * (PAIR_NZ + 2) * PAIR_C + size_t(PAIR_NZ) * PAIR_C + size_t(L::NV) * PAIR_LPR * PAIR_C) * sizeof(float) +
-           size_t(PAIR_LPR) * PAIR_C * (sizeof(float2) + sizeof(float)) + size_t(2) * PAIR_C * sizeof(int) +
+           size_t(PAIR_LPR) * PAIR_C * (sizeof(float2) + sizeof(float)) + size_t(2) * PAIR_C * sizeof(unsigned long long) +
            size_t(1 + PAIR_C * PAIR_TJ / 32) * sizeof(unsigned long long);
 }
 
@@ -127,6 +127,7 @@ __global__ void grid_consts_kernel(const float* __restrict__ T, const float* __r
 
 #ifdef KID_EXP_TIMING
 // experiment build (scripts/build_variant.sh timing -DKID_EXP_TIMING): cycles the warps spend between phases, per round
+__device__ unsigned long long g_pair_work[8][8];    // [warp][round]: cycles outside the round-barrier wait
 __device__ unsigned long long g_pair_cycles[8][8];  // [barrier wait | READ | sources | act + tendencies | u^n wait | combine + stores | prefetch issue | post][round]
 #endif
 
@@ -163,8 +164,10 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
     float* uns = rds + NZ * C + warp * (NV * LW * C);  // [NWARP][NV][LW][C] u^n of this round's levels: one TMA box per warp
     float2* gca = reinterpret_cast<float2*>(rds + NZ * C + NV * LPR * C);  // [LPR][C] (ps_mix, 1/ps_liq) of this round's levels (cp.async)
     float* gcb = reinterpret_cast<float*>(gca + LPR * C);        // [LPR][C] T
-    int* cb = reinterpret_cast<int*>(gcb + LPR * C);   // [2][C] cloud-base level (lowest activating level), two stages in flight
-    unsigned long long* mbar_round = reinterpret_cast<unsigned long long*>(cb + 2 * C);  // round barrier: one arrival per warp
+    // [2][C] cloud base of the column, two stages in flight: (lowest activating level << 32) | bits of its ARG rate, so that an
+    // atomicMin keeps the lowest level together with ITS rate and the activation source needs no second ARG evaluation
+    unsigned long long* cb = reinterpret_cast<unsigned long long*>(gcb + LPR * C);
+    unsigned long long* mbar_round = cb + 2 * C;  // round barrier: one arrival per warp
     unsigned long long* mbar = mbar_round + 1 + warp;                                     // completion of this warp's u^n box
 
     // row of level k inside a plane: even levels first, then the odd ones.  The pair rows (k0, k0 + 1) of consecutive
@@ -179,7 +182,8 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
         }
         w1c = A.w1[gc]; qsurf = A.q_surf[gc]; Ndc = A.Nd[gc];
     }
-    if (j == 0) { cb[c] = INT_MAX; cb[C + c] = INT_MAX; }
+    constexpr unsigned long long CB_NONE = ~0ull;
+    if (j == 0) { cb[c] = CB_NONE; cb[C + c] = CB_NONE; }
     if (tid == 0) {
         mbar_init(mbar_round, NWARP);
         for (int w = 0; w < NWARP; ++w) mbar_init(mbar_round + 1 + w, 1);
@@ -229,7 +233,8 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
         const float rw2 = 2.f * rw;
         const float surf_flux[3] = {0.f, rw * qsurf, rw * Ndc * (1.f - qsurf) / 1.225f};
         const bool fcc_tot = sw.qtot_flux_correction != 0;
-        int cbk = INT_MAX;
+        unsigned cbk = ~0u;   // cloud-base level of this stage (none: all ones)
+        float cb_rate = 0.f;  // its ARG rate
 
 #pragma unroll 1
         for (int r = 0; r < R; ++r) {
@@ -356,23 +361,28 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
             long long tcA = tc3, tcB = tc3, tcC = tc3, tcD = tc3;
 #endif
             round_phase ^= 1u;
-            if (r == 0) cbk = cb[par * C + c];  // complete: its last atomicMin precedes the owner's arrival at this round's barrier
+            if (r == 0) {  // complete: its last atomicMin precedes the owner's arrival at this round's barrier
+                const unsigned long long v = cb[par * C + c];
+                cbk = unsigned(v >> 32);
+                cb_rate = __uint_as_float(unsigned(v));
+            }
             // The slot just consumed serves the NEXT stage's candidates: every thread read it after the wait of round 0, i.e.
             // before it arrived at round 1's barrier, whose wait this thread has passed; the next writers (atomicMin in the
             // next stage) have passed the wait of this stage's LAST round, for which this warp must have arrived (R >= 3;
             // R = 2: the stage barrier)
-            if (r == 1 && j == 0) cb[par * C + c] = INT_MAX;
+            if (r == 1 && j == 0) cb[par * C + c] = CB_NONE;
             if (real && active) {
-                // activation source: the rate at the cloud-base level found one stage ago (or at every level, local_activation);
-                // re-evaluated here from the same state instead of being stored per level
+                // activation source: the rate at the cloud-base level found one stage ago (or at every level, local_activation)
                 F2 act = f2(0.f);
                 if (k1d) {
                     if (loc) {
                         const F2 S = supersaturation_x2(P.td_R_v, a.rho, a.q_tot, a.q_liq + a.q_rai, a.q_ice, g);
                         if (!(S.x < S_SCREEN) && !(a.N_aer.x < 1.1920929e-07f)) act.x = arg_rate(a, 0, k0, rw);
                         if (!(S.y < S_SCREEN) && !(a.N_aer.y < 1.1920929e-07f)) act.y = arg_rate(a, 1, k0 + 1, rw);
-                    } else if ((cbk >> 1) == (k0 >> 1)) {
-                        if (cbk & 1) act.y = arg_rate(a, 1, k0 + 1, rw); else act.x = arg_rate(a, 0, k0, rw);
+                    } else if ((cbk >> 1) == unsigned(k0 >> 1)) {
+                        // the rate the cloud-base search of the previous stage's post phase found for this level, from the
+                        // same state and the same ρw: no second evaluation
+                        if (cbk & 1u) act.y = cb_rate; else act.x = cb_rate;
                     }
                 }
                 F2 tend[NV];
@@ -437,9 +447,46 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
 #ifdef KID_EXP_TIMING
             tcC = clock64();
 #endif
+            if (do_post && active) {
+                // aux of the state just formed, as the next rhs! call starts with (precompute_aux_thermo!,
+                // precompute_aux_precip!, precompute_aux_activation!: K1DModel/ode_utils.jl:33-38)
+                thermo_point_x2<MOIST>(P.td_R_v, y, rd, g, a);
+                F2 vq, vN;
+                terminal_velocities_x2(P, sw, a, vq, vN);
+                pa[VT1 * sV] = vq.x; pa[VT1 * sV + HO] = vq.y;
+                pa[VT2 * sV] = vN.x; pa[VT2 * sV + HO] = vN.y;
+                if (k1d && !loc) {
+                    // find_cloud_base! (K1DModel/tendency.jl:21-32): the lowest level with a positive ARG rate; the
+                    // accumulator starts at level 1 and is replaced only while its S is 0 and the candidate's S is > 0 (so a
+                    // NEGATIVE rate at level 1 sticks).  Once this thread has a candidate its higher levels are skipped.
+                    // A candidate is published at once, and a level above an already published candidate of the column (any
+                    // thread's; the rounds climb) can never be the lowest: its ARG evaluation is skipped.  A stale read of the
+                    // slot only costs an evaluation.
+                    const unsigned cb_seen = reinterpret_cast<volatile unsigned*>(&cb[parn * C + c])[1];  // level (high word)
+                    if (first == INT_MAX && unsigned(k0) < cb_seen) {
+                        const F2 S = supersaturation_x2(P.td_R_v, a.rho, a.q_tot, a.q_liq + a.q_rai, a.q_ice, g);
+                        float rate = 0.f;
+                        if (!(S.x < S_SCREEN) && !(a.N_aer.x < 1.1920929e-07f)) {
+                            rate = arg_rate(a, 0, k0, rw_n);
+                            if ((k0 == 0) ? (rate != 0.f) : (rate > 0.f)) first = k0;
+                        }
+                        if (first == INT_MAX && !(S.y < S_SCREEN) && !(a.N_aer.y < 1.1920929e-07f)) {
+                            rate = arg_rate(a, 1, k0 + 1, rw_n);
+                            if (rate > 0.f) first = k0 + 1;
+                        }
+                        if (first != INT_MAX)
+                            atomicMin(&cb[parn * C + c], (static_cast<unsigned long long>(first) << 32) | __float_as_uint(rate));
+                    }
+                    if (r == R - 1) first = INT_MAX;
+                }
+            }
+#ifdef KID_EXP_TIMING
+            tcD = clock64();
+#endif
             // u^n of this warp's levels in the NEXT round that combines with it (stages 2 and 3 of a step) — a (C columns x LW
             // levels x NV variables) box of the device state — straight into the warp's staging rows with ONE TMA instruction:
-            // it lands while the next round's stencil and sources are evaluated.  The box is private to the warp, so the only
+            // it lands while the next round's stencil and sources are evaluated (requested after the post phase, so that a step's
+            // store of the same box has long been read).  The box is private to the warp, so the only
             // ordering needed is that all its lanes are done with the previous box.
             {
                 const bool last = (r + 1 == R);
@@ -457,39 +504,6 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
                 }
             }
 #ifdef KID_EXP_TIMING
-            tcD = clock64();
-#endif
-            if (do_post && active) {
-                // aux of the state just formed, as the next rhs! call starts with (precompute_aux_thermo!,
-                // precompute_aux_precip!, precompute_aux_activation!: K1DModel/ode_utils.jl:33-38)
-                thermo_point_x2<MOIST>(P.td_R_v, y, rd, g, a);
-                F2 vq, vN;
-                terminal_velocities_x2(P, sw, a, vq, vN);
-                pa[VT1 * sV] = vq.x; pa[VT1 * sV + HO] = vq.y;
-                pa[VT2 * sV] = vN.x; pa[VT2 * sV + HO] = vN.y;
-                if (k1d && !loc) {
-                    // find_cloud_base! (K1DModel/tendency.jl:21-32): the lowest level with a positive ARG rate; the
-                    // accumulator starts at level 1 and is replaced only while its S is 0 and the candidate's S is > 0 (so a
-                    // NEGATIVE rate at level 1 sticks).  Once this thread has a candidate its higher levels are skipped.
-                    // A candidate is published at once, and a level above an already published candidate of the column (any
-                    // thread's; the rounds climb) can never be the lowest: its ARG evaluation is skipped.  A stale read of the
-                    // slot only costs an evaluation.
-                    const int cb_seen = *reinterpret_cast<volatile int*>(&cb[parn * C + c]);
-                    if (first == INT_MAX && k0 < cb_seen) {
-                        const F2 S = supersaturation_x2(P.td_R_v, a.rho, a.q_tot, a.q_liq + a.q_rai, a.q_ice, g);
-                        if (!(S.x < S_SCREEN) && !(a.N_aer.x < 1.1920929e-07f)) {
-                            const float S_Nl = arg_rate(a, 0, k0, rw_n);
-                            if ((k0 == 0) ? (S_Nl != 0.f) : (S_Nl > 0.f)) first = k0;
-                        }
-                        if (first == INT_MAX && !(S.y < S_SCREEN) && !(a.N_aer.y < 1.1920929e-07f)) {
-                            if (arg_rate(a, 1, k0 + 1, rw_n) > 0.f) first = k0 + 1;
-                        }
-                        if (first != INT_MAX) atomicMin(&cb[parn * C + c], first);
-                    }
-                    if (r == R - 1) first = INT_MAX;
-                }
-            }
-#ifdef KID_EXP_TIMING
             if (lane == 0 && real) {
                 const long long tc4 = clock64();
                 atomicAdd(&g_pair_cycles[0][r], (unsigned long long)(tc3 - tc2));
@@ -498,8 +512,9 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
                 atomicAdd(&g_pair_cycles[3][r], (unsigned long long)(tcA - tc3));
                 atomicAdd(&g_pair_cycles[4][r], (unsigned long long)(tcB - tcA));
                 atomicAdd(&g_pair_cycles[5][r], (unsigned long long)(tcC - tcB));
-                atomicAdd(&g_pair_cycles[6][r], (unsigned long long)(tcD - tcC));
-                atomicAdd(&g_pair_cycles[7][r], (unsigned long long)(tc4 - tcD));
+                atomicAdd(&g_pair_cycles[7][r], (unsigned long long)(tcD - tcC));
+                atomicAdd(&g_pair_cycles[6][r], (unsigned long long)(tc4 - tcD));
+                atomicAdd(&g_pair_work[warp & 7][r], (unsigned long long)((tc2 - tc0) + (tc4 - tc3)));
             }
 #endif
         }

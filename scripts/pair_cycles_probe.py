@@ -11,11 +11,16 @@ cs = M.k1d_ensemble_case(np.float32, nc=262144, n_elem=128, ic="device", order="
 h = M.make_handle(cs, Handle)
 h.step(0.0, 480); h.synchronize()
 lib = KL.load_library()
-buf = (C.c_ulonglong * 64)()
+buf = (C.c_ulonglong * 128)()
 lib.kid_exp_pair_cycles(buf, 1)
 h.set_steps_per_launch(10); h.step(480.0, 10); h.synchronize()
 lib.kid_exp_pair_cycles(buf, 0)
-a = np.array(list(buf), dtype=np.float64).reshape(8, 8)[:, :4]
+a = np.array(list(buf)[:64], dtype=np.float64).reshape(8, 8)[:, :4]
+w = np.array(list(buf)[64:], dtype=np.float64).reshape(8, 8)[:, :4]
 tot = a.sum()
 for name, row in zip(("wait at round barrier", "READ (stencil)", "sources", "activation + tendencies", "wait for the u^n box", "combine + stores", "u^n prefetch issue", "post (vt, cloud base)"), a):
     print(f"{name:24s}", " ".join(f"r{r}: {100*v/tot:5.1f}%" for r, v in enumerate(row)), f" | {100*row.sum()/tot:5.1f}%")
+print("work (cycles outside the barrier wait) per warp and round, relative to the mean of the round:")
+for i, row in enumerate(w):
+    print(f"warp {i}:", " ".join(f"r{r}: {v / w[:, r].mean():5.2f}" for r, v in enumerate(row)), f" | stage total {row.sum() / w.sum(axis=1).mean():5.2f}")
+print("round maximum / round mean:", " ".join(f"r{r}: {w[:, r].max() / w[:, r].mean():5.2f}" for r in range(4)), "| sum of round maxima / mean stage total:", f"{w.max(axis=0).sum() / w.sum(axis=1).mean():5.2f}")
