@@ -108,7 +108,8 @@ cudaError_t gconsts(const KArgs<float>& a, const DevParams<float>& P, float4* ou
 extern "C" int kid_exp_pair_cycles(unsigned long long* out, int reset) {
     if (cudaMemcpyFromSymbol(out, kid::g_pair_cycles, sizeof(kid::g_pair_cycles)) != cudaSuccess) return 1;
     if (cudaMemcpyFromSymbol(out + 64, kid::g_pair_work, sizeof(kid::g_pair_work)) != cudaSuccess) return 1;
-    if (reset) { unsigned long long z[8][8] = {}; cudaMemcpyToSymbol(kid::g_pair_cycles, z, sizeof(z)); cudaMemcpyToSymbol(kid::g_pair_work, z, sizeof(z)); }
+    if (cudaMemcpyFromSymbol(out + 128, kid::g_pair_wait, sizeof(kid::g_pair_wait)) != cudaSuccess) return 1;
+    if (reset) { unsigned long long z[8][8] = {}; cudaMemcpyToSymbol(kid::g_pair_cycles, z, sizeof(z)); cudaMemcpyToSymbol(kid::g_pair_work, z, sizeof(z)); cudaMemcpyToSymbol(kid::g_pair_wait, z, sizeof(z)); }
     return 0;
 }
 namespace kid {

@@ -42,7 +42,11 @@ inline size_t k1d_pair_smem_bytes() {
     using L = Lay<MOIST, KID_PRECIP_2M>;
     return (size_t(L::NV + 2) * (PAIR_NZ + 2) * PAIR_C + size_t(PAIR_NZ) * PAIR_C + size_t(L::NV) * PAIR_LPR * PAIR_C) * sizeof(float) +
            size_t(PAIR_LPR) * PAIR_C * (sizeof(float2) + sizeof(float)) + size_t(2) * PAIR_C * sizeof(unsigned long long) +
-           size_t(1 + PAIR_C * PAIR_TJ / 32) * sizeof(unsigned long long);
+           size_t(1 + PAIR_C * PAIR_TJ / 32) * sizeof(unsigned long long)
+#ifdef KID_EXP_SMEM_PAD  // experiment: fewer resident tiles per SM
+           + KID_EXP_SMEM_PAD
+#endif
+        ;
 }
 
 // ---- sm_90+/sm_100 asynchronous-copy plumbing (PTX): mbarrier, bulk copy global -> shared (UBLKCP), cp.async (LDGSTS)
@@ -127,6 +131,7 @@ __global__ void grid_consts_kernel(const float* __restrict__ T, const float* __r
 
 #ifdef KID_EXP_TIMING
 // experiment build (scripts/build_variant.sh timing -DKID_EXP_TIMING): cycles the warps spend between phases, per round
+__device__ unsigned long long g_pair_wait[8][8];    // [warp][round]: cycles in the round-barrier wait
 __device__ unsigned long long g_pair_work[8][8];    // [warp][round]: cycles outside the round-barrier wait
 __device__ unsigned long long g_pair_cycles[8][8];  // [barrier wait | READ | sources | act + tendencies | u^n wait | combine + stores | prefetch issue | post][round]
 #endif
@@ -514,6 +519,7 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
                 atomicAdd(&g_pair_cycles[5][r], (unsigned long long)(tcC - tcB));
                 atomicAdd(&g_pair_cycles[7][r], (unsigned long long)(tcD - tcC));
                 atomicAdd(&g_pair_cycles[6][r], (unsigned long long)(tc4 - tcD));
+                atomicAdd(&g_pair_wait[warp & 7][r], (unsigned long long)(tc3 - tc2));
                 atomicAdd(&g_pair_work[warp & 7][r], (unsigned long long)((tc2 - tc0) + (tc4 - tc3)));
             }
 #endif
