@@ -12,6 +12,12 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 tail -1 gpurun_out/ncu_launches.log | cut -c1-300
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k1d_pair -s 9 -c 1 -f -o gpurun_out/k1d_pair_r02 python bench.py --steps 20 --warmup 3 --cpu-seconds 0 --no-parity --k2d-steps 0 > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log | cut -c1-200
+mkdir -p gpurun_out/sum
+python scripts/ncu_summary.py gpurun_out/k1d_pair_r02.ncu-rep > gpurun_out/sum/k1d_pair_f32_2M.json
+python scripts/ncu_sass_hist.py gpurun_out/k1d_pair_r02.ncu-rep 40 > gpurun_out/sum/k1d_pair_f32_2M_sass.txt
+ncu -i gpurun_out/k1d_pair_r02.ncu-rep --page details > gpurun_out/sum/k1d_pair_f32_2M_details.txt 2>/dev/null
+timeout 600 python scripts/bench_configs.py > gpurun_out/configs.log 2>&1; tail -3 gpurun_out/configs.log | cut -c1-300
+nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/f32x2_peak scripts/microbench/f32x2_peak.cu 2>/dev/null && /tmp/f32x2_peak > gpurun_out/f32x2_peak.jsonl 2>&1; tail -3 gpurun_out/f32x2_peak.jsonl
 for f in bench_n1 bench_n1_hash bench_ref; do python -c "
 import json;d=json.load(open('gpurun_out/$f.json'));print('$f', d.get('value'), d.get('ms_per_step'), (d.get('e2e') or {}).get('value'), d.get('clocks'), d.get('parity_sample'), (d.get('secondary') or {}).get('k2d'))"; done
 ls -la gpurun_out

@@ -80,3 +80,26 @@ def test_reordering_columns_does_not_change_any_member():
     dperm = M.warp_coherent_order(dcase)
     dord = M.reorder_columns(dcase, dperm)
     assert np.array_equal(dord.device_ic["p0"], dcase.device_ic["p0"][dperm])
+
+
+def test_nested_bin_order_groups_members_by_profile_then_updraft():
+    """The storage order of large ensembles (model.nested_bin_order): a permutation; neighbouring members are close in the
+    primary key (surface pressure) AND, inside a primary bin, in the secondary key; small ensembles fall back to the Z-order
+    curve.  warp_coherent_order picks it for ensembles that differ in the sounding, w1 and Nd."""
+    rng = np.random.default_rng(5)
+    n = 1 << 14
+    p0, w1, nd = rng.uniform(0.98e5, 1.02e5, n), rng.uniform(1.0, 2.2, n), rng.uniform(7.0, 8.5, n)
+    perm = M.nested_bin_order(p0, w1, nd)
+    assert sorted(perm.tolist()) == list(range(n))
+    d_p0 = np.abs(np.diff(p0[perm])).mean() / np.abs(np.diff(p0)).mean()
+    d_w1 = np.abs(np.diff(w1[perm])).mean() / np.abs(np.diff(w1)).mean()
+    assert d_p0 < 0.05 and d_w1 < 0.2, (d_p0, d_w1)     # random order: both ratios are 1
+    small = M.nested_bin_order(p0[:100], w1[:100], nd[:100])
+    assert sorted(small.tolist()) == list(range(100))
+    case = M.k1d_ensemble_case(np.float32, nc=4096, ic="device", order="hash", **KW)
+    perm = M.warp_coherent_order(case)
+    ref = M.nested_bin_order(np.asarray(case.device_ic["p0"], dtype=np.float64), np.asarray(case.col_scalars[COL_W1], dtype=np.float64),
+                             np.log10(np.asarray(case.col_scalars[COL_PRESCRIBED_ND], dtype=np.float64)))
+    assert np.array_equal(perm, ref)
+    sorted_case = M.k1d_ensemble_case(np.float32, nc=4096, ic="device", order="sorted", **KW)
+    assert np.array_equal(sorted_case.meta["column_perm"], ref)   # the benchmark's "sorted" order is this order
