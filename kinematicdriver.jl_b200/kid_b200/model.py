@@ -293,6 +293,29 @@ def slice_columns(case: Case, a: int, b: int) -> Case:
                 meta=case.meta, device_ic=case.device_ic)
 
 
+def take_columns(case: Case, idx: np.ndarray) -> Case:
+    """The columns `idx` (any subset, in that order) of an ensemble case as a case of their own — what a rank of a sharded run
+    owns when the shards are dealt out in blocks (bench.py: round-robin blocks of the sorted ensemble give every rank the same
+    mix of members)."""
+    import copy
+    idx = np.asarray(idx)
+    out = copy.copy(case)
+    out.cfg = copy.copy(case.cfg)
+    out.cfg.nc = int(idx.size)
+    out.col_scalars = {k: np.asarray(v)[idx] for k, v in case.col_scalars.items()}
+    out.column_to_set = None if case.column_to_set is None else np.asarray(case.column_to_set)[idx]
+    if case.device_ic is not None:
+        out.device_ic = dict(case.device_ic, **{k: np.asarray(v)[idx] for k, v in case.device_ic.items()
+                                                if k in ("p0", "qt", "Nd", "k", "rhod")})
+    if case.Y0 is not None:
+        out.Y0 = case.Y0[idx]
+        if np.ndim(case.ρ_dry) == 2:
+            out.ρ_dry, out.T = case.ρ_dry[idx], case.T[idx]
+    if "column_perm" in case.meta:
+        out.meta = dict(case.meta, column_perm=np.asarray(case.meta["column_perm"])[idx])
+    return out
+
+
 def reorder_columns(case: Case, perm: np.ndarray) -> Case:
     """The same ensemble with column i of the result = column perm[i] of `case`.  Columns are independent, so any order
     gives the same per-column results; the order decides which members share a warp (32 neighbouring columns)."""
