@@ -112,7 +112,7 @@ typedef struct kid_config {
     int32_t local_activation;
     int32_t qtot_flux_correction;
     int32_t device;          /* CUDA device ordinal */
-    int32_t reserved[8];     /* reserved[0..4]: tuning overrides (0 = library default): max level-warps per tile (>= 2), columns per tile, 1 = never use the compile-time-shape kernel, 1 = never use the packed two-levels-per-thread 2M kernel, 2 = layout kernels access page-locked host buffers in place even without a column map */
+    int32_t reserved[8];     /* reserved[0..5]: tuning overrides (0 = library default): max level-warps per tile (>= 2), columns per tile, 1 = never use the compile-time-shape kernel, 1 = never use the packed two-levels-per-thread 2M kernel, 2 = layout kernels access page-locked host buffers in place even without a column map, 1 = K2D steps with the two legacy horizontal launches per stage */
     double z_min, z_max;     /* make_function_space (K1DModel/ode_utils.jl:9-21) */
     double dt;               /* TimeStepping.dt (src/Common/ode_utils.jl:12-16) */
     double domain_width;     /* K2D aux.domain_width  */

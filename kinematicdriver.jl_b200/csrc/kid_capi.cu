@@ -130,6 +130,8 @@ struct kid_handle {
     int C = 32, NW = 1;
     // K2D
     void *U = nullptr, *Y3 = nullptr, *S = nullptr, *prev_aux = nullptr, *xc = nullptr, *out2 = nullptr;
+    void* Y2 = nullptr;        // second state buffer of the single-launch horizontal kernel (swapped with Y after every stage)
+    double k2d_t_stage = 0.0;  // stage time of the last k2d_begin (the horizontal kernel of k2d_end needs ρu(t))
     // in-library neighbour exchange of a decomposed domain (kid_k2d_comm_init): NCCL communicator of the x-ring
     struct ncclComm* comm = nullptr;
     int comm_rank = 0, comm_world = 1;
@@ -324,7 +326,7 @@ KArgs<FT> make_args(kid_handle* h, double t0, int nsteps, int diag_mode, int fie
 template <class FT>
 K2DArgs<FT> make_k2d_args(kid_handle* h, double t_stage, int stage, int use_recv, int rhs_only) {
     K2DArgs<FT> a{};
-    a.Y = (FT*)h->Y; a.U = (FT*)h->U; a.dY = (FT*)h->out; a.S = (FT*)h->S; a.out = (FT*)h->out2;
+    a.Y = (FT*)h->Y; a.Yout = (FT*)h->Y2; a.U = (FT*)h->U; a.dY = (FT*)h->out; a.S = (FT*)h->S; a.out = (FT*)h->out2;
     a.rho_dry = (const FT*)h->rho_dry; a.w1 = (const FT*)h->w1; a.xc = (const FT*)h->xc;
     a.send_left = (FT*)h->send_left; a.send_right = (FT*)h->send_right;
     a.recv_left = (const FT*)h->recv_left; a.recv_right = (const FT*)h->recv_right;
@@ -477,9 +479,36 @@ double k2d_stage_time(kid_handle* h, double t_step, int stage) {
     float t = float(t_step), dt = float(h->cfg.dt);
     return double(stage == 0 ? t : (stage == 1 ? t + dt : t + dt / 2.0f));
 }
-int k2d_begin(kid_handle* h, double t_stage, int /*stage*/) {
+// style dispatch of the templated K2D kernels
+#define KID_K2D_STYLE_CASE(M, P, ...) if (h->cfg.moisture == M && h->cfg.precip == P) { constexpr int MOIST = M, PRECIP = P; __VA_ARGS__; }
+#define KID_K2D_DISPATCH(...)                                                                   \
+    KID_K2D_STYLE_CASE(KID_MOIST_EQ, KID_PRECIP_NONE, __VA_ARGS__)                              \
+    KID_K2D_STYLE_CASE(KID_MOIST_EQ, KID_PRECIP_0M, __VA_ARGS__)                                \
+    KID_K2D_STYLE_CASE(KID_MOIST_EQ, KID_PRECIP_1M, __VA_ARGS__)                                \
+    KID_K2D_STYLE_CASE(KID_MOIST_EQ, KID_PRECIP_2M, __VA_ARGS__)                                \
+    KID_K2D_STYLE_CASE(KID_MOIST_NONEQ, KID_PRECIP_NONE, __VA_ARGS__)                           \
+    KID_K2D_STYLE_CASE(KID_MOIST_NONEQ, KID_PRECIP_0M, __VA_ARGS__)                             \
+    KID_K2D_STYLE_CASE(KID_MOIST_NONEQ, KID_PRECIP_1M, __VA_ARGS__)                             \
+    KID_K2D_STYLE_CASE(KID_MOIST_NONEQ, KID_PRECIP_2M, __VA_ARGS__)
+
+// Single-launch horizontal part (k2d_horizontal_kernel): needs the Nq nodes of an element in one warp.  cfg.reserved[5] = 1
+// keeps the two legacy launches (k2d_hdiv_kernel + k2d_dss_update_kernel), which kid_rhs always uses.
+bool k2d_single_launch(const kid_handle* h) { return (32 % h->Nq == 0) && h->cfg.reserved[5] == 0; }
+
+int k2d_begin(kid_handle* h, double t_stage, int /*stage*/, bool pack_edges, bool legacy) {
     if (ensure_out(h, state_elems(h) * h->fsz)) return 1;
     if (launch_tile(h, t_stage, 1, 1, 0, 1)) return 1;
+    h->k2d_t_stage = t_stage;
+    if (!legacy && k2d_single_launch(h)) {
+        if (pack_edges) {  // decomposed domain: the rank-edge tendencies for the neighbours' DSS
+            dim3 block(128), grid((h->cfg.nz + 127) / 128);
+            if (h->f64) { KID_K2D_DISPATCH((k2d_edge_pack_kernel<double, MOIST, PRECIP><<<grid, block, 0, h->stream>>>(make_k2d_args<double>(h, t_stage, 0, 0, 0)))) }
+            else { KID_K2D_DISPATCH((k2d_edge_pack_kernel<float, MOIST, PRECIP><<<grid, block, 0, h->stream>>>(make_k2d_args<float>(h, t_stage, 0, 0, 0)))) }
+            KID_CUDA(cudaGetLastError());
+            h->launches++;
+        }
+        return 0;
+    }
     dim3 block(64), grid((h->cfg.helem + 63) / 64, h->cfg.nz);
     if (h->f64) k2d_hdiv_kernel<double><<<grid, block, 0, h->stream>>>(make_k2d_args<double>(h, t_stage, 0, 0, 0));
     else k2d_hdiv_kernel<float><<<grid, block, 0, h->stream>>>(make_k2d_args<float>(h, t_stage, 0, 0, 0));
@@ -488,6 +517,16 @@ int k2d_begin(kid_handle* h, double t_stage, int /*stage*/) {
     return 0;
 }
 int k2d_end(kid_handle* h, int stage, int use_recv, int rhs_only) {
+    if (!rhs_only && k2d_single_launch(h)) {
+        const int per_block = 128 - 2 * h->Nq;  // the first and last element of a block are halo
+        dim3 block(128), grid((h->cfg.nc + per_block - 1) / per_block, h->cfg.nz);
+        if (h->f64) { KID_K2D_DISPATCH((k2d_horizontal_kernel<double, MOIST, PRECIP><<<grid, block, 0, h->stream>>>(make_k2d_args<double>(h, h->k2d_t_stage, stage, use_recv, 0)))) }
+        else { KID_K2D_DISPATCH((k2d_horizontal_kernel<float, MOIST, PRECIP><<<grid, block, 0, h->stream>>>(make_k2d_args<float>(h, h->k2d_t_stage, stage, use_recv, 0)))) }
+        KID_CUDA(cudaGetLastError());
+        h->launches++;
+        std::swap(h->Y, h->Y2);  // the kernel wrote the new stage state into the second buffer
+        return 0;
+    }
     dim3 block(128), grid((h->cfg.nc + 127) / 128, h->cfg.nz);
     if (h->f64) k2d_dss_update_kernel<double><<<grid, block, 0, h->stream>>>(make_k2d_args<double>(h, 0.0, stage, use_recv, rhs_only));
     else k2d_dss_update_kernel<float><<<grid, block, 0, h->stream>>>(make_k2d_args<float>(h, 0.0, stage, use_recv, rhs_only));
@@ -519,6 +558,8 @@ int k2d_setup(kid_handle* h) {
     size_t st = state_elems(h) * h->fsz, plane = size_t(c.nz) * h->ncp * h->fsz, edge = size_t(KID_MAX_DSS) * c.nz * h->fsz;
     KID_CUDA(cudaMalloc(&h->U, st));
     KID_CUDA(cudaMalloc(&h->out2, st));
+    KID_CUDA(cudaMalloc(&h->Y2, st));
+    KID_CUDA(cudaMemsetAsync(h->Y2, 0, st, h->stream));
     KID_CUDA(cudaMalloc(&h->S, 2 * plane));
     KID_CUDA(cudaMalloc(&h->prev_aux, 3 * plane));
     KID_CUDA(cudaMemsetAsync(h->S, 0, 2 * plane, h->stream));
@@ -718,7 +759,7 @@ void kid_destroy(kid_handle_t* h) {
         if (h->ev_done[b]) cudaEventDestroy(h->ev_done[b]);
     }
     for (void* p : {h->colmap, h->colmap_local, h->gconst, h->ps_liq, h->ps_mix, h->prm_sets, h->col_to_set, h->Y, h->rho_dry, h->T, h->w1, h->q_surf, h->Nd, h->aux_Naer,
-                    h->out, h->staging, h->U, h->Y3, h->S, h->prev_aux, h->xc, h->out2, h->send_left, h->send_right, h->recv_left,
+                    h->out, h->staging, h->U, h->Y3, h->Y2, h->S, h->prev_aux, h->xc, h->out2, h->send_left, h->send_right, h->recv_left,
                     h->recv_right, (void*)h->obsG, (void*)h->red, (void*)h->zsin, (void*)h->cosx, (void*)h->cosz})
         if (p) cudaFree(p);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -926,7 +967,7 @@ int kid_step(kid_handle_t* h, double t0, int32_t nsteps) {
         for (int s = 0; s < nsteps; ++s) {
             double ts = h->f64 ? t0 + double(s) * h->cfg.dt : double(float(t0 + double(s) * h->cfg.dt));
             for (int stage = 0; stage < 3; ++stage) {
-                if (k2d_begin(h, k2d_stage_time(h, ts, stage), stage)) return 1;
+                if (k2d_begin(h, k2d_stage_time(h, ts, stage), stage, decomposed, false)) return 1;
                 if (decomposed && k2d_exchange_nccl(h)) return 1;
                 if (k2d_end(h, stage, decomposed ? 1 : 0, 0)) return 1;
             }
@@ -953,7 +994,7 @@ int kid_rhs(kid_handle_t* h, double t, void* dY_out) {
     KID_CUDA(cudaMemsetAsync(h->out, 0, state_elems(h) * h->fsz, h->stream));
     if (h->cfg.model == KID_MODEL_K2D) {
         if (h->cfg.helem != h->cfg.helem_global) return fail("kid_rhs is only available on an undecomposed K2D handle");
-        if (k2d_begin(h, t, 0)) return 1;
+        if (k2d_begin(h, t, 0, false, true)) return 1;
         if (k2d_end(h, 0, 0, 1)) return 1;
         return to_host_layout(h, h->out2, dY_out, h->nv);
     }
@@ -1273,7 +1314,7 @@ int kid_k2d_stage_begin(kid_handle_t* h, double t0, int32_t stage) {
     if (h->cfg.model != KID_MODEL_K2D) return fail("not a K2D handle");
     if (stage < 0 || stage > 2) return fail("stage must be 0, 1 or 2");
     double ts = h->f64 ? t0 : double(float(t0));
-    return k2d_begin(h, k2d_stage_time(h, ts, stage), stage);
+    return k2d_begin(h, k2d_stage_time(h, ts, stage), stage, true, false);
 }
 int kid_k2d_edge_buffers(kid_handle_t* h, void** send_left, void** send_right, void** recv_left, void** recv_right,
                          size_t* edge_count) {

@@ -26,6 +26,7 @@ struct K2DField {
 template <class FT>
 struct K2DArgs {
     FT* Y;          // [NV][nz][ncp] stage state (in/out)
+    FT* Yout;       // k2d_horizontal_kernel: the new stage state goes to a second buffer (other blocks still read Y); host swaps
     FT* U;          // [NV][nz][ncp] u^n of the current step
     FT* dY;         // [NV][nz][ncp]
     FT* S;          // [2][nz][ncp]
@@ -175,6 +176,159 @@ __global__ void k2d_dss_update_kernel(const K2DArgs<FT> A) {
         else if (A.stage == 1) yn = (FT(3) * u + y + A.dt * tend) / FT(4);
         else yn = (u + FT(2) * y + FT(2) * A.dt * tend) / FT(3);
         A.Y[gi] = yn;
+    }
+}
+
+// ---------------------------------------------------------------- one launch for the horizontal part of a stage
+// horizontally advected / DSS'd fields per style, in the order of kid_capi.cu::k2d_setup (src/K2DModel/tendency.jl:57-213):
+// {state variable whose flux is taken, target is an S plane, target plane}
+template <int MOIST, int PRECIP>
+__host__ __device__ constexpr int k2d_field_count() {
+    return 1 + (MOIST == KID_MOIST_NONEQ ? 2 : 0) + (PRECIP >= KID_PRECIP_1M ? 2 : 0);
+}
+template <int MOIST, int PRECIP>
+__host__ __device__ constexpr K2DField k2d_field(int f) {
+    using L = Lay<MOIST, PRECIP>;
+    if (f == 0) return {L::tot, 0, L::tot};
+    int b = 1;
+    if (MOIST == KID_MOIST_NONEQ) {
+        if (f == 1) return {L::liq, 0, L::liq};
+        if (f == 2) return {L::ice, 0, L::ice};
+        b = 3;
+    }
+    if (PRECIP == KID_PRECIP_1M) return f == b ? K2DField{L::rai, 1, 0} : K2DField{L::sno, 1, 1};
+    return f == b ? K2DField{L::Nr, 0, L::Nr} : K2DField{L::rai, 1, 0};  // 2M
+}
+
+// u/ρ at (column c, level k) exactly as k2d_hdiv_kernel forms it
+template <class FT>
+KID_DEV FT k2d_u_over_rho(const K2DArgs<FT>& A, int c, int k, FT y_tot) {
+    const FT rd = A.rho_dry[A.prof_per_column ? size_t(k) * A.ncp + c : size_t(k)];
+    const FT rho = rd + y_tot;
+    const FT rho_u = FT(0.5 * double(A.w1[c]) * A.width / A.height * A.cosz[k] * A.cosx[c] * A.ts);
+    return rho_u / rho;
+}
+// The not yet DSS'd tendency of field f at an arbitrary column (slow path: the duplicate of a node that lies in another
+// thread block, and the rank-edge pack): vertical part from dY / S plus the horizontal weak divergence of the column's element.
+template <class FT, int MOIST, int PRECIP>
+KID_DEV FT k2d_field_tendency_at(const K2DArgs<FT>& A, K2DField fd, int c, int k) {
+    using L = Lay<MOIST, PRECIP>;
+    const int Nq = A.Nq, e = c / Nq, i = c % Nq;
+    const size_t plane = size_t(A.nz) * A.ncp, row = size_t(k) * A.ncp;
+    FT acc = FT(0);
+    for (int q = 0; q < Nq; ++q) {
+        const int cq = e * Nq + q;
+        const FT uor = k2d_u_over_rho(A, cq, k, A.Y[size_t(L::tot) * plane + row + cq]);
+        acc += A.D[q * Nq + i] * (A.w[q] * (uor * A.Y[size_t(fd.adv_var) * plane + row + cq]));
+    }
+    const FT hd = -acc / A.w[i] * (FT(2) / FT(A.dxe));
+    FT t = ((fd.is_S ? A.S : A.dY) + size_t(fd.plane) * plane + row)[c];
+    t += -hd;
+    return t;
+}
+// rank-edge pack of a decomposed domain: the tendencies of the first and last column, for the neighbour ranks' DSS
+template <class FT, int MOIST, int PRECIP>
+__global__ void k2d_edge_pack_kernel(const K2DArgs<FT> A) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= A.nz) return;
+    constexpr int NF = k2d_field_count<MOIST, PRECIP>();
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        const K2DField fd = k2d_field<MOIST, PRECIP>(f);
+        A.send_left[size_t(f) * A.nz + k] = k2d_field_tendency_at<FT, MOIST, PRECIP>(A, fd, 0, k);
+        A.send_right[size_t(f) * A.nz + k] = k2d_field_tendency_at<FT, MOIST, PRECIP>(A, fd, A.nc - 1, k);
+    }
+}
+
+// One thread per (column, level).  A block is 128 neighbouring columns = whole elements (the Nq nodes of an element are
+// neighbouring lanes of one warp, Nq in {2, 4, 8}); its first and last ELEMENT are halo: every thread forms the not yet DSS'd
+// tendencies of its column — horizontal weak divergence with the D-matrix row applied across the lanes (coalesced loads; the
+// arithmetic of k2d_hdiv_kernel) — and the 128 - 2 Nq interior columns then take their duplicate node's value from shared
+// memory (weighted_dss!; periodic wrap, or the received rank edge), assemble in the reference's order and do the SSPRK33 stage
+// combine (the arithmetic of k2d_dss_point).  Replaces k2d_hdiv_kernel + k2d_dss_update_kernel for kid_step.
+template <class FT, int MOIST, int PRECIP>
+__global__ void __launch_bounds__(128) k2d_horizontal_kernel(const K2DArgs<FT> A) {
+    using L = Lay<MOIST, PRECIP>;
+    constexpr int NV = L::NV, NF = k2d_field_count<MOIST, PRECIP>();
+    __shared__ FT tvs[NF][128];
+    __shared__ FT Ds[KID_MAX_NQ * KID_MAX_NQ], ws[KID_MAX_NQ];
+    const int tid = threadIdx.x, k = blockIdx.y, Nq = A.Nq;
+    const int c_raw = int(blockIdx.x) * (128 - 2 * Nq) - Nq + tid;   // first / last Nq threads: halo elements
+    // periodic domain: the halo wraps around; decomposed domain: beyond the rank's columns there is nothing (the rank edges
+    // take the received values)
+    const bool outside = c_raw < 0 || c_raw >= A.nc;
+    const int c = outside ? (c_raw < 0 ? c_raw + A.nc : c_raw - A.nc) : c_raw;
+    const bool valid = !(outside && A.use_recv) && c >= 0 && c < A.nc;
+    const bool interior = valid && !outside && tid >= Nq && tid < 128 - Nq;
+    const int ni = tid % Nq, lane = tid & 31, lane0 = lane - ni;
+    const size_t plane = size_t(A.nz) * A.ncp, row = size_t(k) * A.ncp;
+    if (tid < Nq * Nq) Ds[tid] = A.D[tid];
+    if (tid < Nq) ws[tid] = A.w[tid];
+    // ---- all global loads first
+    FT y[NV], tend[NV], u[NV], Sv[2] = {FT(0), FT(0)};
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        y[v] = tend[v] = u[v] = FT(0);
+        if (valid) {
+            const size_t gi = size_t(v) * plane + row + c;
+            y[v] = A.Y[gi];
+            tend[v] = A.dY[gi];
+            if (A.stage != 0 && interior) u[v] = A.U[gi];
+        }
+    }
+    if constexpr (L::has_pr) {
+        if (valid) {
+            Sv[0] = A.S[row + c];
+            if constexpr (PRECIP == KID_PRECIP_1M) Sv[1] = A.S[plane + row + c];
+        }
+    }
+    const FT uor = valid ? k2d_u_over_rho(A, c, k, y[L::tot]) : FT(0);
+    __syncthreads();
+    // ---- horizontal weak divergence: -(1/w_i) Σ_q D_qi w_q f_q · 2/Δx_e, f = (ρu/ρ) x
+    const FT w_own = ws[ni], scale = FT(2) / FT(A.dxe);
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        const K2DField fd = k2d_field<MOIST, PRECIP>(f);
+        const FT wflux = w_own * (uor * y[fd.adv_var]);
+        FT acc = FT(0);
+        for (int q = 0; q < Nq; ++q) acc += Ds[q * Nq + ni] * __shfl_sync(0xffffffffu, wflux, lane0 + q);
+        const FT hd = -acc / w_own * scale;
+        FT& val = fd.is_S ? Sv[fd.plane] : tend[fd.plane];
+        val += -hd;
+        tvs[f][tid] = val;
+    }
+    __syncthreads();
+    if (!interior) return;
+    // ---- weighted_dss!: mean of the two copies of an element-edge node (the neighbouring thread)
+    const bool left_edge = (ni == 0), right_edge = (ni == Nq - 1);
+    if (left_edge || right_edge) {
+        const bool from_recv = A.use_recv && ((left_edge && c == 0) || (right_edge && c == A.nc - 1));
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            const K2DField fd = k2d_field<MOIST, PRECIP>(f);
+            const FT pv = from_recv ? (left_edge ? A.recv_left : A.recv_right)[size_t(f) * A.nz + k]
+                                    : tvs[f][left_edge ? tid - 1 : tid + 1];
+            FT& val = fd.is_S ? Sv[fd.plane] : tend[fd.plane];
+            val = left_edge ? (pv + val) / FT(2) : (val + pv) / FT(2);
+        }
+    }
+    // ---- assembly in the reference's order, SSPRK33 stage combine
+    if constexpr (PRECIP == KID_PRECIP_1M) {
+        tend[L::tot] += Sv[0] + Sv[1]; tend[L::rai] += Sv[0]; tend[L::sno] += Sv[1];
+    } else if constexpr (PRECIP == KID_PRECIP_2M) {
+        tend[L::tot] += Sv[0]; tend[L::rai] += Sv[0];
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const size_t gi = size_t(v) * plane + row + c;
+        const FT yv = y[v];
+        const FT uu = (A.stage == 0) ? yv : u[v];
+        if (A.stage == 0) A.U[gi] = yv;
+        FT yn;
+        if (A.stage == 0) yn = yv + A.dt * tend[v];
+        else if (A.stage == 1) yn = (FT(3) * uu + yv + A.dt * tend[v]) / FT(4);
+        else yn = (uu + FT(2) * yv + FT(2) * A.dt * tend[v]) / FT(3);
+        A.Yout[gi] = yn;
     }
 }
 

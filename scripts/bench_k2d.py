@@ -11,7 +11,7 @@ from kid_b200 import k2d, model as M
 from kid_b200.lib import Handle
 
 ap = argparse.ArgumentParser(); ap.add_argument("--steps", type=int, default=200); ap.add_argument("--weak", action="store_true")
-ap.add_argument("--exchange", default="lib", choices=["lib", "torch"]); ap.add_argument("--ft", default="f32"); ap.add_argument("--tile-c", type=int, default=0); ap.add_argument("--nw", type=int, default=0)
+ap.add_argument("--exchange", default="lib", choices=["lib", "torch"]); ap.add_argument("--ft", default="f32"); ap.add_argument("--tile-c", type=int, default=0); ap.add_argument("--nw", type=int, default=0); ap.add_argument("--legacy", type=int, default=0, help="1: two legacy horizontal launches per stage")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -26,6 +26,7 @@ kw = dict(nx=nx, nz=256, npoly=3, moisture_choice="NonEquilibriumMoisture", prec
 cs = k2d.k2d_case(FT, rank=rank, world=world, device=local, **kw)
 if a.tile_c: cs.cfg.reserved[1] = a.tile_c
 if a.nw: cs.cfg.reserved[0] = a.nw
+if a.legacy: cs.cfg.reserved[5] = 1
 h = M.make_handle(cs, Handle)
 ring = ((k2d.LibraryRing if a.exchange == "lib" else k2d.DistributedRing)(h, dist, rank, world)) if world > 1 else None
 def step(t0, n):
