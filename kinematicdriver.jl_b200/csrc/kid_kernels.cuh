@@ -607,8 +607,12 @@ k1d_tile_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared
 // ------------------------------------------------------------------ Box model
 // One thread per box, the whole state in registers for all nsteps x 3 stages
 // (src/BoxModel/ode_utils.jl:10-22: zero -> thermo -> precip -> precip sources).
+// Float64: 4 resident blocks (128 registers, 16 warps per SM) instead of the 194 registers / 8 warps the compiler picks on its
+// own: the kernel is bound by the latency of dependent double-precision chains (1 M boxes, Precipitation1M: 4.35e9 -> 7.28e9
+// box-steps/s with 316 B of spills; Precipitation2M unchanged).  Float32 fits in 90 registers either way.
+template <class FT> constexpr int box_min_blocks() { return sizeof(FT) == 8 ? 4 : 1; }
 template <class FT, int MOIST, int PRECIP, class PRMSRC>
-__global__ void __launch_bounds__(128) box_step_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared) {
+__global__ void __launch_bounds__(128, box_min_blocks<FT>()) box_step_kernel(const KArgs<FT> A, const __grid_constant__ DevParams<FT> Pshared) {
     using L = Lay<MOIST, PRECIP>;
     constexpr int NV = L::NV;
     const int gc = blockIdx.x * blockDim.x + threadIdx.x;

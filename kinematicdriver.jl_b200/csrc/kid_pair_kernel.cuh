@@ -167,6 +167,8 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
     float* Ys = reinterpret_cast<float*>(smem_raw);    // [NP][NR][C]; rows NZ, NZ+1: old values of the level below a block (2 parities)
     float* rds = Ys + NP * sV;                         // [NZ][C] ρ_dry
     float* uns = rds + NZ * C + warp * (NV * LW * C);  // [NWARP][NV][LW][C] u^n of this round's levels: one TMA box per warp
+    // staging slots of a thread: row j (lower level of its pair) and row TJ + j (upper level): the two pair-rows of a warp are
+    // neighbouring rows, so a warp reads 32 consecutive slots
     float2* gca = reinterpret_cast<float2*>(rds + NZ * C + NV * LPR * C);  // [LPR][C] (ps_mix, 1/ps_liq) of this round's levels (cp.async)
     float* gcb = reinterpret_cast<float*>(gca + LPR * C);        // [LPR][C] T
     // [2][C] cloud base of the column, two stages in flight: (lowest activating level << 32) | bits of its ARG rate, so that an
@@ -255,10 +257,10 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
                     const size_t i0 = A.prof_per_column ? size_t(k0) * ncp + gc : size_t(k0);
                     const float* g0 = reinterpret_cast<const float*>(gconst + i0);
                     const float* g1 = reinterpret_cast<const float*>(gconst + i0 + (A.prof_per_column ? size_t(ncp) : size_t(1)));
-                    cp_async8(gca + (2 * j) * C + c, g0);
-                    cp_async8(gca + (2 * j + 1) * C + c, g1);
-                    cp_async4(gcb + (2 * j) * C + c, g0 + 2);
-                    cp_async4(gcb + (2 * j + 1) * C + c, g1 + 2);
+                    cp_async8(gca + j * C + c, g0);
+                    cp_async8(gca + (TJ + j) * C + c, g1);
+                    cp_async4(gcb + j * C + c, g0 + 2);
+                    cp_async4(gcb + (TJ + j) * C + c, g1 + 2);
                     cp_async_commit();
                 }
                 if (real) {
@@ -336,9 +338,9 @@ k1d_pair_kernel(const KArgs<float> A, const float4* __restrict__ gconst, const f
                 for (int v = 0; v < NV; ++v) y[v] = f2(pa[v * sV], pa[v * sV + HO]);
                 rd = f2(rda[0], rda[HO]);
                 cp_async_wait_all();
-                const float2 a0 = gca[(2 * j) * C + c], a1 = gca[(2 * j + 1) * C + c];
+                const float2 a0 = gca[j * C + c], a1 = gca[(TJ + j) * C + c];
                 g.ps_mix = f2(a0.x, a1.x); g.inv_psl = f2(a0.y, a1.y);
-                g.T = f2(gcb[(2 * j) * C + c], gcb[(2 * j + 1) * C + c]);
+                g.T = f2(gcb[j * C + c], gcb[(TJ + j) * C + c]);
                 g.lam = liquid_fraction_x2(P, g.T);
                 // G(T): only rain evaporation reads it; straight from global memory inside that branch
                 const size_t i0 = A.prof_per_column ? size_t(k0) * ncp + gc : size_t(k0);
