@@ -489,6 +489,9 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": world * state_bytes / e2e_steps,
                     "d2h_bytes_per_step": world * state_bytes / e2e_steps, "resident_fraction": e2e_value / value,
+                    # what the end-to-end leg moved between host and devices, all ranks together (the ranks share one host
+                    # memory system: at N = 8 this, not the GPUs, bounds the leg)
+                    "host_transfer_gbs_all_ranks": 2 * world * state_bytes / (float(te.item()) * 1e-3) / 1e9,
                     "member_index_order_host_arrays": ({"value": e2e_user, "of_sorted_host_arrays": e2e_user / e2e_value,
                                                         "how": "every pipeline chunk = a contiguous block of the caller's rows stored in its own warp-coherent order "
                                                                "(block-local kid_set_column_map: copy engine + permutation on the device)"}
