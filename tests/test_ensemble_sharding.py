@@ -103,3 +103,29 @@ def test_nested_bin_order_groups_members_by_profile_then_updraft():
     assert np.array_equal(perm, ref)
     sorted_case = M.k1d_ensemble_case(np.float32, nc=4096, ic="device", order="sorted", **KW)
     assert np.array_equal(sorted_case.meta["column_perm"], ref)   # the benchmark's "sorted" order is this order
+
+
+def test_round_robin_block_shards_cover_the_ensemble_and_take_columns_slices_everything():
+    """bench.py --gpus N: blocks of 4096 sorted columns are dealt round-robin (every rank gets the same mix of members);
+    model.take_columns gives a rank its columns of a host-built or device-built case."""
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("bench", Path(__file__).resolve().parents[1] / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    total = 3 * bench.SHARD_BLOCK * 4 + 100
+    for world in (1, 2, 4, 8):
+        parts = [bench.shard_columns(total, r, world) for r in range(world)]
+        assert sorted(np.concatenate(parts).tolist()) == list(range(total))
+        assert max(p.size for p in parts) - min(p.size for p in parts) <= bench.SHARD_BLOCK
+        assert all(np.all(np.diff(p) > 0) for p in parts)
+    full = M.k1d_ensemble_case(np.float32, nc=96, n_profiles=4, order="sorted", **KW)
+    idx = np.array([5, 6, 7, 40, 41, 90])
+    sub = M.take_columns(full, idx)
+    assert sub.cfg.nc == 6 and full.cfg.nc == 96
+    assert np.array_equal(sub.Y0, full.Y0[idx]) and np.array_equal(sub.ρ_dry, full.ρ_dry[idx])
+    assert np.array_equal(sub.col_scalars[COL_W1], full.col_scalars[COL_W1][idx])
+    dev = M.k1d_ensemble_case(np.float32, nc=96, ic="device", order="sorted", **KW)
+    sd = M.take_columns(dev, idx)
+    assert np.array_equal(sd.device_ic["p0"], dev.device_ic["p0"][idx])
+    assert np.array_equal(sd.meta["column_perm"], np.asarray(dev.meta["column_perm"])[idx])
