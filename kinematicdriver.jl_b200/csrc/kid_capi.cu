@@ -501,7 +501,7 @@ int k2d_begin(kid_handle* h, double t_stage, int /*stage*/, bool pack_edges, boo
     h->k2d_t_stage = t_stage;
     if (!legacy && k2d_single_launch(h)) {
         if (pack_edges) {  // decomposed domain: the rank-edge tendencies for the neighbours' DSS
-            dim3 block(128), grid((h->cfg.nz + 127) / 128);
+            dim3 block(128), grid((2 * KID_MAX_DSS * h->cfg.nz + 127) / 128);
             if (h->f64) { KID_K2D_DISPATCH((k2d_edge_pack_kernel<double, MOIST, PRECIP><<<grid, block, 0, h->stream>>>(make_k2d_args<double>(h, t_stage, 0, 0, 0)))) }
             else { KID_K2D_DISPATCH((k2d_edge_pack_kernel<float, MOIST, PRECIP><<<grid, block, 0, h->stream>>>(make_k2d_args<float>(h, t_stage, 0, 0, 0)))) }
             KID_CUDA(cudaGetLastError());

@@ -229,15 +229,17 @@ KID_DEV FT k2d_field_tendency_at(const K2DArgs<FT>& A, K2DField fd, int c, int k
 // rank-edge pack of a decomposed domain: the tendencies of the first and last column, for the neighbour ranks' DSS
 template <class FT, int MOIST, int PRECIP>
 __global__ void k2d_edge_pack_kernel(const K2DArgs<FT> A) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= A.nz) return;
+    // one thread per (level, side, field): the pack sits on the critical path of every stage of a decomposed run
     constexpr int NF = k2d_field_count<MOIST, PRECIP>();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = t % A.nz, side = (t / A.nz) % 2, f = t / (2 * A.nz);
+    if (f >= NF) return;
+    K2DField fd = k2d_field<MOIST, PRECIP>(0);
 #pragma unroll
-    for (int f = 0; f < NF; ++f) {
-        const K2DField fd = k2d_field<MOIST, PRECIP>(f);
-        A.send_left[size_t(f) * A.nz + k] = k2d_field_tendency_at<FT, MOIST, PRECIP>(A, fd, 0, k);
-        A.send_right[size_t(f) * A.nz + k] = k2d_field_tendency_at<FT, MOIST, PRECIP>(A, fd, A.nc - 1, k);
-    }
+    for (int g = 1; g < NF; ++g)
+        if (g == f) fd = k2d_field<MOIST, PRECIP>(g);
+    const FT v = k2d_field_tendency_at<FT, MOIST, PRECIP>(A, fd, side ? A.nc - 1 : 0, k);
+    (side ? A.send_right : A.send_left)[size_t(f) * A.nz + k] = v;
 }
 
 // One thread per (column, level).  A block is 128 neighbouring columns = whole elements (the Nq nodes of an element are
