@@ -1,29 +1,32 @@
 // k1d_pair_kernel — the headline kernel: K1DModel / col_sed, Precipitation2M (SB2006), Float32, 128 levels, one
-// parameter set shared by the ensemble (BASELINE configs[3]).
+// parameter set shared by the ensemble (BASELINE configs[3]).  DESIGN.md §3.1a; measurements in profiles/README.md.
 //
-// Same tile design as k1d_tile_kernel (kid_kernels.cuh: one CTA owns 32 columns x all levels in shared memory for all
-// SSPRK33 stages of a launch; lanes = neighbouring columns; rounds over blocks of levels with a READ phase that turns
-// the OLD neighbours into advective tendencies, a barrier, and a WRITE phase that applies sources + stage combine in
-// place), with two changes that cut the issued instructions per grid point (the kernel is issue-bound):
+// Same tile idea as k1d_tile_kernel (kid_kernels.cuh: one CTA owns a tile of columns x all levels in shared memory for all
+// SSPRK33 stages of a launch; lanes = neighbouring columns; rounds over blocks of levels with a READ phase that turns the
+// OLD neighbours into advective tendencies and a WRITE phase that applies sources + stage combine in place), built for
+// fewer issued instructions per grid point and fewer stalls:
 //
 //  * every thread works on TWO vertically adjacent levels (k0, k0+1) and keeps their arithmetic in the packed
 //    Float32 instructions of sm_100a (FFMA2 / FADD2 / FMUL2, kid_f2.cuh, kid_physics_x2.cuh): one issue slot per two
 //    results, and all per-thread overhead — addressing, parameter loads, branches, loop control — is paid once per
 //    two grid points.  The two cells share their middle face, so the stencil needs 3 face fluxes and 4 loads per
-//    variable for 2 cells instead of 4 and 6.  512 threads x 128 registers per tile (16 level-pairs x 32 columns per
-//    round, 4 rounds per stage).
-//  * the two global inputs of a round never pass through registers: u^n of the stage combine — a 32 columns x 32 levels x
-//    NV variables box of the state — is fetched by ONE TMA instruction (cp.async.bulk.tensor.3d, completion on an
-//    mbarrier) while the sources are evaluated, the grid-point constants by cp.async during the READ phase.  (As register loads they tied up scoreboard slots that the
-//    shared-memory loads of the stencil then had to wait on: 12 % of the issue stalls of the first version.)
-//  * there is no separate pass 1: the WRITE phase of stage s evaluates the terminal velocities, the ARG activation rate
-//    and the cloud-base candidate of the NEW state it has just formed, i.e. the aux fields stage s+1 needs
+//    variable for 2 cells instead of 4 and 6.  A tile is 16 columns x 128 levels: 256 threads x 128 registers (16
+//    level-pairs x 16 columns per round, 4 rounds per stage), two tiles per SM.
+//  * all HBM traffic of the stage loop is asynchronous and never passes through registers: u^n of the stage combine is one
+//    TMA box per WARP and round (cp.async.bulk.tensor.3d, 16 columns x 4 levels x NV variables, completion on the warp's
+//    own mbarrier), requested a round ahead; the new state of a step leaves through the same staging rows as one TMA STORE
+//    per warp and round (loads and stores both in the async proxy: no proxy fence on global memory); the grid-point constants
+//    come by cp.async during the READ phase.
+//  * the round barrier is split: a warp ARRIVES on an mbarrier after its stencil reads and WAITS just before its stores.
+//  * there is no separate pass 1: the WRITE phase of stage s evaluates the terminal velocities and the cloud-base search
+//    (ARG rate of the candidates) of the NEW state it has just formed, i.e. the aux fields stage s+1 needs
 //    (precompute_aux_precip!, precompute_aux_activation!; K1DModel/ode_utils.jl:30-47 evaluates them at the start of
 //    the next rhs! call from the same state).  The terminal velocities are two more planes of the shared-memory tile
-//    with their own round-boundary stash row.  A launch starts with a pseudo-stage that only does this evaluation.
+//    with their own round-boundary stash row; the cloud-base slot carries (level, rate), so the activation source needs
+//    no second ARG evaluation.  A launch starts with a pseudo-stage that only does this evaluation.
 //
-// Time-invariant values per grid point (p_sat,mixed(T), 1 / p_sat,liq(T), λ(T), T; G(T) in an array of its own) come from
-// arrays filled at upload (grid_consts_kernel).
+// Time-invariant values per grid point (p_sat,mixed(T), 1 / p_sat,liq(T), T; λ(T) is 1 above freezing and recomputed below;
+// G(T) in an array of its own) come from arrays filled at upload (grid_consts_kernel).
 #pragma once
 #include <cuda.h>  // CUtensorMap
 
@@ -36,7 +39,8 @@ namespace kid {
 constexpr int PAIR_LPR = 2 * PAIR_TJ;  // levels per round
 
 // shared memory of one tile: state + terminal-velocity planes (NZ levels + 2 stash rows each), ρ_dry, the staging buffers
-// of one round (u^n of the stage combine: bulk copies; grid-point constants: cp.async), cloud-base slots, one mbarrier
+// of one round (u^n of the stage combine / new state of a step: one TMA box per warp; grid-point constants: cp.async),
+// cloud-base slots, the round mbarrier and one mbarrier per warp
 template <int MOIST>
 inline size_t k1d_pair_smem_bytes() {
     using L = Lay<MOIST, KID_PRECIP_2M>;
