@@ -70,6 +70,14 @@ KID_F2_DEV F2 vexp(F2 a) { return vex2(a * 1.4426950408889634f); }
 KID_F2_DEV F2 vlog(F2 a) { return vlg2(a) * 0.6931471805599453f; }
 KID_F2_DEV F2 vpow(F2 a, float y) { return vex2(vlg2(a) * y); }
 KID_F2_DEV F2 vcbrt(F2 a) { return vex2(vlg2(a) * 0.333333343f); }
+// kid_physics.cuh::pow_small_int for two values (the exponent is uniform)
+KID_F2_DEV F2 vpow_small_int(F2 x, float y) {
+    if (y == 3.f) return x * x * x;
+    if (y == 4.f) { const F2 x2 = x * x; return x2 * x2; }
+    if (y == -5.f) { const F2 x2 = x * x; return vrcp(x2 * x2 * x); }
+    if (y == 2.f) return x * x;
+    return vpow(x, y);
+}
 KID_F2_DEV F2 vsqrt_fast(F2 a) { return F2{sqrt_approx1(a.x), sqrt_approx1(a.y)}; }
 // Mth<float>::sqrt_lim for two values: rsqrt + one Newton step in FMA form, sqrt_lim(0) = 0 exactly
 KID_F2_DEV F2 vsqrt_lim(F2 x) {

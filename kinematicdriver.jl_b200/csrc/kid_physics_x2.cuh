@@ -196,7 +196,7 @@ KID_DEV void precip_sources_2m_x2(const PRM& P, const DevSwitches& sw, const Poi
             const F2 x_liq = vmin(L_liq / N_liq, P.sb_x_star);
             const F2 tau = vmax(1.f - q_liq / (q_liq + vmax(q_rai, 0.f)), 0.f);
             const F2 tau_a = vpow(tau, P.sb_a);
-            const F2 phi_au = P.sb_A * tau_a * vpow(vmax(1.f - tau_a, 0.f), P.sb_b);
+            const F2 phi_au = P.sb_A * tau_a * vpow_small_int(vmax(1.f - tau_a, 0.f), P.sb_b);
             const F2 omt = 1.f - tau;
             const F2 dL = P.sb_acnv_pref * (L_liq * L_liq) * (x_liq * x_liq) * (1.f + phi_au / (omt * omt)) * (P.sb_rho0 * a.inv_rho);
             const F2 S1 = sel(m_au, tri_x2(dL * a.inv_rho, limit_x2(q_liq, inv_dt)), 0.f);
@@ -211,7 +211,7 @@ KID_DEV void precip_sources_2m_x2(const PRM& P, const DevSwitches& sw, const Poi
         const B2 m_r = has_rai && has_Nr;
         if (do_rai) {
             const F2 lam_x = lam_r * P.sb_c6pr;
-            const F2 sc_r = (-P.sb_krr * N_rai) * L_rai * sq_rho0 * vpow(1.f + P.sb_kappa_rr / lam_x, P.sb_d);
+            const F2 sc_r = (-P.sb_krr * N_rai) * L_rai * sq_rho0 * vpow_small_int(1.f + P.sb_kappa_rr / lam_x, P.sb_d);
             const F2 S1 = -sel(m_r, tri_x2(-sc_r, limit_x2(N_rai, inv_dt)), 0.f);
             const F2 Dr = P.sb_c6pr * vcbrt(x_r);
             const F2 dD = Dr - P.sb_Deq;
@@ -221,7 +221,7 @@ KID_DEV void precip_sources_2m_x2(const PRM& P, const DevSwitches& sw, const Poi
             // accretion
             const B2 m_ac = has_liq && has_rai && has_Nl;
             const F2 tau = vmax(1.f - q_liq / (q_liq + q_rai), 0.f);
-            const F2 phi_ac = vpow(tau / (tau + P.sb_tau0), P.sb_c);
+            const F2 phi_ac = vpow_small_int(tau / (tau + P.sb_tau0), P.sb_c);
             const F2 dL = P.sb_kcr * L_liq * L_rai * phi_ac * sq_rho0;
             const F2 dN = dL * N_liq / L_liq;   // dL / x_liq, x_liq = L_liq / N_liq  (= -dN_ac)
             const F2 A1 = sel(m_ac, tri_x2(dL * a.inv_rho, limit_x2(q_liq, inv_dt)), 0.f);
