@@ -161,6 +161,25 @@ def sample_errors(a, b, var_names) -> dict:
     return out
 
 
+def knife_edge_measures(a, b, names, tol_q=5e-3, tol_n=5e-2) -> dict:
+    """The number fields carry the reference formulation's knife-edge (find_cloud_base!: the sign of N_act - N_liq at the level
+    where N_liq has just reached N_act decides which level activates): a flip moves the activated number by one level in a
+    single column.  Two measures that do not hinge on it: how many columns exceed the tolerance, and the error of the
+    column-integrated aerosol + droplet number (conserved by activation in the closed system)."""
+    a64, b64 = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    over = {}
+    for i, v in enumerate(names):
+        tol = tol_n if v.startswith("N_") else tol_q
+        den = max(np.abs(b64[:, i]).max(), 1e-300)
+        over[v] = int((np.abs(a64[:, i] - b64[:, i]).max(axis=1) / den > tol).sum())
+    iN = [names.index(v) for v in ("N_liq", "N_rai", "N_aer") if v in names]
+    col_int = None
+    if iN:
+        sa, sb = a64[:, iN].sum(axis=(1, 2)), b64[:, iN].sum(axis=(1, 2))
+        col_int = float("%.3e" % np.max(np.abs(sa - sb) / np.maximum(np.abs(sb), 1e-300)))
+    return {"columns_over_tolerance": over, "tolerance": {"q": tol_q, "N": tol_n}, "column_integrated_number_rel_err": col_int}
+
+
 def cpu_arm_threads(lib) -> int:
     """All host cores, explicitly: torch.distributed.run exports OMP_NUM_THREADS=1 to its workers."""
     from oracle import oracle as O
@@ -230,24 +249,7 @@ def cpu_check_and_baseline(case_sample, Y_start, Y_gpu_end, t_start: float, nste
     per_step = (time.perf_counter() - t0) / nsteps
     Yo = o.get_state()
     parity = sample_errors(Y_gpu_end, Yo, case_sample.var_names)
-    # The number fields carry the reference formulation's knife-edge (find_cloud_base!: the sign of N_act - N_liq at the
-    # level where N_liq has just reached N_act decides which level activates): a flip moves the activated number by one
-    # level in a single column.  Two measures that do not hinge on it: how many sampled columns exceed the tolerance, and the
-    # error of the column-integrated aerosol + droplet number (conserved by activation in the closed system).
-    names = case_sample.var_names
-    a64, b64 = np.asarray(Y_gpu_end, dtype=np.float64), np.asarray(Yo, dtype=np.float64)
-    over = {}
-    for i, v in enumerate(names):
-        tol = 5e-2 if v.startswith("N_") else 5e-3
-        den = max(np.abs(b64[:, i]).max(), 1e-300)
-        over[v] = int((np.abs(a64[:, i] - b64[:, i]).max(axis=1) / den > tol).sum())
-    iN = [names.index(v) for v in ("N_liq", "N_rai", "N_aer") if v in names]
-    col_int = None
-    if iN:
-        sa, sb = a64[:, iN].sum(axis=(1, 2)), b64[:, iN].sum(axis=(1, 2))
-        col_int = float("%.3e" % np.max(np.abs(sa - sb) / np.maximum(np.abs(sb), 1e-300)))
-    parity = {"max_err_rel_field_max": parity, "columns_over_tolerance": over, "tolerance": {"q": 5e-3, "N": 5e-2},
-              "column_integrated_number_rel_err": col_int}
+    parity = {"max_err_rel_field_max": parity, **knife_edge_measures(Y_gpu_end, Yo, case_sample.var_names)}
     cpu = None
     if target_s > 0:
         n2 = int(max(8, min(4000, target_s / max(per_step, 1e-6))))
@@ -258,6 +260,22 @@ def cpu_check_and_baseline(case_sample, Y_start, Y_gpu_end, t_start: float, nste
                "sample": f"first {ncpu} columns x {NZ} levels x {n2} SSPRK33 steps continuing the same developed ensemble state "
                          f"(t={t_start + nsteps:g}s); restated CPU path (oracle/, {build}), OpenMP over columns on {threads} threads; not Julia"}
     return parity, cpu
+
+
+K2D_PARITY_STEPS = 3  # the K2D oracle is single-threaded: about a second per step of the 4096 x 256 domain
+
+
+def k2d_parity_sample(case, Y_start, Y_gpu_end, t_start: float, nsteps: int) -> dict:
+    """The whole K2D domain stepped `nsteps` steps on the CPU oracle from the state the GPU started from; errors per variable
+    relative to the field maximum (the metric of tests/parity.py)."""
+    from kid_b200 import model as M
+    from oracle import oracle as O
+    o = M.make_handle(case, O.OracleHandle)
+    o.set_state(np.ascontiguousarray(Y_start))
+    o.step(t_start, nsteps)
+    Yo = o.get_state()
+    return {"columns": int(case.cfg.nc), "levels": int(case.cfg.nz), "steps": nsteps, "vs": "CPU oracle from the same start state",
+            "max_err_rel_field_max": sample_errors(Y_gpu_end, Yo, case.var_names), **knife_edge_measures(Y_gpu_end, Yo, case.var_names)}
 
 
 def run_k2d(args, rank, world, local, dist):
@@ -288,12 +306,27 @@ def run_k2d(args, rank, world, local, dist):
     if dist is not None:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     finite = bool(np.isfinite(h.get_state()).all())
+    launches_per_step = (h.launch_count - l0) / args.k2d_steps
+    parity = None
+    if world == 1 and args.parity:
+        # parity at BASELINE size: the whole 4096 x 256 domain stepped K2D_PARITY_STEPS steps on the CPU oracle from the state the
+        # timed window ended in.  (Not later: with dt = 1 s this synthetic domain — u ~ w1 W/H = 32 m/s over 13 m node spacing —
+        # violates the horizontal CFL limit and goes non-finite by t = 600 s in the oracle and on the GPU alike.)
+        try:
+            t_dev = 20.0 + args.k2d_steps
+            Y1 = h.get_state()
+            h.set_state(Y1)                      # both sides restart the "previous call's aux" of K2D activation from Y1
+            h.step(t_dev, K2D_PARITY_STEPS)
+            parity = k2d_parity_sample(cs, Y1, h.get_state(), t_dev, K2D_PARITY_STEPS)
+            parity["model_time_s"] = t_dev
+        except Exception as ex:
+            parity = {"error": f"{type(ex).__name__}: {ex}"[:200]}
     n_nodes = 4096
     return {"workload": "K2D 4096 GLL node columns x 256 levels, NonEq+Precipitation2M, Float32 (BASELINE configs[4])",
             "value": n_nodes * 256 * args.k2d_steps / (float(ms.item()) * 1e-3), "unit": METRIC, "n_gpus": world,
             "ms_per_step": float(ms.item()) / args.k2d_steps, "steps": args.k2d_steps, "scaling": "strong",
             "exchange": "in-library NCCL send/recv of the GLL edge columns, one group per SSPRK33 stage" if world > 1 else None,
-            "launches_per_step": (h.launch_count - l0) / args.k2d_steps, "state_finite": finite}
+            "launches_per_step": launches_per_step, "state_finite": finite, "parity_sample": parity}
 
 
 def run_ours(args):
