@@ -129,3 +129,23 @@ def test_round_robin_block_shards_cover_the_ensemble_and_take_columns_slices_eve
     sd = M.take_columns(dev, idx)
     assert np.array_equal(sd.device_ic["p0"], dev.device_ic["p0"][idx])
     assert np.array_equal(sd.meta["column_perm"], np.asarray(dev.meta["column_perm"])[idx])
+
+
+def test_bench_parity_measures():
+    """bench.py's parity helpers: field-maximum errors, columns over tolerance, column-integrated number."""
+    import importlib.util
+    from pathlib import Path
+    spec = importlib.util.spec_from_file_location("bench", Path(__file__).resolve().parents[1] / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    names = ("ρq_tot", "ρq_liq", "N_liq", "N_rai", "N_aer")
+    rng = np.random.default_rng(0)
+    b = rng.random((10, 5, 8)) + 0.5
+    a = b.copy()
+    a[3, 2, 4] += 0.5   # one column: activation moved by a level (N_liq up, N_aer down: the sum is conserved)
+    a[3, 4, 4] -= 0.5
+    m = bench.knife_edge_measures(a, b, names)
+    assert m["columns_over_tolerance"] == {"ρq_tot": 0, "ρq_liq": 0, "N_liq": 1, "N_rai": 0, "N_aer": 1}
+    assert m["column_integrated_number_rel_err"] < 1e-12
+    e = bench.sample_errors(a, b, names)
+    assert e["ρq_tot"] == 0.0 and 0.3 < e["N_liq"] < 0.4
