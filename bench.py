@@ -143,6 +143,7 @@ def workload_config(args, world: int) -> dict:
             "member_order": ("hash (SURVEY 8d counter hash)" if args.order == "hash"
                              else "sorted into nested quantile bins (p0, then w1, then Nd): model.nested_bin_order"),
             "initial_condition": "every member its own p0 (SURVEY 8d), hydrostatic profile + initial state per column",
+            "l2": "no flush between timed steps: the state per GPU (%.2f GiB) is far larger than the 126 MB L2" % (total / world * NZ * 8 * 4 / 2**30),
             "parallelism": f"columns sharded x{world}: blocks of {SHARD_BLOCK} columns dealt round-robin, no collective"}
 
 
